@@ -1,0 +1,487 @@
+// elementwise.cu — the HBM-bound kernels of the DGL step: input layout conversion,
+// BatchNorm (training mode) statistics / apply / backward, ReLU and residual add fused into
+// the BN passes, MaxPool 3x3/s2, global average pooling.  All activations NHWC bf16, 16-byte
+// vector accesses, fp32 math, deterministic fixed-order reductions (per-block partials reduced
+// by a finalize kernel; no float atomics — reference utils/utils.py:12 asks for determinism).
+#include "common.cuh"
+
+namespace gdl {
+
+// ------------------------------------------------------------------------------------------
+// layout: f32 [B,C,T,H,W] -> bf16 [B*T,H,W,8]      (reference models/backbone.py:162-164)
+// ------------------------------------------------------------------------------------------
+__global__ void layout_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int C,
+                              int T, int H, int W) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t total = (int64_t)B * T * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t bt = i / HW;
+    int64_t hw = i - bt * HW;
+    int b = int(bt / T), t = int(bt - (int64_t)b * T);
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      f[c] = c < C ? src[(((int64_t)b * C + c) * T + t) * HW + hw] : 0.f;
+    *reinterpret_cast<uint4*>(dst + i * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm statistics
+// ------------------------------------------------------------------------------------------
+constexpr int kBnThreads = 256;
+constexpr int kBnMaxBlocks = 4 * kNumSMs;
+
+static int bn_blocks(int64_t P, int C) {
+  int lanes = kBnThreads / (C / 8);
+  int64_t want = ceil_div64(P, (int64_t)lanes * 8);
+  if (want < 1) want = 1;
+  return int(want < kBnMaxBlocks ? want : kBnMaxBlocks);
+}
+
+// Reduce the 8-channel accumulators of all pixel lanes of a block; thread layout is
+// tid = lane * (C/8) + cg.  Result (2 x C floats) is written to partial[block].
+template <int NACC>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NACC][8], int C,
+                                                     float* __restrict__ partial_blk) {
+  __shared__ float red[kBnThreads * 8];
+  const int groups = C / 8;
+  const int lanes = kBnThreads / groups;
+  const int cg = threadIdx.x % groups;
+  const int lane = threadIdx.x / groups;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) red[(lane * groups + cg) * 8 + c] = acc[a][c];
+    __syncthreads();
+    // fixed-order tree over lanes
+    for (int stride = lanes / 2; stride > 0; stride >>= 1) {
+      if (lane < stride) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          red[(lane * groups + cg) * 8 + c] += red[((lane + stride) * groups + cg) * 8 + c];
+      }
+      __syncthreads();
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) partial_blk[a * C + cg * 8 + c] = red[cg * 8 + c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const bf16* __restrict__ x, int64_t P,
+                                                              int C, float* __restrict__ partial) {
+  const int groups = C / 8;
+  const int lanes = kBnThreads / groups;
+  const int cg = threadIdx.x % groups;
+  const int lane = threadIdx.x / groups;
+  float acc[2][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[0][c] = acc[1][c] = 0.f;
+  for (int64_t pix = (int64_t)blockIdx.x * lanes + lane; pix < P; pix += (int64_t)gridDim.x * lanes) {
+    float f[8];
+    unpack8(ld_stream16(x + pix * C + cg * 8), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc[0][c] += f[c];
+      acc[1][c] = fmaf(f[c], f[c], acc[1][c]);
+    }
+  }
+  block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
+}
+
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t P, int C,
+                                         const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, float momentum,
+                                         float* running_mean, float* running_var, float* mean_out,
+                                         float* invstd_out, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s1 += (double)partial[(size_t)b * 2 * C + c];
+    s2 += (double)partial[(size_t)b * 2 * C + C + c];
+  }
+  double mean = s1 / (double)P;
+  double var = s2 / (double)P - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  float m = (float)mean;
+  mean_out[c] = m;
+  invstd_out[c] = invstd;
+  float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - m * sc;
+  if (running_mean != nullptr) {
+    double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// y = [relu](x*scale + shift [+ res])
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x,
+                                                       const bf16* __restrict__ res,
+                                                       bf16* __restrict__ y, int64_t nvec, int C,
+                                                       const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, int relu) {
+  __shared__ float s_scale[512], s_shift[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_scale[c] = scale[c];
+    s_shift[c] = shift[c];
+  }
+  __syncthreads();
+  const int groups = C / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = int(i % groups);
+    float f[8];
+    unpack8(ld_stream16(x + i * 8), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = fmaf(f[c], s_scale[cg * 8 + c], s_shift[cg * 8 + c]);
+    if (res != nullptr) {
+      float r[8];
+      unpack8(ld_stream16(res + i * 8), r);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] += r[c];
+    }
+    if (relu) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = fmaxf(f[c], 0.f);
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8(f);
+  }
+}
+
+// backward pass 1: dz = dy * (y > 0); partial sums of dz and dz * xhat
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
+    const bf16* dy, const bf16* __restrict__ y, const bf16* __restrict__ x, bf16* dz, int64_t P, int C, const float* __restrict__ mean,
+    const float* __restrict__ invstd, float* __restrict__ partial, int relu) {
+  const int groups = C / 8;
+  const int lanes = kBnThreads / groups;
+  const int cg = threadIdx.x % groups;
+  const int lane = threadIdx.x / groups;
+  float mu[8], is[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    mu[c] = mean[cg * 8 + c];
+    is[c] = invstd[cg * 8 + c];
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[0][c] = acc[1][c] = 0.f;
+  for (int64_t pix = (int64_t)blockIdx.x * lanes + lane; pix < P; pix += (int64_t)gridDim.x * lanes) {
+    const int64_t off = pix * C + cg * 8;
+    float g[8], xv[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + off), g);  // dz may alias dy: no .nc path
+    unpack8(ld_stream16(x + off), xv);
+    if (relu) {
+      float yv[8];
+      unpack8(ld_stream16(y + off), yv);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] = yv[c] > 0.f ? g[c] : 0.f;
+      *reinterpret_cast<uint4*>(dz + off) = pack8(g);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc[0][c] += g[c];
+      acc[1][c] = fmaf(g[c], (xv[c] - mu[c]) * is[c], acc[1][c]);
+    }
+  }
+  block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s1 += (double)partial[(size_t)b * 2 * C + c];
+    s2 += (double)partial[(size_t)b * 2 * C + C + c];
+  }
+  dbeta[c] = (float)s1;
+  dgamma[c] = (float)s2;
+}
+
+// backward pass 2: dx = gamma*invstd*(dz - dbeta/P - xhat*dgamma/P)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    const bf16* __restrict__ dz, const bf16* __restrict__ x, bf16* __restrict__ dx, int64_t nvec,
+    int C, float invP, const float* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ dgamma,
+    const float* __restrict__ dbeta) {
+  // dx = a*dz + b*x + c  with  a = gamma*invstd,  b = -a*invstd*dgamma/P,
+  //                            c = -a*dbeta/P - b*mean
+  __shared__ float s_a[512], s_b[512], s_c[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = gamma[c] * invstd[c];
+    float b = -a * invstd[c] * dgamma[c] * invP;
+    s_a[c] = a;
+    s_b[c] = b;
+    s_c[c] = -a * dbeta[c] * invP - b * mean[c];
+  }
+  __syncthreads();
+  const int groups = C / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = int(i % groups);
+    float g[8], xv[8];
+    unpack8(ld_stream16(dz + i * 8), g);
+    unpack8(ld_stream16(x + i * 8), xv);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      g[c] = fmaf(s_a[cg * 8 + c], g[c], fmaf(s_b[cg * 8 + c], xv[c], s_c[cg * 8 + c]));
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool2d(kernel 3, stride 2, pad 1)       (reference models/backbone.py:106)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const bf16* __restrict__ x,
+                                                          bf16* __restrict__ y,
+                                                          uint8_t* __restrict__ amax, int N, int H,
+                                                          int W, int C, int Ho, int Wo) {
+  const int groups = C / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = int(i % groups);
+    int64_t pix = i / groups;
+    int wo = int(pix % Wo);
+    int64_t t = pix / Wo;
+    int ho = int(t % Ho);
+    int n = int(t / Ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      best[c] = -INFINITY;
+      bi[c] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int h = ho * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int w = wo * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + (((int64_t)n * H + h) * W + w) * C + cg * 8), f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (f[c] > best[c]) {  // strict: the first maximum in scan order wins (ATen rule)
+            best[c] = f[c];
+            bi[c] = r * 3 + s;
+          }
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(y + pix * C + cg * 8) = pack8(best);
+    uint2 packed;
+    packed.x = uint32_t(bi[0]) | (uint32_t(bi[1]) << 8) | (uint32_t(bi[2]) << 16) | (uint32_t(bi[3]) << 24);
+    packed.y = uint32_t(bi[4]) | (uint32_t(bi[5]) << 8) | (uint32_t(bi[6]) << 16) | (uint32_t(bi[7]) << 24);
+    *reinterpret_cast<uint2*>(amax + pix * C + cg * 8) = packed;
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict__ dy,
+                                                          const uint8_t* __restrict__ amax,
+                                                          bf16* __restrict__ dx, int N, int H, int W,
+                                                          int C, int Ho, int Wo) {
+  const int groups = C / 8;
+  const int64_t total = (int64_t)N * H * W * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = int(i % groups);
+    int64_t pix = i / groups;
+    int w = int(pix % W);
+    int64_t t = pix / W;
+    int h = int(t % H);
+    int n = int(t / H);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    int ho_lo = h >> 1, ho_hi = (h + 1) >> 1;  // windows ho with 2*ho-1 <= h <= 2*ho+1
+    int wo_lo = w >> 1, wo_hi = (w + 1) >> 1;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      if (ho >= Ho) continue;
+      int r = h - (ho * 2 - 1);
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        if (wo >= Wo) continue;
+        int s = w - (wo * 2 - 1);
+        int idx = r * 3 + s;
+        int64_t o = (((int64_t)n * Ho + ho) * Wo + wo) * C + cg * 8;
+        uint2 am = *reinterpret_cast<const uint2*>(amax + o);
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + o), g);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t word = c < 4 ? am.x : am.y;
+          int a = (word >> ((c & 3) * 8)) & 0xff;
+          if (a == idx) acc[c] += g[c];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + pix * C + cg * 8) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// global average pool   (reference models/basic_model.py:73-82)
+// ------------------------------------------------------------------------------------------
+__global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ out, int B, int G,
+                               int C) {
+  const int groups = C / 8;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * groups) return;
+  int cg = int(i % groups);
+  int b = int(i / groups);
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  const bf16* p = x + (int64_t)b * G * C + cg * 8;
+  for (int g = 0; g < G; ++g) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(p + (int64_t)g * C), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] += f[c];
+  }
+  const float inv = 1.f / (float)G;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) out[(int64_t)b * C + cg * 8 + c] = acc[c] * inv;
+}
+
+__global__ void gap_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ dx, int B, int G,
+                               int C) {
+  const int groups = C / 8;
+  const int64_t total = (int64_t)B * G * groups;
+  const float inv = 1.f / (float)G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = int(i % groups);
+    int b = int(i / ((int64_t)G * groups));
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = dout[(int64_t)b * C + cg * 8 + c] * inv;
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(f);
+  }
+}
+
+static unsigned ew_grid(int64_t work_items, int threads) {
+  int64_t blocks = ceil_div64(work_items, threads);
+  int64_t cap = (int64_t)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+static bool chan_ok(int C) { return C >= 64 && C <= 512 && (C & (C - 1)) == 0; }
+
+}  // namespace gdl
+
+using namespace gdl;
+
+extern "C" int gdl_layout_ncthw_to_nhwc8(const float* src, void* dst, int B, int C, int T, int H,
+                                         int W, gdl_stream_t s) {
+  GDL_REQUIRE(src && dst, "gdl_layout_ncthw_to_nhwc8: null pointer");
+  GDL_REQUIRE(B > 0 && C > 0 && C <= 8 && T > 0 && H > 0 && W > 0, "gdl_layout_ncthw_to_nhwc8: bad shape");
+  int64_t total = (int64_t)B * T * H * W;
+  layout_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(src, (bf16*)dst, B, C, T, H, W);
+  GDL_CHECK_LAUNCH("layout_kernel");
+  return GDL_OK;
+}
+
+extern "C" int64_t gdl_bn_partial_floats(int64_t P, int C) {
+  (void)P;
+  return (int64_t)kBnMaxBlocks * 2 * C;
+}
+
+extern "C" int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, const float* gamma,
+                            const float* beta, float eps, float momentum, float* running_mean,
+                            float* running_var, float* mean, float* invstd, float* scale,
+                            float* shift, gdl_stream_t s) {
+  GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_stats: bad shape");
+  GDL_REQUIRE(x && partial && gamma && beta && mean && invstd && scale && shift, "gdl_bn_stats: null pointer");
+  int nblk = bn_blocks(P, C);
+  bn_stats_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)x, P, C, partial);
+  GDL_CHECK_LAUNCH("bn_stats_kernel");
+  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(
+      partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
+  GDL_CHECK_LAUNCH("bn_stats_finalize_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_bn_apply(const void* x, const void* res, void* y, int64_t P, int C,
+                            const float* scale, const float* shift, int relu, gdl_stream_t s) {
+  GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_apply: bad shape");
+  GDL_REQUIRE(x && y && scale && shift, "gdl_bn_apply: null pointer");
+  int64_t nvec = P * C / 8;
+  bn_apply_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)x, (const bf16*)res,
+                                                                  (bf16*)y, nvec, C, scale, shift, relu);
+  GDL_CHECK_LAUNCH("bn_apply_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz, void* dx,
+                          int64_t P, int C, const float* gamma, const float* mean,
+                          const float* invstd, float* partial, float* dgamma, float* dbeta,
+                          int relu, gdl_stream_t s) {
+  GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_bwd: bad shape");
+  GDL_REQUIRE(dy && x && dx && gamma && mean && invstd && partial && dgamma && dbeta, "gdl_bn_bwd: null pointer");
+  GDL_REQUIRE(!relu || (y && dz), "gdl_bn_bwd: relu needs y and dz");
+  int nblk = bn_blocks(P, C);
+  bn_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
+      (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, mean, invstd, partial, relu);
+  GDL_CHECK_LAUNCH("bn_bwd_reduce_kernel");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
+  GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  int64_t nvec = P * C / 8;
+  const bf16* dzp = relu ? (const bf16*)dz : (const bf16*)dy;
+  bn_bwd_apply_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>(
+      dzp, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, dgamma, dbeta);
+  GDL_CHECK_LAUNCH("bn_bwd_apply_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C,
+                               int Ho, int Wo, gdl_stream_t s) {
+  GDL_REQUIRE(x && y && argmax, "gdl_maxpool_fwd: null pointer");
+  GDL_REQUIRE(C % 8 == 0 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_maxpool_fwd: bad shape");
+  int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)x, (bf16*)y, argmax,
+                                                                      N, H, W, C, Ho, Wo);
+  GDL_CHECK_LAUNCH("maxpool_fwd_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int N, int H, int W,
+                               int C, int Ho, int Wo, gdl_stream_t s) {
+  GDL_REQUIRE(dy && dx && argmax, "gdl_maxpool_bwd: null pointer");
+  GDL_REQUIRE(C % 8 == 0 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_maxpool_bwd: bad shape");
+  int64_t total = (int64_t)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)dy, argmax, (bf16*)dx,
+                                                                      N, H, W, C, Ho, Wo);
+  GDL_CHECK_LAUNCH("maxpool_bwd_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_gap_fwd(const void* x, float* out, int B, int G, int C, gdl_stream_t s) {
+  GDL_REQUIRE(x && out && B > 0 && G > 0 && C % 8 == 0, "gdl_gap_fwd: bad arguments");
+  int64_t total = (int64_t)B * (C / 8);
+  gap_fwd_kernel<<<(unsigned)ceil_div64(total, 128), 128, 0, (cudaStream_t)s>>>((const bf16*)x, out, B, G, C);
+  GDL_CHECK_LAUNCH("gap_fwd_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_gap_bwd(const float* dout, void* dx, int B, int G, int C, gdl_stream_t s) {
+  GDL_REQUIRE(dout && dx && B > 0 && G > 0 && C % 8 == 0, "gdl_gap_bwd: bad arguments");
+  int64_t total = (int64_t)B * G * (C / 8);
+  gap_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(dout, (bf16*)dx, B, G, C);
+  GDL_CHECK_LAUNCH("gap_bwd_kernel");
+  return GDL_OK;
+}

@@ -1,0 +1,88 @@
+"""ctypes binding of libgdl_b200.so (the C-ABI declared in include/gdl_b200.h).
+
+The product path has NO fallback: if the shared library is missing, or a call returns a
+negative status, a GdlError is raised.  Nothing here imports the oracle.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgdl_b200.so")
+
+GDL_OK, GDL_EINVAL, GDL_EARCH, GDL_ECUDA, GDL_ENOMEM = 0, -1, -2, -3, -4
+
+
+class GdlError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    """Mirror of gdl_conv_desc."""
+    _fields_ = [(n, C.c_int32) for n in
+                ("N", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "R", "S", "stride", "pad")]
+
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_int64
+_f = C.c_float
+_dp = C.POINTER(ConvDesc)
+
+# name -> (restype, argtypes); every symbol of include/gdl_b200.h
+SIGNATURES = {
+    "gdl_version": (_i, []),
+    "gdl_last_error_string": (C.c_char_p, []),
+    "gdl_init": (_i, [_i]),
+    "gdl_conv_packed_k": (_l, [_dp]),
+    "gdl_conv_wgrad_workspace_bytes": (_l, [_dp]),
+    "gdl_conv_pack_weights": (_i, [_dp, _i, _p, _p, _p, _p]),
+    "gdl_conv_fwd": (_i, [_dp, _p, _p, _p, _p]),
+    "gdl_conv_dgrad": (_i, [_dp, _p, _p, _p, _p, _i, _p]),
+    "gdl_conv_wgrad": (_i, [_dp, _i, _p, _p, _p, _p, _l, _p]),
+    "gdl_layout_ncthw_to_nhwc8": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "gdl_bn_partial_floats": (_l, [_l, _i]),
+    "gdl_bn_stats": (_i, [_p, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "gdl_bn_apply": (_i, [_p, _p, _p, _l, _i, _p, _p, _i, _p]),
+    "gdl_bn_bwd": (_i, [_p, _p, _p, _p, _p, _l, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "gdl_maxpool_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "gdl_maxpool_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "gdl_gap_fwd": (_i, [_p, _p, _i, _i, _i, _p]),
+    "gdl_gap_bwd": (_i, [_p, _p, _i, _i, _i, _p]),
+    "gdl_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "gdl_linear_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "gdl_head_scratch_floats": (_l, [_i, _i]),
+    "gdl_dgl_head_linear": (_i, [_i, _p, _p, _p, _p, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p,
+                                 _p, _i, _p, _p, _p, _i, _i, _i, _p]),
+    "gdl_softmax_ce": (_i, [_p, _p, _f, _f, _p, _p, _p, _i, _i, _p]),
+    "gdl_gated_fwd": (_i, [_p, _p, _p, _p, _p, _l, _p]),
+    "gdl_gated_bwd": (_i, [_p, _p, _p, _p, _p, _p, _l, _p]),
+    "gdl_optim_scratch_floats": (_l, [_l, _i]),
+    "gdl_grad_stats": (_i, [_p, _l, _p, _p, _p, _i, _f, _p, _p, _p]),
+    "gdl_sgd_momentum": (_i, [_p, _p, _p, _l, _f, _f, _f, _i, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the extension once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GdlError(
+            "libgdl_b200.so not found at %s — build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C iccv2025-gdl_b200/csrc`. There is no CPU/PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != GDL_OK:
+        msg = load().gdl_last_error_string()
+        raise GdlError("%s failed with status %d: %s" % (what, status, (msg or b"").decode()))

@@ -1,0 +1,168 @@
+"""Thin tensor-level wrappers over the C-ABI: borrow device pointers from torch tensors, pass
+torch's current CUDA stream, check the status.  PyTorch is plumbing only (memory, streams);
+every computation below runs in libgdl_b200.so.  No fallbacks.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+_initialised = set()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "gdl ops need contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def init(device=None):
+    lib = _lib.load()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev not in _initialised:
+        check(lib.gdl_init(dev), "gdl_init")
+        _initialised.add(dev)
+    return lib
+
+
+def conv_desc(N, Hi, Wi, Ci, Co, R, S, stride, pad):
+    Ho = (Hi + 2 * pad - R) // stride + 1
+    Wo = (Wi + 2 * pad - S) // stride + 1
+    return ConvDesc(N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad)
+
+
+def conv_packed_k(d):
+    return int(_lib.load().gdl_conv_packed_k(C.byref(d)))
+
+
+def conv_wgrad_workspace_bytes(d):
+    return int(_lib.load().gdl_conv_wgrad_workspace_bytes(C.byref(d)))
+
+
+def conv_pack_weights(d, ci_real, w_oihw, w_packed, w_packed_T=None):
+    check(_lib.load().gdl_conv_pack_weights(C.byref(d), ci_real, _ptr(w_oihw), _ptr(w_packed),
+                                            _ptr(w_packed_T), _stream()), "gdl_conv_pack_weights")
+
+
+def conv_fwd(d, x, w_packed, y):
+    check(_lib.load().gdl_conv_fwd(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(y), _stream()),
+          "gdl_conv_fwd")
+
+
+def conv_dgrad(d, dy, w_packed_T, dx, add_src=None, add_mode=0):
+    check(_lib.load().gdl_conv_dgrad(C.byref(d), _ptr(dy), _ptr(w_packed_T), _ptr(dx),
+                                     _ptr(add_src), add_mode, _stream()), "gdl_conv_dgrad")
+
+
+def conv_wgrad(d, ci_real, x, dy, dw_oihw, workspace):
+    check(_lib.load().gdl_conv_wgrad(C.byref(d), ci_real, _ptr(x), _ptr(dy), _ptr(dw_oihw),
+                                     _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                     _stream()), "gdl_conv_wgrad")
+
+
+def layout_ncthw_to_nhwc8(src, dst, B, Cc, T, H, W):
+    check(_lib.load().gdl_layout_ncthw_to_nhwc8(_ptr(src), _ptr(dst), B, Cc, T, H, W, _stream()),
+          "gdl_layout_ncthw_to_nhwc8")
+
+
+def bn_partial_floats(P, Cc):
+    return int(_lib.load().gdl_bn_partial_floats(P, Cc))
+
+
+def bn_stats(x, P, Cc, partial, gamma, beta, eps, momentum, running_mean, running_var, mean,
+             invstd, scale, shift):
+    check(_lib.load().gdl_bn_stats(_ptr(x), P, Cc, _ptr(partial), _ptr(gamma), _ptr(beta), eps,
+                                   momentum, _ptr(running_mean), _ptr(running_var), _ptr(mean),
+                                   _ptr(invstd), _ptr(scale), _ptr(shift), _stream()), "gdl_bn_stats")
+
+
+def bn_apply(x, res, y, P, Cc, scale, shift, relu):
+    check(_lib.load().gdl_bn_apply(_ptr(x), _ptr(res), _ptr(y), P, Cc, _ptr(scale), _ptr(shift),
+                                   int(relu), _stream()), "gdl_bn_apply")
+
+
+def bn_bwd(dy, y, x, dz, dx, P, Cc, gamma, mean, invstd, partial, dgamma, dbeta, relu):
+    check(_lib.load().gdl_bn_bwd(_ptr(dy), _ptr(y), _ptr(x), _ptr(dz), _ptr(dx), P, Cc, _ptr(gamma),
+                                 _ptr(mean), _ptr(invstd), _ptr(partial), _ptr(dgamma), _ptr(dbeta),
+                                 int(relu), _stream()), "gdl_bn_bwd")
+
+
+def maxpool_fwd(x, y, argmax, N, H, W, Cc, Ho, Wo):
+    check(_lib.load().gdl_maxpool_fwd(_ptr(x), _ptr(y), _ptr(argmax), N, H, W, Cc, Ho, Wo, _stream()),
+          "gdl_maxpool_fwd")
+
+
+def maxpool_bwd(dy, argmax, dx, N, H, W, Cc, Ho, Wo):
+    check(_lib.load().gdl_maxpool_bwd(_ptr(dy), _ptr(argmax), _ptr(dx), N, H, W, Cc, Ho, Wo, _stream()),
+          "gdl_maxpool_bwd")
+
+
+def gap_fwd(x, out, B, G, Cc):
+    check(_lib.load().gdl_gap_fwd(_ptr(x), _ptr(out), B, G, Cc, _stream()), "gdl_gap_fwd")
+
+
+def gap_bwd(dout, dx, B, G, Cc):
+    check(_lib.load().gdl_gap_bwd(_ptr(dout), _ptr(dx), B, G, Cc, _stream()), "gdl_gap_bwd")
+
+
+def linear_fwd(x, W, b, y, B, In, Out):
+    check(_lib.load().gdl_linear_fwd(_ptr(x), _ptr(W), _ptr(b), _ptr(y), B, In, Out, _stream()),
+          "gdl_linear_fwd")
+
+
+def linear_bwd(dy, x, W, dx, dW, db, B, In, Out, accumulate=False):
+    check(_lib.load().gdl_linear_bwd(_ptr(dy), _ptr(x), _ptr(W), _ptr(dx), _ptr(dW), _ptr(db), B, In,
+                                     Out, int(accumulate), _stream()), "gdl_linear_bwd")
+
+
+def head_scratch_floats(B, n):
+    return int(_lib.load().gdl_head_scratch_floats(B, n))
+
+
+def dgl_head_linear(kind, a, v, Wx_ptr, Wy_ptr, ldw, bx, by, labels, alpha, inv_batch, logits, losses,
+                    da, dv, dWx_ptr, dWy_ptr, lddw, dbx, dby, scratch, B, D, n):
+    """Wx_ptr/Wy_ptr/dWx_ptr/dWy_ptr are raw integer device addresses (they may point into the
+    middle of a tensor: concat's Wy = fc_out.weight + D)."""
+    check(_lib.load().gdl_dgl_head_linear(kind, _ptr(a), _ptr(v), C.c_void_p(Wx_ptr), C.c_void_p(Wy_ptr),
+                                          ldw, _ptr(bx), _ptr(by), _ptr(labels), alpha, inv_batch,
+                                          _ptr(logits), _ptr(losses), _ptr(da), _ptr(dv),
+                                          C.c_void_p(dWx_ptr), C.c_void_p(dWy_ptr), lddw, _ptr(dbx),
+                                          _ptr(dby), _ptr(scratch), B, D, n, _stream()),
+          "gdl_dgl_head_linear")
+
+
+def softmax_ce(logits, labels, loss_scale, grad_scale, loss_out, dlogits, scratch, B, n):
+    check(_lib.load().gdl_softmax_ce(_ptr(logits), _ptr(labels), loss_scale, grad_scale, _ptr(loss_out),
+                                     _ptr(dlogits), _ptr(scratch), B, n, _stream()), "gdl_softmax_ce")
+
+
+def gated_fwd(hx, hy, m_out, m_x, m_y):
+    check(_lib.load().gdl_gated_fwd(_ptr(hx), _ptr(hy), _ptr(m_out), _ptr(m_x), _ptr(m_y), hx.numel(),
+                                    _stream()), "gdl_gated_fwd")
+
+
+def gated_bwd(hx, hy, dm_x, dm_y, dhx, dhy):
+    check(_lib.load().gdl_gated_bwd(_ptr(hx), _ptr(hy), _ptr(dm_x), _ptr(dm_y), _ptr(dhx), _ptr(dhy),
+                                    hx.numel(), _stream()), "gdl_gated_bwd")
+
+
+def optim_scratch_floats(numel, nseg):
+    return int(_lib.load().gdl_optim_scratch_floats(numel, nseg))
+
+
+def grad_stats(grad, numel, seg_end, seg_group, seg_inv_numel, nseg, max_norm, scratch, stats):
+    check(_lib.load().gdl_grad_stats(_ptr(grad), numel, _ptr(seg_end), _ptr(seg_group),
+                                     _ptr(seg_inv_numel), nseg, max_norm, _ptr(scratch), _ptr(stats),
+                                     _stream()), "gdl_grad_stats")
+
+
+def sgd_momentum(param, grad, buf, numel, lr, mu, wd, first_step, stats):
+    check(_lib.load().gdl_sgd_momentum(_ptr(param), _ptr(grad), _ptr(buf), numel, lr, mu, wd,
+                                       int(first_step), _ptr(stats), _stream()), "gdl_sgd_momentum")

@@ -1,0 +1,170 @@
+/*
+ * gdl_b200.h — C-ABI of the B200-native DGL training-step kernels.
+ *
+ * Drop-in boundary for ONE hot path of shicaiwei123/ICCV2025-GDL: the Disentangled
+ * Gradient Learning step (reference main_dgl.py:69-165).  The reference has no FFI of
+ * its own (it is pure Python calling torch/ATen); each entry point below therefore cites
+ * the reference call site (file:line under the reference tree) whose ATen op it replaces.
+ * The host side stays PyTorch: callers pass raw device pointers borrowed from torch
+ * tensors plus a cudaStream_t.  Conventions:
+ *   - every function returns GDL_OK (0) or a negative gdl_status; no exceptions,
+ *     no hidden allocation, no hidden synchronisation, asynchronous w.r.t. the host;
+ *   - all kernels are sm_100a only (tcgen05/TMEM for the convolutions); there is no
+ *     CPU, cuDNN, cuBLAS or Triton fallback;
+ *   - activations are NHWC bf16; parameters/gradients/optimizer state are fp32;
+ *     reductions are deterministic (fixed-order partials, no float atomics).
+ */
+#ifndef GDL_B200_H_
+#define GDL_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gdl_stream_t; /* a cudaStream_t */
+
+typedef enum {
+  GDL_OK = 0,
+  GDL_EINVAL = -1, /* bad shape / alignment / null pointer */
+  GDL_EARCH = -2,  /* device is not sm_100 */
+  GDL_ECUDA = -3,  /* CUDA runtime error; see gdl_last_error_string() */
+  GDL_ENOMEM = -4  /* caller-provided workspace too small */
+} gdl_status;
+
+/* ---- library / context -------------------------------------------------------------- */
+int gdl_version(void);
+const char* gdl_last_error_string(void);
+/* Checks the device is sm_100 and sets kernel attributes (max dynamic smem). */
+int gdl_init(int device);
+
+/* ---- convolution (reference models/backbone.py:20-28,97-100 nn.Conv2d, bias=False) --- */
+typedef struct {
+  int32_t N;          /* images (B for audio, B*T for visual)                         */
+  int32_t Hi, Wi;     /* input spatial size                                           */
+  int32_t Ci;         /* input channels AS STORED: multiple of 64, or 8 (padded stem) */
+  int32_t Ho, Wo;     /* output spatial size                                          */
+  int32_t Co;         /* output channels, multiple of 64                              */
+  int32_t R, S;       /* filter size                                                  */
+  int32_t stride, pad;
+} gdl_conv_desc;
+
+/* Length (elements) of one packed weight row: R*S*Ci rounded up to 64. */
+int64_t gdl_conv_packed_k(const gdl_conv_desc* d);
+/* Bytes of scratch gdl_conv_wgrad needs for its split-K partials. */
+int64_t gdl_conv_wgrad_workspace_bytes(const gdl_conv_desc* d);
+
+/* fp32 OIHW master weight [Co][ci_real][R][S] -> bf16 packed [Co][Kp] (k=(r,s,ci)) and
+ * bf16 transposed [Ci][R*S*Co] (k=(r,s,co)) for dgrad (wT may be NULL). */
+int gdl_conv_pack_weights(const gdl_conv_desc* d, int ci_real, const float* w_oihw,
+                          void* w_packed, void* w_packed_T, gdl_stream_t s);
+/* y[N,Ho,Wo,Co] = conv(x[N,Hi,Wi,Ci], w).  Implicit GEMM, tcgen05 + TMEM accumulators. */
+int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
+                 gdl_stream_t s);
+/* dx[N,Hi,Wi,Ci] = conv_transpose(dy, w) (+ add_src).  add_mode: 0 none, 1 add_src has the
+ * shape of dx (residual gradient), 2 add_src is [N,ceil(Hi/2),ceil(Wi/2),Ci] and is added at
+ * even (h,w) only (gradient of a 1x1 stride-2 downsample branch). */
+int gdl_conv_dgrad(const gdl_conv_desc* d, const void* dy, const void* w_packed_T, void* dx,
+                   const void* add_src, int add_mode, gdl_stream_t s);
+/* dw_oihw[Co][ci_real][R][S] (fp32) = sum over pixels; deterministic split-K. */
+int gdl_conv_wgrad(const gdl_conv_desc* d, int ci_real, const void* x, const void* dy,
+                   float* dw_oihw, void* workspace, int64_t workspace_bytes, gdl_stream_t s);
+
+/* ---- layout (reference models/backbone.py:162-164 permute/contiguous/view, and
+ *      main_dgl.py:100 spec.unsqueeze(1).float()) ---------------------------------------- */
+/* src f32 [B,C,T,H,W] -> dst bf16 [B*T,H,W,8] (channels >= C zero). */
+int gdl_layout_ncthw_to_nhwc8(const float* src, void* dst, int B, int C, int T, int H, int W,
+                              gdl_stream_t s);
+
+/* ---- BatchNorm2d training mode (reference models/backbone.py:45,48,104,144) ---------- */
+/* Per-channel batch statistics of x bf16 [P,C]: mean, invstd (biased var, eps), running
+ * stats update (momentum, unbiased var), and the fused affine scale/shift.
+ * partial: scratch of gdl_bn_partial_floats(P,C) floats. */
+int64_t gdl_bn_partial_floats(int64_t P, int C);
+int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, const float* gamma,
+                 const float* beta, float eps, float momentum, float* running_mean,
+                 float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                 gdl_stream_t s);
+/* y = [relu](x*scale + shift [+ res])  (BN-apply fused with ReLU backbone.py:46,57,66 and
+ * the residual add backbone.py:65). */
+int gdl_bn_apply(const void* x, const void* res, void* y, int64_t P, int C, const float* scale,
+                 const float* shift, int relu, gdl_stream_t s);
+/* Backward of y = [relu](bn(x) [+res]).  Pass 1: dz = dy*(y>0) (written to dz; dz may alias
+ * dy; if !relu dz is not written and dy is used as dz), partial sums of dz and dz*xhat.
+ * Then dgamma/dbeta (fp32, overwritten) and dx = gamma*invstd*(dz - dbeta/P - xhat*dgamma/P). */
+int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz, void* dx, int64_t P,
+               int C, const float* gamma, const float* mean, const float* invstd,
+               float* partial, float* dgamma, float* dbeta, int relu, gdl_stream_t s);
+
+/* ---- MaxPool2d(3,2,1) (reference models/backbone.py:106) ------------------------------ */
+int gdl_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C, int Ho,
+                    int Wo, gdl_stream_t s);
+int gdl_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int N, int H, int W, int C,
+                    int Ho, int Wo, gdl_stream_t s);
+
+/* ---- global average pool (reference models/basic_model.py:73-82) ---------------------- */
+/* x bf16 [B, G, C] (G = T*H*W pixels per sample) -> out f32 [B,C]. */
+int gdl_gap_fwd(const void* x, float* out, int B, int G, int C, gdl_stream_t s);
+/* dout f32 [B,C] -> dx bf16 [B,G,C] = dout/G. */
+int gdl_gap_bwd(const float* dout, void* dx, int B, int G, int C, gdl_stream_t s);
+
+/* ---- heads --------------------------------------------------------------------------- */
+/* Generic Linear (reference models/fusion_modules.py nn.Linear call sites): y = x W^T + b. */
+int gdl_linear_fwd(const float* x, const float* W, const float* b, float* y, int B, int In,
+                   int Out, gdl_stream_t s);
+/* dx = dy W (if dx), dW (+)= dy^T x, db (+)= sum dy (if dW/db); accumulate: 0 overwrite, 1 add. */
+int gdl_linear_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW,
+                   float* db, int B, int In, int Out, int accumulate, gdl_stream_t s);
+
+/* Fused DGL head, forward + 3x softmax-CE + truncated backward in one pass over the logits
+ * (reference models/fusion_modules.py:51-59 ConcatFusion_DGL / :22-30 SumFusion_DGL,
+ * main_dgl.py:102-122).
+ *   kind 0 = concat: Wx = fc_out.weight, Wy = Wx + D, ldw = 2D, one bias bx (by unused);
+ *   kind 1 = sum   : Wx = fc_x.weight, Wy = fc_y.weight, ldw = D, biases bx, by.
+ *   a,v        f32 [B,D]     pooled features
+ *   logits     f32 [3,B,n]   out, out_a, out_v (reference return order basic_model.py:86)
+ *   losses     f32 [3]       Lf, La, Lv = inv_batch * sum over the B local rows
+ *   da,dv      f32 [B,D]     alpha*dLa/da, alpha*dLv/dv  (the encoders see ONLY these)
+ *   dWx,dWy,dbx,dby          dLf/d(head params)          (the head sees ONLY Lf); row stride lddw
+ *   scratch    f32 [gdl_head_scratch_floats(B,n)]
+ */
+int64_t gdl_head_scratch_floats(int B, int n);
+int gdl_dgl_head_linear(int kind, const float* a, const float* v, const float* Wx, const float* Wy,
+                        int ldw, const float* bx, const float* by, const int64_t* labels,
+                        float alpha, float inv_batch, float* logits, float* losses, float* da,
+                        float* dv, float* dWx, float* dWy, int lddw, float* dbx, float* dby,
+                        float* scratch, int B, int D, int n, gdl_stream_t s);
+/* Softmax-CE on given logits [B,n] (reference main_dgl.py:71,102-104 nn.CrossEntropyLoss):
+ * loss_out[0] = loss_scale * sum_b loss_b; dlogits = grad_scale*(softmax-onehot) (may be NULL).
+ * scratch f32 [B].  Used by the gated/film heads, whose layers run through gdl_linear_*. */
+int gdl_softmax_ce(const float* logits, const int64_t* labels, float loss_scale, float grad_scale,
+                   float* loss_out, float* dlogits, float* scratch, int B, int n, gdl_stream_t s);
+/* Gated-head elementwise pieces (reference models/fusion_modules.py:230-250). */
+int gdl_gated_fwd(const float* hx, const float* hy, float* m_out, float* m_x, float* m_y,
+                  int64_t numel, gdl_stream_t s);
+int gdl_gated_bwd(const float* hx, const float* hy, const float* dm_x, const float* dm_y,
+                  float* dhx, float* dhy, int64_t numel, gdl_stream_t s);
+
+/* ---- optimizer / clipping / diagnostics (reference main_dgl.py:129-154,249) ---------- */
+/* Flat fp32 gradient arena with a segment table: seg_end[nseg] (exclusive end offsets,
+ * padding belongs to the preceding segment), seg_group[nseg] (0 = audio_net, 1 = visual_net,
+ * 2 = fusion head) and seg_inv_numel[nseg] (1/numel of the parameter tensor).
+ * stats_out f32 [4]: total L2 norm, clip coefficient min(1, max_norm/(norm+1e-6)),
+ * audio  sum_p mean|g_p|*coef, visual sum_p mean|g_p|*coef  (main_dgl.py:132-143, computed on
+ * the CLIPPED gradients like the reference).  scratch f32 [gdl_optim_scratch_floats()]. */
+int64_t gdl_optim_scratch_floats(int64_t numel, int nseg);
+int gdl_grad_stats(const float* grad, int64_t numel, const int64_t* seg_end,
+                   const int32_t* seg_group, const float* seg_inv_numel, int nseg, float max_norm,
+                   float* scratch, float* stats_out, gdl_stream_t s);
+/* SGD-momentum with weight decay (torch.optim.SGD semantics, main_dgl.py:154,249):
+ * g = grad*coef (written back, like clip_grad_norm_); g += wd*p; buf = first ? g : mu*buf+g;
+ * p -= lr*buf.  coef is read from stats[1] on the device (may be NULL => 1). */
+int gdl_sgd_momentum(float* param, float* grad, float* momentum_buf, int64_t numel, float lr,
+                     float mu, float wd, int first_step, const float* stats, gdl_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDL_B200_H_ */

@@ -1,0 +1,424 @@
+"""Per-kernel parity of the C-ABI ops against plain PyTorch fp32 references of the same op,
+on bf16-rounded operands (the kernels compute bf16 x bf16 -> fp32).  GPU only."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from gdl_b200 import ops
+    ops.init()
+    return ops
+
+
+def nhwc(x_nchw):  # fp32 NCHW -> bf16 NHWC contiguous
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(x_nhwc):  # bf16 NHWC -> fp32 NCHW
+    return x_nhwc.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rel_err(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+CONV_CASES = [
+    # N, H, W, Ci, Co, R, stride, pad
+    (2, 14, 14, 64, 64, 3, 1, 1),
+    (2, 13, 9, 64, 128, 3, 2, 1),
+    (3, 9, 6, 256, 512, 3, 1, 1),
+    (2, 12, 10, 64, 128, 1, 2, 0),
+    (1, 33, 24, 128, 128, 3, 1, 1),
+    (4, 17, 12, 128, 256, 3, 2, 1),
+    (2, 7, 7, 512, 512, 3, 1, 1),
+    (5, 56, 56, 64, 64, 3, 1, 1),
+]
+
+
+def _mk(N, H, W, Ci, Co, R, stride, pad, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(N, Ci, H, W, device="cuda", generator=g)
+    w = torch.randn(Co, Ci, R, R, device="cuda", generator=g) * (2.0 / (Ci * R * R)) ** 0.5
+    xb = x.to(torch.bfloat16).float()
+    wb = w.to(torch.bfloat16).float()
+    return xb, wb
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd(case):
+    ops = _ops()
+    N, H, W, Ci, Co, R, stride, pad = case
+    xb, wb = _mk(*case)
+    d = ops.conv_desc(N, H, W, Ci, Co, R, R, stride, pad)
+    Kp = ops.conv_packed_k(d)
+    wp = torch.empty(Co, Kp, device="cuda", dtype=torch.bfloat16)
+    ops.conv_pack_weights(d, Ci, wb, wp, None)
+    y = torch.full((N, d.Ho, d.Wo, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd(d, nhwc(xb), wp, y)
+    torch.cuda.synchronize()
+    ref = F.conv2d(xb, wb, stride=stride, padding=pad)
+    assert torch.isfinite(y.float()).all()
+    assert rel_err(nchw(y), ref) < 6e-3, rel_err(nchw(y), ref)
+
+
+@pytest.mark.parametrize("ci_real,H,W", [(3, 37, 29), (1, 41, 30), (3, 224, 224)])
+def test_conv_fwd_stem(ci_real, H, W):
+    ops = _ops()
+    N, Co, R, stride, pad = 2, 64, 7, 2, 3
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(N, ci_real, H, W, device="cuda", generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(Co, ci_real, R, R, device="cuda", generator=g) * 0.1).to(torch.bfloat16).float()
+    d = ops.conv_desc(N, H, W, 8, Co, R, R, stride, pad)
+    Kp = ops.conv_packed_k(d)
+    assert Kp == 448
+    wp = torch.empty(Co, Kp, device="cuda", dtype=torch.bfloat16)
+    ops.conv_pack_weights(d, ci_real, w, wp, None)
+    x8 = torch.zeros(N, H, W, 8, device="cuda", dtype=torch.bfloat16)
+    x8[..., :ci_real] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    y = torch.empty(N, d.Ho, d.Wo, Co, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd(d, x8, wp, y)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, stride=stride, padding=pad)
+    assert rel_err(nchw(y), ref) < 6e-3
+
+    # wgrad of the stem
+    dy = torch.randn(N, Co, d.Ho, d.Wo, device="cuda", generator=g).to(torch.bfloat16).float()
+    ws = torch.empty(ops.conv_wgrad_workspace_bytes(d) // 4, device="cuda", dtype=torch.float32)
+    dw = torch.full((Co, ci_real, R, R), float("nan"), device="cuda")
+    ops.conv_wgrad(d, ci_real, x8, nhwc(dy), dw, ws)
+    torch.cuda.synchronize()
+    ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=stride, padding=pad)
+    assert rel_err(dw, ref_dw) < 2e-3, rel_err(dw, ref_dw)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("add_mode", [0, 1])
+def test_conv_dgrad(case, add_mode):
+    ops = _ops()
+    N, H, W, Ci, Co, R, stride, pad = case
+    xb, wb = _mk(*case)
+    d = ops.conv_desc(N, H, W, Ci, Co, R, R, stride, pad)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    dy = torch.randn(N, Co, d.Ho, d.Wo, device="cuda", generator=g).to(torch.bfloat16).float()
+    Kp = ops.conv_packed_k(d)
+    wp = torch.empty(Co, Kp, device="cuda", dtype=torch.bfloat16)
+    wT = torch.zeros(Ci, R * R * Co, device="cuda", dtype=torch.bfloat16)
+    ops.conv_pack_weights(d, Ci, wb, wp, wT)
+    dx = torch.full((N, H, W, Ci), float("nan"), device="cuda", dtype=torch.bfloat16)
+    add = None
+    if add_mode == 1:
+        add = torch.randn(N, H, W, Ci, device="cuda", generator=g).to(torch.bfloat16)
+    ops.conv_dgrad(d, nhwc(dy), wT, dx, add, add_mode)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input(xb.shape, wb, dy, stride=stride, padding=pad)
+    if add is not None:
+        ref = ref + nchw(add)
+    assert torch.isfinite(dx.float()).all()
+    assert rel_err(nchw(dx), ref) < 6e-3, rel_err(nchw(dx), ref)
+
+
+def test_conv_dgrad_add_compact():
+    """add_mode 2: gradient of the 1x1/s2 downsample branch added at even pixels."""
+    ops = _ops()
+    N, H, W, Ci, Co = 2, 13, 9, 64, 128
+    case = (N, H, W, Ci, Co, 3, 2, 1)
+    xb, wb = _mk(*case)
+    d = ops.conv_desc(N, H, W, Ci, Co, 3, 3, 2, 1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dy = torch.randn(N, Co, d.Ho, d.Wo, device="cuda", generator=g).to(torch.bfloat16).float()
+    wp = torch.empty(Co, ops.conv_packed_k(d), device="cuda", dtype=torch.bfloat16)
+    wT = torch.zeros(Ci, 9 * Co, device="cuda", dtype=torch.bfloat16)
+    ops.conv_pack_weights(d, Ci, wb, wp, wT)
+    Hc, Wc = (H + 1) // 2, (W + 1) // 2
+    add = torch.randn(N, Hc, Wc, Ci, device="cuda", generator=g).to(torch.bfloat16)
+    dx = torch.empty(N, H, W, Ci, device="cuda", dtype=torch.bfloat16)
+    ops.conv_dgrad(d, nhwc(dy), wT, dx, add, 2)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input(xb.shape, wb, dy, stride=2, padding=1)
+    up = torch.zeros_like(ref)
+    up[:, :, ::2, ::2] = nchw(add)
+    assert rel_err(nchw(dx), ref + up) < 6e-3
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_wgrad(case):
+    ops = _ops()
+    N, H, W, Ci, Co, R, stride, pad = case
+    xb, wb = _mk(*case)
+    d = ops.conv_desc(N, H, W, Ci, Co, R, R, stride, pad)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    dy = torch.randn(N, Co, d.Ho, d.Wo, device="cuda", generator=g).to(torch.bfloat16).float()
+    ws = torch.empty(ops.conv_wgrad_workspace_bytes(d) // 4, device="cuda", dtype=torch.float32)
+    dw = torch.full((Co, Ci, R, R), float("nan"), device="cuda")
+    ops.conv_wgrad(d, Ci, nhwc(xb), nhwc(dy), dw, ws)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(xb, wb.shape, dy, stride=stride, padding=pad)
+    assert torch.isfinite(dw).all()
+    assert rel_err(dw, ref) < 2e-3, rel_err(dw, ref)
+    # determinism: bitwise identical on a second run
+    dw2 = torch.empty_like(dw)
+    ops.conv_wgrad(d, Ci, nhwc(xb), nhwc(dy), dw2, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)
+
+
+def test_layout():
+    ops = _ops()
+    B, Cc, T, H, W = 3, 3, 2, 10, 7
+    src = torch.randn(B, Cc, T, H, W, device="cuda")
+    dst = torch.empty(B * T, H, W, 8, device="cuda", dtype=torch.bfloat16)
+    ops.layout_ncthw_to_nhwc8(src, dst, B, Cc, T, H, W)
+    ref = src.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Cc).to(torch.bfloat16)
+    assert torch.equal(dst[..., :Cc], ref)
+    assert (dst[..., Cc:] == 0).all()
+
+
+@pytest.mark.parametrize("P,Cc", [(1000, 64), (777, 128), (50000, 256), (98, 512), (300000, 64)])
+@pytest.mark.parametrize("relu,use_res", [(1, 0), (1, 1), (0, 0)])
+def test_bn_fwd_bwd(P, Cc, relu, use_res):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn(P, Cc, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    res = torch.randn(P, Cc, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    gamma = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cc, device="cuda", generator=g) * 0.1
+    rm = torch.zeros(Cc, device="cuda")
+    rv = torch.ones(Cc, device="cuda")
+    partial = torch.empty(ops.bn_partial_floats(P, Cc), device="cuda")
+    mean, invstd, scale, shift = (torch.empty(Cc, device="cuda") for _ in range(4))
+    ops.bn_stats(x, P, Cc, partial, gamma, beta, 1e-5, 0.1, rm, rv, mean, invstd, scale, shift)
+    y = torch.empty_like(x)
+    ops.bn_apply(x, res, y, P, Cc, scale, shift, relu)
+    torch.cuda.synchronize()
+
+    xf = x.float().requires_grad_(True)
+    gref = gamma.clone().requires_grad_(True)
+    bref = beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    z = F.batch_norm(xf, rm2, rv2, gref, bref, True, 0.1, 1e-5)
+    if use_res:
+        z = z + res.float()
+    yr = F.relu(z) if relu else z
+    assert torch.allclose(mean, xf.detach().mean(0), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(rm, rm2, atol=1e-5, rtol=1e-4)
+    assert torch.allclose(rv, rv2, atol=1e-5, rtol=1e-4)
+    assert rel_err(y.float(), yr.detach()) < 5e-3
+
+    dy = torch.randn(P, Cc, device="cuda", generator=g).to(torch.bfloat16)
+    # use OUR y for the relu mask in the reference too (mask parity is tested above)
+    mask = (y.float() > 0).float() if relu else torch.ones_like(y.float())
+    (z * mask).backward(dy.float())
+    dz = torch.empty_like(dy)
+    dx = torch.empty_like(dy)
+    dgamma, dbeta = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    ops.bn_bwd(dy, y, x, dz if relu else None, dx, P, Cc, gamma, mean, invstd, partial, dgamma, dbeta, relu)
+    torch.cuda.synchronize()
+    assert rel_err(dgamma, gref.grad) < 2e-3
+    assert rel_err(dbeta, bref.grad) < 2e-3
+    assert rel_err(dx.float(), xf.grad) < 8e-3
+    if relu:
+        assert torch.equal(dz.float(), dy.float() * mask)
+
+
+@pytest.mark.parametrize("N,H,W,Cc", [(2, 129, 94, 64), (3, 112, 112, 64), (1, 7, 9, 64)])
+def test_maxpool(N, H, W, Cc):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.relu(torch.randn(N, Cc, H, W, device="cuda", generator=g)).to(torch.bfloat16)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    y = torch.empty(N, Ho, Wo, Cc, device="cuda", dtype=torch.bfloat16)
+    am = torch.empty(N, Ho, Wo, Cc, device="cuda", dtype=torch.uint8)
+    ops.maxpool_fwd(xn, y, am, N, H, W, Cc, Ho, Wo)
+    xf = x.float().requires_grad_(True)
+    yr = F.max_pool2d(xf, 3, 2, 1)
+    assert torch.equal(nchw(y), yr.detach())
+    dy = torch.randn(N, Cc, Ho, Wo, device="cuda", generator=g).to(torch.bfloat16)
+    yr.backward(dy.float())
+    dx = torch.empty(N, H, W, Cc, device="cuda", dtype=torch.bfloat16)
+    ops.maxpool_bwd(nhwc(dy.float()), am, dx, N, H, W, Cc, Ho, Wo)
+    torch.cuda.synchronize()
+    # ties between equal positive bf16 values may route differently from cuDNN; compare sums and bulk
+    assert rel_err(nchw(dx), xf.grad) < 2e-2
+    assert abs(nchw(dx).sum().item() - xf.grad.sum().item()) < 1e-1 * (1 + abs(xf.grad.sum().item()))
+
+
+def test_gap():
+    ops = _ops()
+    B, G, Cc = 5, 147, 512
+    x = torch.randn(B, G, Cc, device="cuda").to(torch.bfloat16)
+    out = torch.empty(B, Cc, device="cuda")
+    ops.gap_fwd(x, out, B, G, Cc)
+    assert torch.allclose(out, x.float().mean(1), atol=1e-5, rtol=1e-5)
+    dout = torch.randn(B, Cc, device="cuda")
+    dx = torch.empty_like(x)
+    ops.gap_bwd(dout, dx, B, G, Cc)
+    ref = (dout / G).to(torch.bfloat16)[:, None, :].expand(B, G, Cc)
+    assert torch.equal(dx, ref)
+
+
+@pytest.mark.parametrize("B,In,Out", [(7, 512, 6), (64, 512, 512), (33, 1024, 309)])
+def test_linear(B, In, Out):
+    ops = _ops()
+    x = torch.randn(B, In, device="cuda", requires_grad=True)
+    W = (torch.randn(Out, In, device="cuda") * 0.05).requires_grad_(True)
+    b = torch.randn(Out, device="cuda", requires_grad=True)
+    y = torch.empty(B, Out, device="cuda")
+    ops.linear_fwd(x.detach(), W.detach(), b.detach(), y, B, In, Out)
+    yr = F.linear(x.double(), W.double(), b.double())
+    assert torch.allclose(y.double(), yr, atol=1e-4, rtol=1e-4)
+    dy = torch.randn(B, Out, device="cuda")
+    yr.backward(dy.double())
+    dx, dW, db = torch.empty_like(x), torch.empty_like(W), torch.empty_like(b)
+    ops.linear_bwd(dy, x.detach(), W.detach(), dx, dW, db, B, In, Out)
+    assert torch.allclose(dx, x.grad, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(dW, W.grad, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(db, b.grad, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("B,n", [(16, 6), (37, 34), (64, 309)])
+def test_dgl_head_linear(kind, B, n):
+    """Fused head vs an autograd restatement of reference fusion_modules.py:22-30,51-59 +
+    main_dgl.py:102-122 (two backward passes with the fusion grads wiped in between)."""
+    ops = _ops()
+    D, alpha = 512, 4.0
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randn(B, D, device="cuda", generator=g).double().requires_grad_(True)
+    v = torch.randn(B, D, device="cuda", generator=g).double().requires_grad_(True)
+    labels = torch.randint(0, n, (B,), device="cuda", generator=g)
+    if kind == 0:
+        W = (torch.randn(n, 2 * D, device="cuda", generator=g) * 0.05).double().requires_grad_(True)
+        bx = torch.randn(n, device="cuda", generator=g).double().requires_grad_(True)
+        out = F.linear(torch.cat((a, v), 1).detach(), W, bx)
+        xo = F.linear(torch.cat((a, torch.zeros_like(v)), 1), W, bx)
+        yo = F.linear(torch.cat((torch.zeros_like(a), v), 1), W, bx)
+        params = [W, bx]
+    else:
+        Wx = (torch.randn(n, D, device="cuda", generator=g) * 0.05).double().requires_grad_(True)
+        Wy = (torch.randn(n, D, device="cuda", generator=g) * 0.05).double().requires_grad_(True)
+        bx = torch.randn(n, device="cuda", generator=g).double().requires_grad_(True)
+        by = torch.randn(n, device="cuda", generator=g).double().requires_grad_(True)
+        xo, yo = F.linear(a, Wx, bx), F.linear(v, Wy, by)
+        out = F.linear(a.detach(), Wx, bx) + F.linear(v.detach(), Wy, by)
+        params = [Wx, Wy, bx, by]
+    Lf, La, Lv = (F.cross_entropy(t, labels) for t in (out, xo, yo))
+    ((La + Lv) * alpha).backward(retain_graph=True)
+    for p in params:
+        p.grad = None
+    Lf.backward()
+
+    f32 = lambda t: t.detach().float().contiguous()
+    logits = torch.empty(3, B, n, device="cuda")
+    losses = torch.empty(3, device="cuda")
+    da, dv = torch.empty(B, D, device="cuda"), torch.empty(B, D, device="cuda")
+    scratch = torch.empty(ops.head_scratch_floats(B, n), device="cuda")
+    if kind == 0:
+        Wf, bf = f32(W), f32(bx)
+        dW, db = torch.empty_like(Wf), torch.empty_like(bf)
+        ops.dgl_head_linear(0, f32(a), f32(v), Wf.data_ptr(), Wf.data_ptr() + 4 * D, 2 * D, bf, None, labels,
+                            alpha, 1.0 / B, logits, losses, da, dv, dW.data_ptr(), dW.data_ptr() + 4 * D,
+                            2 * D, db, None, scratch, B, D, n)
+        got = [dW, db]
+    else:
+        Wxf, Wyf, bxf, byf = f32(Wx), f32(Wy), f32(bx), f32(by)
+        dWx, dWy, dbx, dby = (torch.empty_like(t) for t in (Wxf, Wyf, bxf, byf))
+        ops.dgl_head_linear(1, f32(a), f32(v), Wxf.data_ptr(), Wyf.data_ptr(), D, bxf, byf, labels, alpha,
+                            1.0 / B, logits, losses, da, dv, dWx.data_ptr(), dWy.data_ptr(), D, dbx, dby,
+                            scratch, B, D, n)
+        got = [dWx, dWy, dbx, dby]
+    torch.cuda.synchronize()
+    tol = dict(atol=2e-5, rtol=2e-4)
+    assert torch.allclose(logits[0].double(), out.detach(), **tol)
+    assert torch.allclose(logits[1].double(), xo.detach(), **tol)
+    assert torch.allclose(logits[2].double(), yo.detach(), **tol)
+    assert torch.allclose(losses.double(), torch.stack([Lf, La, Lv]).detach(), **tol)
+    assert torch.allclose(da.double(), a.grad, **tol)
+    assert torch.allclose(dv.double(), v.grad, **tol)
+    for gt, p in zip(got, params):
+        assert torch.allclose(gt.double(), p.grad, **tol)
+
+
+def test_softmax_ce_and_gated():
+    ops = _ops()
+    B, n = 19, 34
+    z = torch.randn(B, n, device="cuda", requires_grad=True)
+    labels = torch.randint(0, n, (B,), device="cuda")
+    loss = torch.empty(1, device="cuda")
+    dz = torch.empty(B, n, device="cuda")
+    scratch = torch.empty(B, device="cuda")
+    ops.softmax_ce(z.detach(), labels, 1.0 / B, 4.0 / B, loss, dz, scratch, B, n)
+    Lr = F.cross_entropy(z, labels)
+    (Lr * 4.0).backward()
+    assert torch.allclose(loss[0], Lr.detach(), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(dz, z.grad, atol=1e-6, rtol=1e-4)
+
+    hx = torch.randn(B, 512, device="cuda", requires_grad=True)
+    hy = torch.randn(B, 512, device="cuda", requires_grad=True)
+    mo, mx, my = (torch.empty(B, 512, device="cuda") for _ in range(3))
+    ops.gated_fwd(hx.detach(), hy.detach(), mo, mx, my)
+    rx, ry = torch.sigmoid(hx) * hx, torch.sigmoid(hy) * hy
+    assert torch.allclose(mo, (torch.sigmoid(hx) * hy).detach(), atol=1e-6, rtol=1e-5)
+    assert torch.allclose(mx, rx.detach(), atol=1e-6, rtol=1e-5)
+    gx, gy = torch.randn_like(hx), torch.randn_like(hy)
+    (rx * gx + ry * gy).sum().backward()
+    dhx, dhy = torch.empty_like(gx), torch.empty_like(gy)
+    ops.gated_bwd(hx.detach(), hy.detach(), gx, gy, dhx, dhy)
+    assert torch.allclose(dhx, hx.grad, atol=1e-5, rtol=1e-4)
+    assert torch.allclose(dhy, hy.grad, atol=1e-5, rtol=1e-4)
+
+
+def test_grad_stats_and_sgd():
+    ops = _ops()
+    sizes = [(64, 3, 7, 7), (64,), (64,), (128, 64, 3, 3), (6, 1024), (6,), (100003,)]
+    groups = [0, 0, 1, 1, 2, 2, 1]
+    pad = lambda n: (n + 63) // 64 * 64
+    offs, total = [], 0
+    for s in sizes:
+        offs.append(total)
+        total += pad(int(torch.tensor(s).prod()))
+    g = torch.Generator(device="cuda").manual_seed(8)
+    grad = torch.zeros(total, device="cuda")
+    param = torch.zeros(total, device="cuda")
+    grads, params = [], []
+    for s, o in zip(sizes, offs):
+        n = int(torch.tensor(s).prod())
+        grad[o:o + n] = torch.randn(n, device="cuda", generator=g) * 3
+        param[o:o + n] = torch.randn(n, device="cuda", generator=g)
+        grads.append(grad[o:o + n].clone().view(s))
+        params.append(param[o:o + n].clone().view(s).requires_grad_(True))
+    seg_end = torch.tensor([o + pad(int(torch.tensor(s).prod())) for s, o in zip(sizes, offs)],
+                           device="cuda", dtype=torch.int64)
+    seg_group = torch.tensor(groups, device="cuda", dtype=torch.int32)
+    seg_inv = torch.tensor([1.0 / int(torch.tensor(s).prod()) for s in sizes], device="cuda")
+    scratch = torch.empty(ops.optim_scratch_floats(total, len(sizes)), device="cuda")
+    stats = torch.empty(4, device="cuda")
+    ops.grad_stats(grad, total, seg_end, seg_group, seg_inv, len(sizes), 40.0, scratch, stats)
+    buf = torch.zeros(total, device="cuda")
+    p0 = param.clone()
+    for step in range(2):
+        ops.sgd_momentum(param, grad, buf, total, 0.01, 0.9, 1e-4, step == 0, stats)
+        if step == 0:
+            stats[1] = 1.0  # second step: grads already clipped
+    torch.cuda.synchronize()
+
+    for p, gr in zip(params, grads):
+        p.grad = gr.clone()
+    norm = torch.nn.utils.clip_grad_norm_(params, 40.0, 2)
+    opt = torch.optim.SGD(params, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    a_sum = sum(p.grad.abs().mean().item() for p, gg in zip(params, groups) if gg == 0)
+    v_sum = sum(p.grad.abs().mean().item() for p, gg in zip(params, groups) if gg == 1)
+    opt.step()
+    opt.step()
+    assert abs(stats[0].item() - norm.item()) < 1e-3 * norm.item()
+    # stats[2], stats[3] were computed before we overwrote stats[1]
+    assert abs(stats[2].item() - a_sum) < 1e-4 * (1 + a_sum)
+    assert abs(stats[3].item() - v_sum) < 1e-4 * (1 + v_sum)
+    for p, s, o in zip(params, sizes, offs):
+        n = p.numel()
+        assert torch.allclose(param[o:o + n].view(s), p.detach(), atol=1e-6, rtol=1e-5)
+        assert torch.allclose(grad[o:o + n].view(s), p.grad, atol=1e-6, rtol=1e-5)
+    assert p0.shape == param.shape
