@@ -17,7 +17,7 @@ namespace gdl {
 // ------------------------------------------------------------------------------------------
 // generic linear
 // ------------------------------------------------------------------------------------------
-__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, int ldw,
                                   const float* __restrict__ b, float* __restrict__ y, int B, int In,
                                   int Out) {
   int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (b, o)
@@ -25,27 +25,27 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
   if (gw >= (int64_t)B * Out) return;
   int bi = int(gw / Out), o = int(gw - (int64_t)bi * Out);
   const float* xr = x + (int64_t)bi * In;
-  const float* wr = W + (int64_t)o * In;
+  const float* wr = W + (int64_t)o * ldw;
   float acc = 0.f;
   for (int i = lane; i < In; i += 32) acc = fmaf(xr[i], wr[i], acc);
   acc = warp_sum(acc);
   if (lane == 0) y[gw] = acc + (b ? b[o] : 0.f);
 }
 
-__global__ void linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+__global__ void linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W, int ldw,
                                      float* __restrict__ dx, int B, int In, int Out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, i), i fastest
   if (idx >= (int64_t)B * In) return;
   int bi = int(idx / In), i = int(idx - (int64_t)bi * In);
   const float* g = dy + (int64_t)bi * Out;
   float acc = 0.f;
-  for (int o = 0; o < Out; ++o) acc = fmaf(g[o], W[(int64_t)o * In + i], acc);
+  for (int o = 0; o < Out; ++o) acc = fmaf(g[o], W[(int64_t)o * ldw + i], acc);
   dx[idx] = acc;
 }
 
 __global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                     float* __restrict__ dW, float* __restrict__ db, int B, int In,
-                                     int Out, int accumulate) {
+                                     float* __restrict__ dW, int lddw, float* __restrict__ db, int B,
+                                     int In, int Out, int accumulate) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (o, i), i fastest; i == In -> bias
   int64_t total = (int64_t)Out * (In + 1);
   if (idx >= total) return;
@@ -53,7 +53,7 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* 
   float acc = 0.f;
   if (i < In) {
     for (int bi = 0; bi < B; ++bi) acc = fmaf(dy[(int64_t)bi * Out + o], x[(int64_t)bi * In + i], acc);
-    float* dst = dW + (int64_t)o * In + i;
+    float* dst = dW + (int64_t)o * lddw + i;
     *dst = accumulate ? *dst + acc : acc;
   } else if (db != nullptr) {
     for (int bi = 0; bi < B; ++bi) acc += dy[(int64_t)bi * Out + o];
@@ -245,27 +245,28 @@ __global__ void gated_bwd_kernel(const float* __restrict__ hx, const float* __re
 
 using namespace gdl;
 
-extern "C" int gdl_linear_fwd(const float* x, const float* W, const float* b, float* y, int B, int In,
-                              int Out, gdl_stream_t s) {
-  GDL_REQUIRE(x && W && y && B > 0 && In > 0 && Out > 0, "gdl_linear_fwd: bad arguments");
+extern "C" int gdl_linear_fwd(const float* x, const float* W, int ldw, const float* b, float* y, int B,
+                              int In, int Out, gdl_stream_t s) {
+  GDL_REQUIRE(x && W && y && B > 0 && In > 0 && Out > 0 && ldw >= In, "gdl_linear_fwd: bad arguments");
   int64_t threads = (int64_t)B * Out * 32;
-  linear_fwd_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)s>>>(x, W, b, y, B, In, Out);
+  linear_fwd_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)s>>>(x, W, ldw, b, y, B, In, Out);
   GDL_CHECK_LAUNCH("linear_fwd_kernel");
   return GDL_OK;
 }
 
-extern "C" int gdl_linear_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW,
-                              float* db, int B, int In, int Out, int accumulate, gdl_stream_t s) {
+extern "C" int gdl_linear_bwd(const float* dy, const float* x, const float* W, int ldw, float* dx,
+                              float* dW, int lddw, float* db, int B, int In, int Out, int accumulate,
+                              gdl_stream_t s) {
   GDL_REQUIRE(dy && B > 0 && In > 0 && Out > 0, "gdl_linear_bwd: bad arguments");
   if (dx != nullptr) {
     GDL_REQUIRE(W != nullptr, "gdl_linear_bwd: dx needs W");
-    linear_bwd_dx_kernel<<<(unsigned)ceil_div64((int64_t)B * In, 256), 256, 0, (cudaStream_t)s>>>(dy, W, dx, B, In, Out);
+    linear_bwd_dx_kernel<<<(unsigned)ceil_div64((int64_t)B * In, 256), 256, 0, (cudaStream_t)s>>>(dy, W, ldw, dx, B, In, Out);
     GDL_CHECK_LAUNCH("linear_bwd_dx_kernel");
   }
   if (dW != nullptr) {
     GDL_REQUIRE(x != nullptr, "gdl_linear_bwd: dW needs x");
     linear_bwd_dw_kernel<<<(unsigned)ceil_div64((int64_t)Out * (In + 1), 256), 256, 0, (cudaStream_t)s>>>(
-        dy, x, dW, db, B, In, Out, accumulate);
+        dy, x, dW, lddw, db, B, In, Out, accumulate);
     GDL_CHECK_LAUNCH("linear_bwd_dw_kernel");
   }
   return GDL_OK;

@@ -48,8 +48,8 @@ SIGNATURES = {
     "gdl_maxpool_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "gdl_gap_fwd": (_i, [_p, _p, _i, _i, _i, _p]),
     "gdl_gap_bwd": (_i, [_p, _p, _i, _i, _i, _p]),
-    "gdl_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
-    "gdl_linear_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "gdl_linear_fwd": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p]),
+    "gdl_linear_bwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "gdl_head_scratch_floats": (_l, [_i, _i]),
     "gdl_dgl_head_linear": (_i, [_i, _p, _p, _p, _p, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p,
                                  _p, _i, _p, _p, _p, _i, _i, _i, _p]),

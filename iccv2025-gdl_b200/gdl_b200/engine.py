@@ -1,0 +1,226 @@
+"""EncoderEngine — runs one ResNet-18 modality encoder (reference models/backbone.py:160-201
+forward, and its autograd backward) entirely through the sm_100a kernels of libgdl_b200.so.
+
+The engine borrows the parameters of a `backbone.ResNet` module (fp32, reference names and
+shapes), keeps bf16 packed shadows of the conv weights, and owns a static set of NHWC bf16
+activation / gradient buffers for one input geometry, so a whole step is a fixed sequence of
+kernel launches on fixed addresses (CUDA-graph capturable, no allocation inside the step).
+
+Data layout in HBM:
+  activations     bf16 NHWC  [N, H, W, C]                      (C = 64..512; stem input C = 8 padded)
+  conv weights    fp32 OIHW master (the nn.Parameter)  +  bf16 [Co, Kp] (k = (r,s,ci)) for fwd/wgrad
+                  +  bf16 [Ci, R*S*Co] (k = (r,s,co)) for dgrad
+  BN              fp32 per-channel gamma/beta/running stats (nn.Parameter / buffers), fp32 batch
+                  mean / invstd / fused scale+shift saved for backward
+  gradients       activations bf16 NHWC; parameters fp32 written straight into p.grad storage
+"""
+import torch
+
+from . import ops
+
+
+class _Pool:
+    """Static buffer planner: buffers are requested/released while the plan is built; a released
+    buffer of the same size is reused by a later request (backward temporaries)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+        self.total_bytes = 0
+
+    def get(self, shape, dtype=torch.bfloat16):
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        t = torch.empty(shape, device=self.device, dtype=dtype)
+        self.total_bytes += t.numel() * t.element_size()
+        return t
+
+    def put(self, t):
+        self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+class _ConvBN:
+    """One conv + BatchNorm unit with its saved tensors."""
+
+    def __init__(self, eng, name, conv, bn, N, Hi, Wi, ci_store, relu):
+        w = conv.weight
+        Co, ci_real, R, S = w.shape
+        self.name = name
+        self.conv, self.bn = conv, bn
+        self.ci_real = ci_real
+        self.relu = relu
+        self.d = ops.conv_desc(N, Hi, Wi, ci_store, Co, R, S, conv.stride[0], conv.padding[0])
+        self.P = N * self.d.Ho * self.d.Wo
+        self.C = Co
+        dev = eng.device
+        self.Kp = ops.conv_packed_k(self.d)
+        self.wp = torch.zeros(Co, self.Kp, device=dev, dtype=torch.bfloat16)
+        self.wT = None if ci_store == 8 else torch.zeros(ci_store, R * S * Co, device=dev, dtype=torch.bfloat16)
+        self.x = torch.empty(N, self.d.Ho, self.d.Wo, Co, device=dev, dtype=torch.bfloat16)  # conv out
+        self.y = torch.empty_like(self.x)                                                      # bn(+relu) out
+        self.mean, self.invstd, self.scale, self.shift = (torch.empty(Co, device=dev) for _ in range(4))
+        eng.max_wgrad_ws = max(eng.max_wgrad_ws, ops.conv_wgrad_workspace_bytes(self.d))
+        eng.max_bn_partial = max(eng.max_bn_partial, ops.bn_partial_floats(self.P, Co))
+
+    def repack(self):
+        ops.conv_pack_weights(self.d, self.ci_real, self.conv.weight.data, self.wp, self.wT)
+
+    def forward(self, eng, inp, res=None, training=True):
+        ops.conv_fwd(self.d, inp, self.wp, self.x)
+        bn = self.bn
+        if training:
+            ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
+                         bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                         self.scale, self.shift)
+        else:
+            raise NotImplementedError("eval-mode forward goes through EncoderEngine.forward_eval")
+        ops.bn_apply(self.x, res, self.y, self.P, self.C, self.scale, self.shift, self.relu)
+        return self.y
+
+
+class EncoderEngine:
+    def __init__(self, net, N, H, W, device):
+        """net: backbone.ResNet; N images of H x W (audio: N=B, visual: N=B*T)."""
+        ops.init()
+        self.net = net
+        self.N, self.H, self.W = N, H, W
+        self.device = device
+        self.max_wgrad_ws = 0
+        self.max_bn_partial = 0
+        self.units = []
+        self.blocks = []
+        self.stem = self._unit("conv1", net.conv1, net.bn1, N, H, W, 8, True)
+        H1, W1 = self.stem.d.Ho, self.stem.d.Wo
+        self.Hp, self.Wp = (H1 - 1) // 2 + 1, (W1 - 1) // 2 + 1
+        self.pool_y = torch.empty(N, self.Hp, self.Wp, 64, device=device, dtype=torch.bfloat16)
+        self.pool_idx = torch.empty(N, self.Hp, self.Wp, 64, device=device, dtype=torch.uint8)
+        h, w, cin = self.Hp, self.Wp, 64
+        for li in range(1, 5):
+            layer = getattr(net, "layer%d" % li)
+            for bi, blk in enumerate(layer):
+                pre = "layer%d.%d." % (li, bi)
+                u1 = self._unit(pre + "conv1", blk.conv1, blk.bn1, N, h, w, cin, True)
+                u2 = self._unit(pre + "conv2", blk.conv2, blk.bn2, N, u1.d.Ho, u1.d.Wo, u1.C, True)
+                ud = None
+                if blk.downsample is not None:
+                    ud = self._unit(pre + "downsample", blk.downsample[0], blk.downsample[1], N, h, w, cin, False)
+                self.blocks.append((u1, u2, ud))
+                h, w, cin = u1.d.Ho, u1.d.Wo, u1.C
+        self.Hf, self.Wf, self.Cf = h, w, cin
+        self.wgrad_ws = torch.empty(max(self.max_wgrad_ws, 16) // 4, device=device, dtype=torch.float32)
+        self.bn_partial = torch.empty(self.max_bn_partial, device=device, dtype=torch.float32)
+        self._plan_backward()
+        self.repack()
+
+    def _unit(self, name, conv, bn, N, Hi, Wi, ci_store, relu):
+        u = _ConvBN(self, name, conv, bn, N, Hi, Wi, ci_store, relu)
+        self.units.append(u)
+        return u
+
+    # ------------------------------------------------------------------ weights
+    def repack(self):
+        """Refresh the bf16 shadows from the fp32 masters (after every optimizer step)."""
+        for u in self.units:
+            u.repack()
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x8):
+        """x8: bf16 [N,H,W,8] -> bf16 [N,Hf,Wf,512] (the layer4 map, reference backbone.py:175-181)."""
+        s = self.stem
+        y = s.forward(self, x8)
+        ops.maxpool_fwd(y, self.pool_y, self.pool_idx, self.N, s.d.Ho, s.d.Wo, 64, self.Hp, self.Wp)
+        u = self.pool_y
+        for (u1, u2, ud) in self.blocks:
+            y1 = u1.forward(self, u)
+            ident = u
+            if ud is not None:
+                ident = ud.forward(self, u)
+            # bn2 + residual + relu (reference backbone.py:62-66)
+            u = u2.forward(self, y1, res=ident)
+        return u
+
+    # ------------------------------------------------------------------ backward
+    def _plan_backward(self):
+        """Assign the (reused) gradient buffers of every block once."""
+        pool = _Pool(self.device)
+        plan = []
+        N = self.N
+        g_out = pool.get((N, self.Hf, self.Wf, self.Cf))
+        self.g_feat = g_out
+        for (u1, u2, ud) in reversed(self.blocks):
+            d_c2 = pool.get(u2.x.shape)
+            g_y1 = pool.get(u1.y.shape)
+            d_c1 = pool.get(u1.x.shape)
+            in_shape = (N, u1.d.Hi, u1.d.Wi, u1.d.Ci)
+            g_u = pool.get(in_shape)
+            d_cd = g_ds = None
+            if ud is not None:
+                d_cd = pool.get(ud.x.shape)
+                g_ds = pool.get((N, ud.d.Ho, ud.d.Wo, ud.d.Ci))
+            plan.append(dict(g_out=g_out, d_c2=d_c2, g_y1=g_y1, d_c1=d_c1, g_u=g_u, d_cd=d_cd, g_ds=g_ds))
+            # lifetimes: everything but g_u dies with the block; g_out dies too
+            for t in (d_c2, g_y1, d_c1, d_cd, g_ds, g_out):
+                if t is not None:
+                    pool.put(t)
+            g_out = g_u
+        s = self.stem
+        self.g_pool = g_out                      # grad wrt maxpool output
+        self.g_y0 = pool.get(s.y.shape)          # grad wrt stem relu output
+        self.d_c0 = pool.get(s.x.shape)
+        self.bwd_plan = plan
+        self.grad_buffer_bytes = pool.total_bytes
+
+    grad_override = None  # optional {param: tensor} destination map (autograd-compatible mode)
+
+    def _grad(self, p):
+        if self.grad_override is not None:
+            return self.grad_override[p]
+        if p.grad is None:
+            p.grad = torch.zeros_like(p.data)
+        return p.grad
+
+    def parameters(self):
+        """Encoder parameters in the order the backward writes them (units order)."""
+        out = []
+        for u in self.units:
+            out += [u.conv.weight, u.bn.weight, u.bn.bias]
+        return out
+
+    def _bn_bwd(self, u, dy, dz, dx, relu):
+        bn = u.bn
+        ops.bn_bwd(dy, u.y, u.x, dz, dx, u.P, u.C, bn.weight.data, u.mean, u.invstd, self.bn_partial,
+                   self._grad(bn.weight), self._grad(bn.bias), relu)
+
+    def backward(self, x8):
+        """Consumes self.g_feat (grad wrt the layer4 map, bf16) and writes every parameter
+        gradient of the encoder into p.grad (overwrite).  x8 is the stem input of the forward."""
+        for (u1, u2, ud), b, in_t in zip(reversed(self.blocks), self.bwd_plan, reversed(self._block_inputs())):
+            g_out = b["g_out"]
+            # out = relu(bn2(c2) + identity): dz = g_out * (out > 0), in place
+            self._bn_bwd(u2, g_out, g_out, b["d_c2"], True)
+            ops.conv_wgrad(u2.d, u2.ci_real, u1.y, b["d_c2"], self._grad(u2.conv.weight), self.wgrad_ws)
+            ops.conv_dgrad(u2.d, b["d_c2"], u2.wT, b["g_y1"])
+            self._bn_bwd(u1, b["g_y1"], b["g_y1"], b["d_c1"], True)
+            ops.conv_wgrad(u1.d, u1.ci_real, in_t, b["d_c1"], self._grad(u1.conv.weight), self.wgrad_ws)
+            if ud is not None:
+                # identity = bn_d(conv1x1_s2(u)), no relu: its output gradient is dz (= g_out now)
+                self._bn_bwd(ud, g_out, None, b["d_cd"], False)
+                ops.conv_wgrad(ud.d, ud.ci_real, in_t, b["d_cd"], self._grad(ud.conv.weight), self.wgrad_ws)
+                # 1x1 stride-2 dgrad on the compact grid, then folded into conv1's dgrad epilogue
+                dc = ops.conv_desc(self.N, ud.d.Ho, ud.d.Wo, ud.d.Ci, ud.d.Co, 1, 1, 1, 0)
+                ops.conv_dgrad(dc, b["d_cd"], ud.wT, b["g_ds"])
+                ops.conv_dgrad(u1.d, b["d_c1"], u1.wT, b["g_u"], b["g_ds"], 2)
+            else:
+                ops.conv_dgrad(u1.d, b["d_c1"], u1.wT, b["g_u"], g_out, 1)
+        s = self.stem
+        ops.maxpool_bwd(self.g_pool, self.pool_idx, self.g_y0, self.N, s.d.Ho, s.d.Wo, 64, self.Hp, self.Wp)
+        self._bn_bwd(s, self.g_y0, self.g_y0, self.d_c0, True)
+        ops.conv_wgrad(s.d, s.ci_real, x8, self.d_c0, self._grad(s.conv.weight), self.wgrad_ws)
+
+    def _block_inputs(self):
+        ins = [self.pool_y]
+        for (u1, u2, ud) in self.blocks[:-1]:
+            ins.append(u2.y)
+        return ins

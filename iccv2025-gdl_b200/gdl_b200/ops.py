@@ -112,14 +112,24 @@ def gap_bwd(dout, dx, B, G, Cc):
     check(_lib.load().gdl_gap_bwd(_ptr(dout), _ptr(dx), B, G, Cc, _stream()), "gdl_gap_bwd")
 
 
-def linear_fwd(x, W, b, y, B, In, Out):
-    check(_lib.load().gdl_linear_fwd(_ptr(x), _ptr(W), _ptr(b), _ptr(y), B, In, Out, _stream()),
+def _addr(t):
+    """Raw device address; accepts a tensor, an int address or None."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+def linear_fwd(x, W, b, y, B, In, Out, ldw=None):
+    check(_lib.load().gdl_linear_fwd(_ptr(x), _addr(W), ldw or In, _ptr(b), _ptr(y), B, In, Out, _stream()),
           "gdl_linear_fwd")
 
 
-def linear_bwd(dy, x, W, dx, dW, db, B, In, Out, accumulate=False):
-    check(_lib.load().gdl_linear_bwd(_ptr(dy), _ptr(x), _ptr(W), _ptr(dx), _ptr(dW), _ptr(db), B, In,
-                                     Out, int(accumulate), _stream()), "gdl_linear_bwd")
+def linear_bwd(dy, x, W, dx, dW, db, B, In, Out, accumulate=False, ldw=None, lddw=None):
+    check(_lib.load().gdl_linear_bwd(_ptr(dy), _ptr(x), _addr(W), ldw or In, _ptr(dx), _addr(dW),
+                                     lddw or In, _ptr(db), B, In, Out, int(accumulate), _stream()),
+          "gdl_linear_bwd")
 
 
 def head_scratch_floats(B, n):

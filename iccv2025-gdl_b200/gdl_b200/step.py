@@ -1,0 +1,261 @@
+"""DGLStep — the fused Disentangled-Gradient-Learning training step (SURVEY.md §8b mode 2).
+
+One call = reference main_dgl.py:93-158 for one batch: H2D of (spec, image, label), both
+ResNet-18 encoders forward, global average pooling, the fused DGL head (three logit sets,
+three cross-entropies, truncated gradients), both encoder backwards, [gradient all-reduce],
+clip_grad_norm_(40), the audio/visual gradient diagnostics, SGD-momentum, and the refresh of
+the bf16 weight shadows — as a fixed sequence of libgdl_b200.so kernels on two CUDA streams
+(audio || visual), optionally captured into one CUDA graph.  The only device->host traffic is
+one 7-float read (3 losses + norm, clip coefficient, 2 diagnostics) when the caller asks.
+
+Gradient routing (the point of DGL, reference main_dgl.py:108-122):
+    encoders  <- alpha * d(La + Lv)        (the multimodal head saw detached features)
+    head      <- d(Lf)                     (the unimodal gradient of the head is wiped)
+Parameters that never receive a gradient in the reference (ConcatFusion_DGL.fc_auxi,
+GatedFusion_DGL.fc_x / fc_y — SURVEY.md §8a quirks 1-2) are left untouched: no weight decay,
+no momentum, exactly like torch.optim.SGD skipping `grad is None`.
+"""
+import torch
+
+from . import ops
+from .autograd import to_nhwc8  # noqa: F401  (re-export for callers)
+from .basic_model import AVClassifier_DGL
+from .fusion_modules import ConcatFusion_DGL, FiLM_DGL, GatedFusion_DGL, SumFusion_DGL
+
+_SEG_ALIGN = 64  # floats; keeps every tensor 256-byte aligned inside the arenas
+
+
+def _pad(n):
+    return (n + _SEG_ALIGN - 1) // _SEG_ALIGN * _SEG_ALIGN
+
+
+def head_trainable(fm):
+    """Head parameters that receive a gradient from Lf (everything else stays grad-less)."""
+    if isinstance(fm, ConcatFusion_DGL):
+        return [fm.fc_out.weight, fm.fc_out.bias]
+    if isinstance(fm, SumFusion_DGL):
+        return [fm.fc_x.weight, fm.fc_x.bias, fm.fc_y.weight, fm.fc_y.bias]
+    if isinstance(fm, GatedFusion_DGL):
+        return [fm.fc_out.weight, fm.fc_out.bias]
+    if isinstance(fm, FiLM_DGL):
+        return [fm.fc.weight, fm.fc.bias, fm.fc_out.weight, fm.fc_out.bias]
+    raise NotImplementedError('Incorrect fusion method: {}!'.format(type(fm).__name__))
+
+
+class ParamArena:
+    """Flat fp32 arenas (parameters, gradients, momentum) with the nn.Parameters re-pointed to
+    views, so clipping statistics, SGD and the gradient all-reduce are single passes.
+    Order: head | audio_net | visual_net  (groups 2, 0, 1 for the diagnostics)."""
+
+    def __init__(self, model, device):
+        groups = [(2, head_trainable(model.fusion_module)),
+                  (0, list(model.audio_net.parameters())),
+                  (1, list(model.visual_net.parameters()))]
+        self.params, seg_end, seg_group, seg_inv = [], [], [], []
+        off = 0
+        self.offsets = []
+        self.group_ranges = {}
+        for gid, plist in groups:
+            start = off
+            for p in plist:
+                self.params.append(p)
+                self.offsets.append(off)
+                off += _pad(p.numel())
+                seg_end.append(off)
+                seg_group.append(gid)
+                seg_inv.append(1.0 / p.numel())
+            self.group_ranges[gid] = (start, off)
+        self.numel = off
+        self.extra = 64  # tail slots all-reduced together with the gradients (3 losses)
+        self.param = torch.zeros(off, device=device)
+        self.grad = torch.zeros(off + self.extra, device=device)
+        self.momentum = torch.zeros(off, device=device)
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            self.param[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.param[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+        self.nseg = len(seg_end)
+        self.seg_end = torch.tensor(seg_end, device=device, dtype=torch.int64)
+        self.seg_group = torch.tensor(seg_group, device=device, dtype=torch.int32)
+        self.seg_inv = torch.tensor(seg_inv, device=device, dtype=torch.float32)
+        self.scratch = torch.empty(ops.optim_scratch_floats(off, self.nseg), device=device)
+
+
+class DGLStep:
+    def __init__(self, model, batch_size, spec_hw, image_thw, alpha=4.0, lr=0.001, momentum=0.9,
+                 weight_decay=1e-4, max_norm=40.0, world_size=1, process_group=None, use_graph=True):
+        """model: AVClassifier_DGL on a CUDA device (possibly wrapped: `.module` is unwrapped).
+        batch_size: LOCAL batch on this GPU; losses are means over batch_size*world_size."""
+        model = getattr(model, "module", model)
+        if not isinstance(model, AVClassifier_DGL):
+            raise TypeError("DGLStep needs a gdl_b200.AVClassifier_DGL")
+        self.model = model
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("DGLStep runs on a B200 only (no CPU fallback)")
+        ops.init()
+        self.device = dev
+        self.B = batch_size
+        self.F_, self.Tt = spec_hw
+        self.T, self.H, self.W = image_thw
+        self.alpha, self.lr, self.mu, self.wd, self.max_norm = alpha, lr, momentum, weight_decay, max_norm
+        self.world_size, self.pg = world_size, process_group
+        self.inv_batch = 1.0 / (batch_size * world_size)
+        self.n = model.n_classes
+        self.use_graph = use_graph
+        B, T = self.B, self.T
+
+        self.arena = ParamArena(model, dev)
+        self.enc_a = model.audio_net.engine(B, self.F_, self.Tt)
+        self.enc_v = model.visual_net.engine(B * T, self.H, self.W)
+        # static inputs (graph replay needs fixed addresses)
+        self.spec_in = torch.zeros(B, self.F_, self.Tt, device=dev)
+        self.image_in = torch.zeros(B, 3, T, self.H, self.W, device=dev)
+        self.label_in = torch.zeros(B, device=dev, dtype=torch.int64)
+        self.a8 = torch.empty(B, self.F_, self.Tt, 8, device=dev, dtype=torch.bfloat16)
+        self.v8 = torch.empty(B * T, self.H, self.W, 8, device=dev, dtype=torch.bfloat16)
+        D = 512
+        self.a_feat, self.v_feat = torch.empty(B, D, device=dev), torch.empty(B, D, device=dev)
+        self.da, self.dv = torch.empty(B, D, device=dev), torch.empty(B, D, device=dev)
+        self.logits = torch.empty(3, B, self.n, device=dev)
+        self.head_scratch = torch.empty(ops.head_scratch_floats(B, self.n) + 64, device=dev)
+        self.stats = torch.zeros(8, device=dev)  # [0:3] losses Lf,La,Lv  [4:8] norm, coef, audio, visual
+        self.losses = self.arena.grad[self.arena.numel:self.arena.numel + 3]
+        self._bn_counters = [m.num_batches_tracked for m in model.modules()
+                             if isinstance(m, torch.nn.BatchNorm2d)]
+        self._init_head()
+        self.stream_a, self.stream_v = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.steps_done = 0
+        self._graph = None
+        self._graph_lr = None
+        self.kernel_launches = None
+
+    # ------------------------------------------------------------------ heads
+    def _init_head(self):
+        fm, B, n, dev = self.model.fusion_module, self.B, self.n, self.device
+        if isinstance(fm, GatedFusion_DGL):
+            z = lambda *s: torch.empty(*s, device=dev)
+            self.g = dict(hx=z(B, 512), hy=z(B, 512), mo=z(B, 512), mx=z(B, 512), my=z(B, 512),
+                          dl=z(3, B, n), dmx=z(B, 512), dmy=z(B, 512), dhx=z(B, 512), dhy=z(B, 512),
+                          sc=z(B))
+        elif isinstance(fm, FiLM_DGL):
+            from .film import FilmHead
+            self.film = FilmHead(fm, B, n, dev)
+
+    def _head(self):
+        fm, B, n, D = self.model.fusion_module, self.B, self.n, 512
+        if isinstance(fm, ConcatFusion_DGL):
+            W, b = fm.fc_out.weight, fm.fc_out.bias
+            ops.dgl_head_linear(0, self.a_feat, self.v_feat, W.data_ptr(), W.data_ptr() + 4 * D, 2 * D,
+                                b.data, None, self.label_in, self.alpha, self.inv_batch, self.logits,
+                                self.losses, self.da, self.dv, W.grad.data_ptr(), W.grad.data_ptr() + 4 * D,
+                                2 * D, b.grad, None, self.head_scratch, B, D, n)
+        elif isinstance(fm, SumFusion_DGL):
+            ops.dgl_head_linear(1, self.a_feat, self.v_feat, fm.fc_x.weight.data_ptr(),
+                                fm.fc_y.weight.data_ptr(), D, fm.fc_x.bias.data, fm.fc_y.bias.data,
+                                self.label_in, self.alpha, self.inv_batch, self.logits, self.losses,
+                                self.da, self.dv, fm.fc_x.weight.grad.data_ptr(),
+                                fm.fc_y.weight.grad.data_ptr(), D, fm.fc_x.bias.grad, fm.fc_y.bias.grad,
+                                self.head_scratch, B, D, n)
+        elif isinstance(fm, GatedFusion_DGL):
+            self._head_gated(fm)
+        else:
+            self.film.run(self)
+
+    def _head_gated(self, fm):
+        """reference fusion_modules.py:230-250 with the DGL routing: fc_out <- Lf; a, v <- alpha*La/Lv
+        through fc_out, the gates and fc_x / fc_y; fc_x / fc_y themselves get no gradient."""
+        g, B, n = self.g, self.B, self.n
+        Wo, bo = fm.fc_out.weight, fm.fc_out.bias
+        ops.linear_fwd(self.a_feat, fm.fc_x.weight.data, fm.fc_x.bias.data, g["hx"], B, 512, 512)
+        ops.linear_fwd(self.v_feat, fm.fc_y.weight.data, fm.fc_y.bias.data, g["hy"], B, 512, 512)
+        ops.gated_fwd(g["hx"], g["hy"], g["mo"], g["mx"], g["my"])
+        for i, m in enumerate((g["mo"], g["mx"], g["my"])):
+            ops.linear_fwd(m, Wo.data, bo.data, self.logits[i], B, 512, n)
+            gs = self.inv_batch if i == 0 else self.alpha * self.inv_batch
+            ops.softmax_ce(self.logits[i], self.label_in, self.inv_batch, gs, self.losses[i:i + 1], g["dl"][i],
+                           g["sc"], B, n)
+        ops.linear_bwd(g["dl"][0], g["mo"], None, None, Wo.grad, bo.grad, B, 512, n)          # Lf -> fc_out
+        ops.linear_bwd(g["dl"][1], None, Wo.data, g["dmx"], None, None, B, 512, n)
+        ops.linear_bwd(g["dl"][2], None, Wo.data, g["dmy"], None, None, B, 512, n)
+        ops.gated_bwd(g["hx"], g["hy"], g["dmx"], g["dmy"], g["dhx"], g["dhy"])
+        ops.linear_bwd(g["dhx"], None, fm.fc_x.weight.data, self.da, None, None, B, 512, 512)
+        ops.linear_bwd(g["dhy"], None, fm.fc_y.weight.data, self.dv, None, None, B, 512, 512)
+
+    # ------------------------------------------------------------------ the step
+    def _enqueue(self, lr, first):
+        """Enqueue one full step on the current stream (+ the two encoder streams)."""
+        B, T = self.B, self.T
+        main = torch.cuda.current_stream()
+        sa, sv = self.stream_a, self.stream_v
+        sa.wait_stream(main)
+        sv.wait_stream(main)
+        with torch.cuda.stream(sa):
+            ops.layout_ncthw_to_nhwc8(self.spec_in, self.a8, B, 1, 1, self.F_, self.Tt)
+            fa = self.enc_a.forward(self.a8)
+            ops.gap_fwd(fa, self.a_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
+        with torch.cuda.stream(sv):
+            ops.layout_ncthw_to_nhwc8(self.image_in, self.v8, B, 3, T, self.H, self.W)
+            fv = self.enc_v.forward(self.v8)
+            ops.gap_fwd(fv, self.v_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
+        main.wait_stream(sa)
+        main.wait_stream(sv)
+        self._head()
+        sa.wait_stream(main)
+        sv.wait_stream(main)
+        with torch.cuda.stream(sa):
+            ops.gap_bwd(self.da, self.enc_a.g_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
+            self.enc_a.backward(self.a8)
+        with torch.cuda.stream(sv):
+            ops.gap_bwd(self.dv, self.enc_v.g_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
+            self.enc_v.backward(self.v8)
+        main.wait_stream(sa)
+        main.wait_stream(sv)
+        ar = self.arena
+        if self.world_size > 1:
+            # each rank scaled its CE by 1/B_global, so a plain SUM reproduces the reference's
+            # full-batch mean (DataParallel gathers logits, main_dgl.py:102-104); BN stays per replica
+            torch.distributed.all_reduce(ar.grad, group=self.pg)
+        ops.grad_stats(ar.grad, ar.numel, ar.seg_end, ar.seg_group, ar.seg_inv, ar.nseg, self.max_norm,
+                       ar.scratch, self.stats[4:8])
+        ops.sgd_momentum(ar.param, ar.grad, ar.momentum, ar.numel, lr, self.mu, self.wd, first, self.stats[4:8])
+        self.enc_a.repack()
+        self.enc_v.repack()
+        self.stats[0:3].copy_(self.losses)
+        torch._foreach_add_(self._bn_counters, 1)
+
+    def load_inputs(self, spec, image, label):
+        """Copy a batch (host or device tensors of the reference contract) into the static inputs."""
+        if spec.data_ptr() != self.spec_in.data_ptr():
+            self.spec_in.copy_(spec, non_blocking=True)
+        if image.data_ptr() != self.image_in.data_ptr():
+            self.image_in.copy_(image, non_blocking=True)
+        if label.data_ptr() != self.label_in.data_ptr():
+            self.label_in.copy_(label, non_blocking=True)
+
+    def step(self, spec=None, image=None, label=None, lr=None):
+        """Run one training step; returns the device tensor `stats` (8 floats, see __init__)."""
+        if lr is not None:
+            self.lr = lr
+        if spec is not None:
+            self.load_inputs(spec, image, label)
+        first = self.steps_done == 0
+        if first or not self.use_graph:
+            self._enqueue(self.lr, first)
+        else:
+            if self._graph is None or self._graph_lr != self.lr:
+                torch.cuda.synchronize()
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._enqueue(self.lr, False)
+                self._graph_lr = self.lr
+                # capture does not execute: replay below runs this step
+            self._graph.replay()
+        self.steps_done += 1
+        return self.stats
+
+    def read_stats(self):
+        """One D2H copy: (Lf, La, Lv, grad_norm, clip_coef, audio_grad_sum, visual_grad_sum)."""
+        s = self.stats.tolist()
+        return s[0], s[1], s[2], s[4], s[5], s[6], s[7]

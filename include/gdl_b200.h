@@ -111,12 +111,14 @@ int gdl_gap_fwd(const void* x, float* out, int B, int G, int C, gdl_stream_t s);
 int gdl_gap_bwd(const float* dout, void* dx, int B, int G, int C, gdl_stream_t s);
 
 /* ---- heads --------------------------------------------------------------------------- */
-/* Generic Linear (reference models/fusion_modules.py nn.Linear call sites): y = x W^T + b. */
-int gdl_linear_fwd(const float* x, const float* W, const float* b, float* y, int B, int In,
+/* Generic Linear (reference models/fusion_modules.py nn.Linear call sites): y = x W^T + b.
+ * W is [Out][In] with row stride ldw floats (so a column block of a wider matrix works). */
+int gdl_linear_fwd(const float* x, const float* W, int ldw, const float* b, float* y, int B, int In,
                    int Out, gdl_stream_t s);
-/* dx = dy W (if dx), dW (+)= dy^T x, db (+)= sum dy (if dW/db); accumulate: 0 overwrite, 1 add. */
-int gdl_linear_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW,
-                   float* db, int B, int In, int Out, int accumulate, gdl_stream_t s);
+/* dx = dy W (if dx), dW (+)= dy^T x (row stride lddw), db (+)= sum dy (if dW / db);
+ * accumulate: 0 overwrite, 1 add. */
+int gdl_linear_bwd(const float* dy, const float* x, const float* W, int ldw, float* dx, float* dW,
+                   int lddw, float* db, int B, int In, int Out, int accumulate, gdl_stream_t s);
 
 /* Fused DGL head, forward + 3x softmax-CE + truncated backward in one pass over the logits
  * (reference models/fusion_modules.py:51-59 ConcatFusion_DGL / :22-30 SumFusion_DGL,
