@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — DGL training-step throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this repo's CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1     # CPU arm (oracle port, host cores)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one DGL training step (reference main_dgl.py:93-158) on one synthetic batch of the
+CREMA-D shape (spec 257x188, 3 frames of 3x224x224, 6 classes), ConcatFusion_DGL, fp32 master
+weights, bf16 activations, fp32 accumulation.  Per-GPU batch is fixed (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value`: inputs already resident in HBM; `e2e`: the same step
+through DGLStep.step() with pinned-host inputs copied H2D and the 7-float result read D2H
+inside the timed region.  `roofline`: the dominant kernel class (implicit-GEMM convolutions),
+algorithmic FLOPs / CUDA-event time measured in an instrumented pass after the timed region.
+`cpu_baseline`: the CPU oracle port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "iccv2025-gdl_b200"))
+
+METRIC = "DGL train samples/sec (CREMA-D shape)"
+UNIT = "samples/s"
+TRAIN_GFLOP_PER_SAMPLE = {"CREMAD": 42.57, "KineticSound": 50.56, "VGGSound": 50.56}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.f = gpu_index, None, None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def cpu_oracle_throughput(fusion, dataset, shape, batch, steps, warmup, threads=None):
+    """The reference's algorithm on the host cores (oracle port; /root/reference cannot travel)."""
+    import torch
+    from oracle import dgl_oracle as O
+    from oracle.synth import make_batch
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = O.init_state(fusion, dataset, 0)
+    mom = {}
+    n = O.N_CLASSES[dataset]
+    data = make_batch(batch, n, shape, seed=1)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.dgl_step(sd, mom, *data, fusion=fusion, alpha=4.0, lr=0.001)
+        t1 = time.perf_counter()
+        if s >= warmup:
+            times.append(t1 - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec, threads
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = a.cpu_batch
+    v, sec, threads = cpu_oracle_throughput(a.fusion, a.dataset, a.dataset, batch, a.steps, a.warmup)
+    sample = "%d timed steps of batch %d (CREMA-D shape, %s fusion) after %d warm-up" % (
+        a.steps, batch, a.fusion, a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, batch, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(a, batch_per_gpu, n):
+    return {"workload": "%s-shape DGL step, ResNet-18 audio+visual, %sFusion_DGL, batch %d per GPU x %d GPU, "
+                        "synthetic" % ("CREMA-D" if a.dataset == "CREMAD" else a.dataset,
+                                       a.fusion.capitalize(), batch_per_gpu, n),
+            "global_batch": batch_per_gpu * n, "parallelism": "dp%d" % n,
+            "l2": "per-step inputs (%.0f MB) and activations (GBs) exceed the 126 MB L2; no flush needed"
+                  % (batch_per_gpu * (257 * 188 + 3 * 3 * 224 * 224) * 4 / 1e6)}
+
+
+def run_gpu(a):
+    import torch
+    import torch.distributed as dist
+    import gdl_b200
+    from gdl_b200 import ops
+    from gdl_b200.step import DGLStep
+    from oracle.synth import SHAPES, make_batch  # synthetic-shape table only (no oracle compute here)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    n_cls = {"CREMAD": 6, "KineticSound": 34, "VGGSound": 309}[a.dataset]
+    Fq, Tt, T, H, W = SHAPES[a.dataset]
+    B = a.batch
+    args = argparse.Namespace(dataset=a.dataset, fusion_method=a.fusion, modality="full")
+    gdl_b200.setup_seed(0)
+    model = gdl_b200.AVClassifier_DGL(args)
+    model.apply(gdl_b200.weight_init)
+    model.to(dev).train()
+    step = DGLStep(model, B, (Fq, Tt), (T, H, W), alpha=4.0, lr=0.001, world_size=world, process_group=pg,
+                   use_graph=not a.no_graph)
+    spec, image, label = make_batch(B, n_cls, a.dataset, seed=1 + rank)
+    spec_h, image_h, label_h = spec.pin_memory(), image.pin_memory(), label.pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (spec_h, image_h, label_h))
+    step.load_inputs(spec_h, image_h, label_h)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n_steps):
+            if e2e:
+                step.step(spec_h, image_h, label_h)
+                step.read_stats()          # D2H of the step's result (7 floats), syncs the step
+            else:
+                step.step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item()
+
+    launches0 = ops.LAUNCHES
+    for _ in range(max(a.warmup, 3)):
+        step.step()
+    torch.cuda.synchronize()
+    per_step_launches = None
+    if a.no_graph:
+        per_step_launches = (ops.LAUNCHES - launches0) // max(a.warmup, 3)
+    else:
+        # step 0 ran eagerly: its count is the per-step kernel count (graph replays launch the same kernels)
+        per_step_launches = step.launches_per_step
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, wall_ms = timed(a.steps, e2e=False)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step.step(spec_h, image_h, label_h)
+    ms_e2e, _ = timed(a.steps, e2e=True)
+    stats = step.read_stats()
+
+    value = B * world * a.steps / (ms / 1e3)
+    e2e_value = B * world * a.steps / (ms_e2e / 1e3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(a, B, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": per_step_launches * a.steps,
+            "launches_per_step": per_step_launches,
+            "clocks": clocks,
+            "final_losses": {"Lf": stats[0], "La": stats[1], "Lv": stats[2]},
+            "wall_ms_per_step": wall_ms / a.steps}
+
+    if rank == 0 and not a.no_roofline:
+        line["roofline"], line["kernel_breakdown"] = roofline_pass(step, torch, ops, B)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        tf_peak, _, how = measured_peaks()
+        gf = TRAIN_GFLOP_PER_SAMPLE[a.dataset]
+        line["step_tensor_frac"] = {"achieved_tflops": value / world * gf / 1e3, "peak_tflops": tf_peak,
+                                    "frac": value / world * gf / 1e3 / tf_peak, "peak_source": how,
+                                    "gflop_per_sample": gf}
+        if world == 1 and not a.no_cpu:
+            v, sec, threads = cpu_oracle_throughput(a.fusion, a.dataset, a.dataset, a.cpu_batch, 2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "2 timed steps of batch %d after 1 warm-up (oracle port, fp32, "
+                                              "torch %s CPU)" % (a.cpu_batch, torch.__version__)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_pass(step, torch, ops, B):
+    """One instrumented eager step on a single stream: CUDA events around every op.  Returns the
+    roofline object of the dominant kernel class and a per-class breakdown."""
+    tf_peak, hbm_peak, how = measured_peaks()
+    torch.cuda.synchronize()
+    ops.TIMING = []
+    saved = step.stream_a, step.stream_v, step.use_graph
+    cur = torch.cuda.current_stream()
+    step.stream_a = step.stream_v = cur
+    step.use_graph = False
+    try:
+        step.step()
+        torch.cuda.synchronize()
+        recs = ops.TIMING
+    finally:
+        ops.TIMING = None
+        step.stream_a, step.stream_v, step.use_graph = saved
+    agg = {}
+    for name, e0, e1, work in recs:
+        ms = e0.elapsed_time(e1)
+        d = agg.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+        d["ms"] += ms
+        d["launches"] += 1
+        if work:
+            d[work[0]] += work[1]
+    total = sum(d["ms"] for d in agg.values())
+    breakdown = {}
+    for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        e = {"ms": round(d["ms"], 3), "share": round(d["ms"] / total, 4), "ops": d["launches"]}
+        if d["flops"]:
+            e["tflops"] = round(d["flops"] / d["ms"] / 1e9, 1)
+        if d["bytes"]:
+            e["gbs"] = round(d["bytes"] / d["ms"] / 1e6, 1)
+        breakdown[name] = e
+    conv = [agg[k] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad") if k in agg]
+    flops = sum(d["flops"] for d in conv)
+    ms = sum(d["ms"] for d in conv)
+    nl = sum(d["launches"] for d in conv)
+    ach = flops / ms / 1e9
+    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_wgrad_kernel (tcgen05 implicit GEMM; "
+                                         "fwd+dgrad+wgrad aggregated over %d launches)" % nl,
+            "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+            "peak_source": how, "share_of_step": round(ms / total, 4),
+            "avg_launch_ms": ms / nl, "flops_per_launch": flops / nl}
+    return roof, breakdown
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="gdl_b200", choices=["gdl_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE configs[1])")
+    ap.add_argument("--cpu-batch", type=int, default=64, help="CPU arm batch (BASELINE configs[0])")
+    ap.add_argument("--fusion", default="concat")
+    ap.add_argument("--dataset", default="CREMAD")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        if a.steps > 3:
+            a.steps = 3          # bounded sample: each CPU step is several seconds
+        a.warmup = min(a.warmup, 1)
+        run_reference(a)
+    else:
+        run_gpu(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,7 +68,7 @@ class _ConvBN:
         ops.conv_pack_weights(self.d, self.ci_real, self.conv.weight.data, self.wp, self.wT)
 
     def forward(self, eng, inp, res=None, training=True):
-        ops.conv_fwd(self.d, inp, self.wp, self.x)
+        ops.conv_fwd(self.d, inp, self.wp, self.x, self.ci_real)
         bn = self.bn
         if training:
             ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,

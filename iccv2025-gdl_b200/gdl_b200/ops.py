@@ -3,6 +3,7 @@ torch's current CUDA stream, check the status.  PyTorch is plumbing only (memory
 every computation below runs in libgdl_b200.so.  No fallbacks.
 """
 import ctypes as C
+import functools
 
 import torch
 
@@ -10,6 +11,32 @@ from . import _lib
 from ._lib import ConvDesc, check
 
 _initialised = set()
+
+# Kernel-launch accounting (bench.py's "gpu_launches") and optional per-op CUDA-event timing
+# (bench.py's roofline leg).  LAUNCHES counts kernels of libgdl_b200.so enqueued by this process.
+LAUNCHES = 0
+TIMING = None  # when a list: (name, start_event, end_event, work) is appended per op
+
+
+def _op(name, kernels, work=None):
+    """Decorator: count launches; when TIMING is a list, bracket the op with CUDA events on the
+    launching stream.  work(*args) -> ("flops"|"bytes", amount) is the ALGORITHMIC work."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kw):
+            global LAUNCHES
+            LAUNCHES += kernels(*args, **kw) if callable(kernels) else kernels
+            if TIMING is None:
+                return fn(*args, **kw)
+            st = torch.cuda.current_stream()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            out = fn(*args, **kw)
+            e1.record(st)
+            TIMING.append((name, e0, e1, work(*args, **kw) if work else None))
+            return out
+        return wrapper
+    return deco
 
 
 def _stream():
@@ -23,6 +50,15 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _addr(t):
+    """Raw device address; accepts a tensor, an int address or None."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
 def init(device=None):
     lib = _lib.load()
     dev = torch.cuda.current_device() if device is None else int(device)
@@ -32,6 +68,7 @@ def init(device=None):
     return lib
 
 
+# ---------------------------------------------------------------------------------- convolution
 def conv_desc(N, Hi, Wi, Ci, Co, R, S, stride, pad):
     Ho = (Hi + 2 * pad - R) // stride + 1
     Wo = (Wi + 2 * pad - S) // stride + 1
@@ -46,27 +83,39 @@ def conv_wgrad_workspace_bytes(d):
     return int(_lib.load().gdl_conv_wgrad_workspace_bytes(C.byref(d)))
 
 
+def conv_flops(d, ci_real=None):
+    """Algorithmic FLOPs of one conv pass (fwd == dgrad == wgrad): 2*M*Co*R*S*Ci_real."""
+    ci = ci_real if ci_real is not None else d.Ci
+    return 2.0 * d.N * d.Ho * d.Wo * d.Co * d.R * d.S * ci
+
+
+@_op("pack_weights", 1)
 def conv_pack_weights(d, ci_real, w_oihw, w_packed, w_packed_T=None):
     check(_lib.load().gdl_conv_pack_weights(C.byref(d), ci_real, _ptr(w_oihw), _ptr(w_packed),
                                             _ptr(w_packed_T), _stream()), "gdl_conv_pack_weights")
 
 
-def conv_fwd(d, x, w_packed, y):
+@_op("conv_fwd", 1, lambda d, x, w, y, ci_real=None: ("flops", conv_flops(d, ci_real)))
+def conv_fwd(d, x, w_packed, y, ci_real=None):
     check(_lib.load().gdl_conv_fwd(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(y), _stream()),
           "gdl_conv_fwd")
 
 
+@_op("conv_dgrad", 1, lambda d, *a, **k: ("flops", conv_flops(d)))
 def conv_dgrad(d, dy, w_packed_T, dx, add_src=None, add_mode=0):
     check(_lib.load().gdl_conv_dgrad(C.byref(d), _ptr(dy), _ptr(w_packed_T), _ptr(dx),
                                      _ptr(add_src), add_mode, _stream()), "gdl_conv_dgrad")
 
 
+@_op("conv_wgrad", 2, lambda d, ci_real, *a, **k: ("flops", conv_flops(d, ci_real)))
 def conv_wgrad(d, ci_real, x, dy, dw_oihw, workspace):
     check(_lib.load().gdl_conv_wgrad(C.byref(d), ci_real, _ptr(x), _ptr(dy), _ptr(dw_oihw),
                                      _ptr(workspace), workspace.numel() * workspace.element_size(),
                                      _stream()), "gdl_conv_wgrad")
 
 
+# ---------------------------------------------------------------------------------- elementwise
+@_op("layout", 1, lambda src, dst, B, Cc, T, H, W: ("bytes", B * T * H * W * (4.0 * Cc + 16.0)))
 def layout_ncthw_to_nhwc8(src, dst, B, Cc, T, H, W):
     check(_lib.load().gdl_layout_ncthw_to_nhwc8(_ptr(src), _ptr(dst), B, Cc, T, H, W, _stream()),
           "gdl_layout_ncthw_to_nhwc8")
@@ -76,6 +125,7 @@ def bn_partial_floats(P, Cc):
     return int(_lib.load().gdl_bn_partial_floats(P, Cc))
 
 
+@_op("bn_stats", 2, lambda x, P, Cc, *a: ("bytes", 2.0 * P * Cc))
 def bn_stats(x, P, Cc, partial, gamma, beta, eps, momentum, running_mean, running_var, mean,
              invstd, scale, shift):
     check(_lib.load().gdl_bn_stats(_ptr(x), P, Cc, _ptr(partial), _ptr(gamma), _ptr(beta), eps,
@@ -83,49 +133,53 @@ def bn_stats(x, P, Cc, partial, gamma, beta, eps, momentum, running_mean, runnin
                                    _ptr(invstd), _ptr(scale), _ptr(shift), _stream()), "gdl_bn_stats")
 
 
+@_op("bn_apply", 1, lambda x, res, y, P, Cc, *a: ("bytes", (4.0 + (2.0 if res is not None else 0.0)) * P * Cc))
 def bn_apply(x, res, y, P, Cc, scale, shift, relu):
     check(_lib.load().gdl_bn_apply(_ptr(x), _ptr(res), _ptr(y), P, Cc, _ptr(scale), _ptr(shift),
                                    int(relu), _stream()), "gdl_bn_apply")
 
 
+@_op("bn_bwd", 3, lambda dy, y, x, dz, dx, P, Cc, *a: ("bytes", ((8.0 if a[-1] else 4.0) + 6.0) * P * Cc))
 def bn_bwd(dy, y, x, dz, dx, P, Cc, gamma, mean, invstd, partial, dgamma, dbeta, relu):
     check(_lib.load().gdl_bn_bwd(_ptr(dy), _ptr(y), _ptr(x), _ptr(dz), _ptr(dx), P, Cc, _ptr(gamma),
                                  _ptr(mean), _ptr(invstd), _ptr(partial), _ptr(dgamma), _ptr(dbeta),
                                  int(relu), _stream()), "gdl_bn_bwd")
 
 
+def _pool_bytes(a, b, c, N, H, W, Cc, Ho, Wo):
+    return ("bytes", N * Cc * (2.0 * H * W + 3.0 * Ho * Wo))
+
+
+@_op("maxpool_fwd", 1, _pool_bytes)
 def maxpool_fwd(x, y, argmax, N, H, W, Cc, Ho, Wo):
     check(_lib.load().gdl_maxpool_fwd(_ptr(x), _ptr(y), _ptr(argmax), N, H, W, Cc, Ho, Wo, _stream()),
           "gdl_maxpool_fwd")
 
 
+@_op("maxpool_bwd", 1, _pool_bytes)
 def maxpool_bwd(dy, argmax, dx, N, H, W, Cc, Ho, Wo):
     check(_lib.load().gdl_maxpool_bwd(_ptr(dy), _ptr(argmax), _ptr(dx), N, H, W, Cc, Ho, Wo, _stream()),
           "gdl_maxpool_bwd")
 
 
+@_op("gap_fwd", 1, lambda x, out, B, G, Cc: ("bytes", 2.0 * B * G * Cc))
 def gap_fwd(x, out, B, G, Cc):
     check(_lib.load().gdl_gap_fwd(_ptr(x), _ptr(out), B, G, Cc, _stream()), "gdl_gap_fwd")
 
 
+@_op("gap_bwd", 1, lambda dout, dx, B, G, Cc: ("bytes", 2.0 * B * G * Cc))
 def gap_bwd(dout, dx, B, G, Cc):
     check(_lib.load().gdl_gap_bwd(_ptr(dout), _ptr(dx), B, G, Cc, _stream()), "gdl_gap_bwd")
 
 
-def _addr(t):
-    """Raw device address; accepts a tensor, an int address or None."""
-    if t is None:
-        return None
-    if isinstance(t, int):
-        return C.c_void_p(t)
-    return C.c_void_p(t.data_ptr())
-
-
+# ---------------------------------------------------------------------------------- heads
+@_op("linear_fwd", 1)
 def linear_fwd(x, W, b, y, B, In, Out, ldw=None):
     check(_lib.load().gdl_linear_fwd(_ptr(x), _addr(W), ldw or In, _ptr(b), _ptr(y), B, In, Out, _stream()),
           "gdl_linear_fwd")
 
 
+@_op("linear_bwd", lambda dy, x, W, dx, dW, *a, **k: (dx is not None) + (dW is not None))
 def linear_bwd(dy, x, W, dx, dW, db, B, In, Out, accumulate=False, ldw=None, lddw=None):
     check(_lib.load().gdl_linear_bwd(_ptr(dy), _ptr(x), _addr(W), ldw or In, _ptr(dx), _addr(dW),
                                      lddw or In, _ptr(db), B, In, Out, int(accumulate), _stream()),
@@ -136,6 +190,7 @@ def head_scratch_floats(B, n):
     return int(_lib.load().gdl_head_scratch_floats(B, n))
 
 
+@_op("dgl_head", 2)
 def dgl_head_linear(kind, a, v, Wx_ptr, Wy_ptr, ldw, bx, by, labels, alpha, inv_batch, logits, losses,
                     da, dv, dWx_ptr, dWy_ptr, lddw, dbx, dby, scratch, B, D, n):
     """Wx_ptr/Wy_ptr/dWx_ptr/dWy_ptr are raw integer device addresses (they may point into the
@@ -148,31 +203,37 @@ def dgl_head_linear(kind, a, v, Wx_ptr, Wy_ptr, ldw, bx, by, labels, alpha, inv_
           "gdl_dgl_head_linear")
 
 
+@_op("softmax_ce", 2)
 def softmax_ce(logits, labels, loss_scale, grad_scale, loss_out, dlogits, scratch, B, n):
     check(_lib.load().gdl_softmax_ce(_ptr(logits), _ptr(labels), loss_scale, grad_scale, _ptr(loss_out),
                                      _ptr(dlogits), _ptr(scratch), B, n, _stream()), "gdl_softmax_ce")
 
 
+@_op("gated_fwd", 1)
 def gated_fwd(hx, hy, m_out, m_x, m_y):
     check(_lib.load().gdl_gated_fwd(_ptr(hx), _ptr(hy), _ptr(m_out), _ptr(m_x), _ptr(m_y), hx.numel(),
                                     _stream()), "gdl_gated_fwd")
 
 
+@_op("gated_bwd", 1)
 def gated_bwd(hx, hy, dm_x, dm_y, dhx, dhy):
     check(_lib.load().gdl_gated_bwd(_ptr(hx), _ptr(hy), _ptr(dm_x), _ptr(dm_y), _ptr(dhx), _ptr(dhy),
                                     hx.numel(), _stream()), "gdl_gated_bwd")
 
 
+# ---------------------------------------------------------------------------------- optimizer
 def optim_scratch_floats(numel, nseg):
     return int(_lib.load().gdl_optim_scratch_floats(numel, nseg))
 
 
+@_op("grad_stats", 2, lambda grad, numel, *a: ("bytes", 4.0 * numel))
 def grad_stats(grad, numel, seg_end, seg_group, seg_inv_numel, nseg, max_norm, scratch, stats):
     check(_lib.load().gdl_grad_stats(_ptr(grad), numel, _ptr(seg_end), _ptr(seg_group),
                                      _ptr(seg_inv_numel), nseg, max_norm, _ptr(scratch), _ptr(stats),
                                      _stream()), "gdl_grad_stats")
 
 
+@_op("sgd_momentum", 1, lambda param, grad, buf, numel, *a: ("bytes", 24.0 * numel))
 def sgd_momentum(param, grad, buf, numel, lr, mu, wd, first_step, stats):
     check(_lib.load().gdl_sgd_momentum(_ptr(param), _ptr(grad), _ptr(buf), numel, lr, mu, wd,
                                        int(first_step), _ptr(stats), _stream()), "gdl_sgd_momentum")

@@ -129,7 +129,7 @@ class DGLStep:
         self.steps_done = 0
         self._graph = None
         self._graph_lr = None
-        self.kernel_launches = None
+        self.launches_per_step = None
 
     # ------------------------------------------------------------------ heads
     def _init_head(self):
@@ -242,7 +242,9 @@ class DGLStep:
             self.load_inputs(spec, image, label)
         first = self.steps_done == 0
         if first or not self.use_graph:
+            n0 = ops.LAUNCHES
             self._enqueue(self.lr, first)
+            self.launches_per_step = ops.LAUNCHES - n0  # kernels of libgdl_b200.so per step
         else:
             if self._graph is None or self._graph_lr != self.lr:
                 torch.cuda.synchronize()

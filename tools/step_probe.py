@@ -64,7 +64,9 @@ def main():
             c32 = torch.nn.functional.cosine_similarity(gg, g32.flatten().double(), dim=0).item()
             cq = torch.nn.functional.cosine_similarity(gg, rq["grads"][k].flatten().double(), dim=0).item()
             ratio = (gg.norm() / (g32.double().norm() + 1e-30)).item()
-            cos_list[k] = (round(c32, 5), round(cq, 5), round(ratio, 4))
+            cqo = torch.nn.functional.cosine_similarity(rq["grads"][k].flatten().double(),
+                                                        g32.flatten().double(), dim=0).item()
+            cos_list[k] = (round(c32, 5), round(cq, 5), round(ratio, 4), round(cqo, 5))
             if c32 < worst32[0]:
                 worst32 = (c32, k)
             if cq < worstq[0]:
