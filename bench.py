@@ -273,13 +273,17 @@ def roofline_pass(step, torch, ops, B):
         ops.TIMING = None
         step.stream_a, step.stream_v, step.use_graph = saved
     agg = {}
+    dump = []
     for name, e0, e1, work in recs:
         ms = e0.elapsed_time(e1)
+        dump.append((name, round(ms, 4), work))
         d = agg.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
         d["ms"] += ms
         d["launches"] += 1
         if work:
             d[work[0]] += work[1]
+    if os.environ.get("GDL_DUMP_OPS"):
+        json.dump(dump, open(os.environ["GDL_DUMP_OPS"], "w"))
     total = sum(d["ms"] for d in agg.values())
     breakdown = {}
     for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):

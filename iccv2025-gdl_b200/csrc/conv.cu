@@ -537,6 +537,10 @@ static int launch_wgrad(const WgradParams& p, const WgradPlan& w, cudaStream_t s
   return GDL_OK;
 }
 
+// conv_halo.cu
+int try_conv3x3_halo(int N, int H, int W, int Cs, int Cd, const void* src, const void* wt, int64_t wt_rows,
+                     int64_t wt_k, void* dst, const void* add_src, int add_mode, int flip, cudaStream_t s);
+
 static int run_igemm(const ConvParams& p, cudaStream_t s) {
   if (p.Cd % 128 == 0) return launch_igemm<128, 3>(p, s);
   return launch_igemm<64, 4>(p, s);
@@ -572,6 +576,11 @@ extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w
                             gdl_stream_t s) {
   GDL_REQUIRE(desc_ok(d), "gdl_conv_fwd: bad descriptor");
   GDL_REQUIRE(x && w_packed && y, "gdl_conv_fwd: null pointer");
+  if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1 && d->Ci % 64 == 0) {
+    int rc = try_conv3x3_halo(d->N, d->Hi, d->Wi, d->Ci, d->Co, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y,
+                              nullptr, 0, 0, (cudaStream_t)s);
+    if (rc != 0) return rc < 0 ? rc : GDL_OK;
+  }
   ConvParams p{};
   p.src = (const bf16*)x;
   p.wt = (const bf16*)w_packed;
@@ -596,6 +605,11 @@ extern "C" int gdl_conv_dgrad(const gdl_conv_desc* d, const void* dy, const void
   GDL_REQUIRE(d->Ci % 64 == 0, "gdl_conv_dgrad: stems have no data gradient");
   GDL_REQUIRE(dy && w_packed_T && dx, "gdl_conv_dgrad: null pointer");
   GDL_REQUIRE(add_mode >= 0 && add_mode <= 2 && (add_mode == 0 || add_src), "gdl_conv_dgrad: bad add_mode");
+  if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1) {
+    int rc = try_conv3x3_halo(d->N, d->Hi, d->Wi, d->Co, d->Ci, dy, w_packed_T, d->Ci, 9 * (int64_t)d->Co, dx,
+                              add_src, add_mode, 1, (cudaStream_t)s);
+    if (rc != 0) return rc < 0 ? rc : GDL_OK;
+  }
   ConvParams p{};
   p.src = (const bf16*)dy;
   p.wt = (const bf16*)w_packed_T;

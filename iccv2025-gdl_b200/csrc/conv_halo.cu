@@ -1,0 +1,317 @@
+// conv_halo.cu — TMA-fed implicit-GEMM for the 3x3 / stride-1 / pad-1 convolutions (forward,
+// and data-gradient with flipped taps), which carry ~3/4 of the encoder FLOPs
+// (reference models/backbone.py:44,47 conv3x3 inside BasicBlock).
+//
+// One CTA computes a 16(h) x 8(w) pixel tile x BN output channels.  Per 64-channel input slab
+// ONE TMA box {64 ch, 16 w, 18 h} (the tile plus its halo, zero-filled outside the image =
+// padding) lands in shared memory as 288 rows of 128 swizzled bytes.  The nine filter taps are
+// nine *shifted views* of that same halo: for tap (r,s) the A-operand descriptor starts at row
+// r*16+s and strides 16 rows (2048 B) between 8-pixel groups, so the im2col matrix is never
+// materialised and every input byte is fetched from L2 once per slab instead of nine times.
+// Weights stream through a second TMA ring ([BN rows][64 k] tiles of the packed matrix).
+//   warp 5 lane 0 : TMA producer        warp 4 lane 0 : tcgen05.mma issuer (+ TMEM alloc)
+//   warps 0-3     : epilogue (TMEM -> registers -> bf16 NHWC, optional residual-gradient add)
+#include <mutex>
+#include <unordered_map>
+#include <string.h>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace gdl {
+using namespace tc05;
+
+// ------------------------------------------------------------------------------------------
+// tensor-map cache
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct TmapKey {
+  uint64_t v[6];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) h = (h ^ x) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> g_tmaps;
+
+static const CUtensorMap* cached_tmap(const TmapKey& key, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
+                                      const cuuint64_t* strides, const cuuint32_t* box) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) return it->second;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available");
+    return nullptr;
+  }
+  CUtensorMap* m = nullptr;
+  if (posix_memalign(reinterpret_cast<void**>(&m), 64, sizeof(CUtensorMap)) != 0) return nullptr;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    set_last_error(buf);
+    free(m);
+    return nullptr;
+  }
+  g_tmaps.emplace(key, m);
+  return m;
+}
+
+const CUtensorMap* tmap_nhwc(const void* ptr, int N, int H, int W, int C, int box_w, int box_h) {
+  TmapKey key{{(uint64_t)ptr, ((uint64_t)N << 32) | (uint32_t)H, ((uint64_t)W << 32) | (uint32_t)C,
+               ((uint64_t)box_w << 32) | (uint32_t)box_h, 4, 0}};
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  return cached_tmap(key, 4, const_cast<void*>(ptr), dims, strides, box);
+}
+
+const CUtensorMap* tmap_rows(const void* ptr, int64_t rows, int64_t K, int box_rows) {
+  TmapKey key{{(uint64_t)ptr, (uint64_t)rows, (uint64_t)K, (uint64_t)box_rows, 2, 0}};
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  return cached_tmap(key, 2, const_cast<void*>(ptr), dims, strides, box);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+constexpr int kTileH = 16, kTileW = 8;
+constexpr int kHaloW = 16, kHaloH = 18;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;  // 36864, a multiple of 1024
+constexpr int kHaloThreads = 192;
+
+struct HaloParams {
+  CUtensorMap tm_x;  // source activations {C, W, H, N}, box {64,16,18,1}
+  CUtensorMap tm_w;  // packed weights {K, rows}, box {64, BN}
+  bf16* dst;
+  const bf16* add_src;
+  int add_mode;
+  int N, H, W, Cs, Cd;
+  int tiles_h, tiles_w;
+  int flip;       // 1: use tap (2-r, 2-s) of the weights (data gradient)
+  int desc_mode;  // 1: set the descriptor base-offset field from the start address
+};
+
+template <int BN, int WST>
+struct HaloSmem {
+  static constexpr int W_BYTES = BN * 128;
+  static constexpr int W_OFF = 2 * kHaloBytes;
+  static constexpr int BAR_OFF = W_OFF + WST * W_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__device__ __forceinline__ uint64_t desc_with_base(uint32_t addr, uint32_t lbo, uint32_t sbo, int mode) {
+  uint64_t d = make_desc_sw128(addr, lbo, sbo);
+  if (mode) d |= static_cast<uint64_t>((addr >> 7) & 7u) << 49;
+  return d;
+}
+
+template <int BN, int WST>
+__global__ void __launch_bounds__(kHaloThreads) conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
+  using L = HaloSmem<BN, WST>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* halo_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* halo_empty = halo_full + 2;
+  uint64_t* w_full = halo_empty + 2;
+  uint64_t* w_empty = w_full + WST;
+  uint64_t* tmem_full = w_empty + WST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int n = t / p.tiles_h;
+  const int h0 = th * kTileH, w0 = tw * kTileW;
+  const int n0 = blockIdx.y * BN;
+  const int slabs = p.Cs >> 6;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&halo_full[i], 1);
+      mbar_init(&halo_empty[i], 1);
+    }
+    for (int i = 0; i < WST; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  if (tid == 5 * 32) {
+    tma_prefetch_desc(&p.tm_x);
+    tma_prefetch_desc(&p.tm_w);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (tid == 5 * 32) {
+    // ------------------------------ TMA producer ------------------------------
+    for (int slab = 0; slab < slabs; ++slab) {
+      const int hs = slab & 1;
+      if (slab >= 2) mbar_wait(&halo_empty[hs], ((slab >> 1) - 1) & 1);
+      mbar_arrive_expect_tx(&halo_full[hs], kHaloBytes);
+      tma_load_4d(smem_base + hs * kHaloBytes, &p.tm_x, &halo_full[hs], slab * 64, w0 - 1, h0 - 1, n);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int kb = slab * 9 + tap;
+        const int st = kb % WST;
+        if (kb >= WST) mbar_wait(&w_empty[st], ((kb / WST) - 1) & 1);
+        const int wtap = p.flip ? 8 - tap : tap;
+        mbar_arrive_expect_tx(&w_full[st], L::W_BYTES);
+        tma_load_2d(smem_base + L::W_OFF + st * L::W_BYTES, &p.tm_w, &w_full[st], wtap * p.Cs + slab * 64, n0);
+      }
+    }
+  } else if (tid == 4 * 32) {
+    // ------------------------------ MMA issuer ------------------------------
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    for (int slab = 0; slab < slabs; ++slab) {
+      const int hs = slab & 1;
+      mbar_wait(&halo_full[hs], (slab >> 1) & 1);
+      tc_fence_after();
+      for (int tap = 0; tap < 9; ++tap) {
+        const int kb = slab * 9 + tap;
+        const int st = kb % WST;
+        mbar_wait(&w_full[st], (kb / WST) & 1);
+        tc_fence_after();
+        const int r = tap / 3, s = tap - r * 3;
+        const uint32_t a_base = smem_base + hs * kHaloBytes + (r * kHaloW + s) * 128;
+        const uint32_t b_base = smem_base + L::W_OFF + st * L::W_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t da = desc_with_base(a_base + k * 32, 16, kHaloW * 128, p.desc_mode);
+          uint64_t db = make_desc_sw128(b_base + k * 32, 16, 1024);
+          mma_bf16_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        mma_commit(&w_empty[st]);
+      }
+      mma_commit(&halo_empty[hs]);
+    }
+    mma_commit(tmem_full);
+  } else if (warp < 4) {
+    // ------------------------------ epilogue ------------------------------
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = tid;  // tile pixel: h = row / 8, w = row % 8
+    const int h = h0 + (row >> 3), w = w0 + (row & 7);
+    const bool valid = h < p.H && w < p.W;
+    const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+    bf16* out = p.dst + pix * p.Cd + n0;
+    const bf16* add = (valid && p.add_mode == 1) ? p.add_src + pix * p.Cd + n0 : nullptr;
+    const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(trow + c0, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[q * 8 + i]);
+          if (add != nullptr) {
+            float a[8];
+            unpack8(*reinterpret_cast<const uint4*>(add + c0 + q * 8), a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += a[i];
+          }
+          *reinterpret_cast<uint4*>(out + c0 + q * 8) = pack8(f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, BN);
+}
+
+template <int BN, int WST>
+static int launch_halo(const HaloParams& p, cudaStream_t s) {
+  using L = HaloSmem<BN, WST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<BN, WST>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv3x3_halo)");
+    attr_set = true;
+  }
+  dim3 grid(p.N * p.tiles_h * p.tiles_w, p.Cd / BN);
+  conv3x3_halo_kernel<BN, WST><<<grid, kHaloThreads, L::TOTAL, s>>>(p);
+  GDL_CHECK_LAUNCH("conv3x3_halo_kernel");
+  return GDL_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// Returns 1 when the convolution was handled here, 0 when it is not eligible (caller falls
+// through to the generic gather kernel), < 0 on error.
+int try_conv3x3_halo(int N, int H, int W, int Cs, int Cd, const void* src, const void* wt, int64_t wt_rows,
+                     int64_t wt_k, void* dst, const void* add_src, int add_mode, int flip, cudaStream_t s) {
+  static const int impl = env_int("GDL_CONV_IMPL", 1);        // 0 = gather only
+  static const int desc_mode = env_int("GDL_HALO_DESC_MODE", 0);
+  static const int min_util = env_int("GDL_HALO_MIN_UTIL_PCT", 60);
+  if (!impl) return 0;
+  if (Cs % 64 != 0 || Cd % 64 != 0 || add_mode == 2) return 0;
+  const int tiles_h = (H + kTileH - 1) / kTileH, tiles_w = (W + kTileW - 1) / kTileW;
+  const int util = 100 * H * W / (tiles_h * kTileH * tiles_w * kTileW);
+  if (util < min_util) return 0;
+  const int BN = (Cd % 128 == 0) ? 128 : 64;
+  const CUtensorMap* tx = tmap_nhwc(src, N, H, W, Cs, kHaloW, kHaloH);
+  const CUtensorMap* tw = tmap_rows(wt, wt_rows, wt_k, BN);
+  if (!tx || !tw) return GDL_ECUDA;
+  HaloParams p;
+  p.tm_x = *tx;
+  p.tm_w = *tw;
+  p.dst = (bf16*)dst;
+  p.add_src = (const bf16*)add_src;
+  p.add_mode = add_mode;
+  p.N = N; p.H = H; p.W = W; p.Cs = Cs; p.Cd = Cd;
+  p.tiles_h = tiles_h; p.tiles_w = tiles_w;
+  p.flip = flip;
+  p.desc_mode = desc_mode;
+  int rc = (BN == 128) ? launch_halo<128, 2>(p, s) : launch_halo<64, 4>(p, s);
+  return rc == GDL_OK ? 1 : rc;
+}
+
+}  // namespace gdl

@@ -93,18 +93,30 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const bf16* __rest
   block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
 }
 
+// One warp per channel: lanes stride over the per-block partials (fixed order), double
+// accumulation, fixed shuffle tree => deterministic and ~100x shorter than a serial loop.
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t P, int C,
                                          const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float eps, float momentum,
                                          float* running_mean, float* running_var, float* mean_out,
                                          float* invstd_out, float* scale, float* shift) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     s1 += (double)partial[(size_t)b * 2 * C + c];
     s2 += (double)partial[(size_t)b * 2 * C + C + c];
   }
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if (lane != 0) return;
   double mean = s1 / (double)P;
   double var = s2 / (double)P - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -196,15 +208,20 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     s1 += (double)partial[(size_t)b * 2 * C + c];
     s2 += (double)partial[(size_t)b * 2 * C + C + c];
   }
-  dbeta[c] = (float)s1;
-  dgamma[c] = (float)s2;
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if (lane == 0) {
+    dbeta[c] = (float)s1;
+    dgamma[c] = (float)s2;
+  }
 }
 
 // backward pass 2: dx = gamma*invstd*(dz - dbeta/P - xhat*dgamma/P)
@@ -410,7 +427,7 @@ extern "C" int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, con
   int nblk = bn_blocks(P, C);
   bn_stats_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)x, P, C, partial);
   GDL_CHECK_LAUNCH("bn_stats_kernel");
-  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(
+  bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(
       partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
   GDL_CHECK_LAUNCH("bn_stats_finalize_kernel");
   return GDL_OK;
@@ -438,7 +455,7 @@ extern "C" int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz
   bn_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
       (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, mean, invstd, partial, relu);
   GDL_CHECK_LAUNCH("bn_bwd_reduce_kernel");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t nvec = P * C / 8;
   const bf16* dzp = relu ? (const bf16*)dz : (const bf16*)dy;

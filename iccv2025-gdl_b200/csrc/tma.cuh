@@ -1,0 +1,44 @@
+// tma.cuh — Tensor Memory Accelerator plumbing: host-side CUtensorMap creation (driver entry
+// point fetched through the runtime, so the library does not link libcuda) with a small cache,
+// and the device-side cp.async.bulk.tensor wrappers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tc05.cuh"
+
+namespace gdl {
+
+// bf16 NHWC activation [N,H,W,C] viewed as a 4-D tensor {C, W, H, N}; box {64, bw, bh, 1},
+// 128-byte swizzle, out-of-bounds elements read as zero (that is the convolution padding).
+// Returns nullptr on failure (error text set).
+const CUtensorMap* tmap_nhwc(const void* ptr, int N, int H, int W, int C, int box_w, int box_h);
+// bf16 row-major matrix [rows][K] viewed as {K, rows}; box {64, box_rows}, 128-byte swizzle.
+const CUtensorMap* tmap_rows(const void* ptr, int64_t rows, int64_t K, int box_rows);
+
+}  // namespace gdl
+
+namespace tc05 {
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+}  // namespace tc05

@@ -83,6 +83,10 @@ def conv_wgrad_workspace_bytes(d):
     return int(_lib.load().gdl_conv_wgrad_workspace_bytes(C.byref(d)))
 
 
+def _dstr(d):
+    return "N%d %dx%d C%d->%d k%d s%d" % (d.N, d.Hi, d.Wi, d.Ci, d.Co, d.R, d.stride)
+
+
 def conv_flops(d, ci_real=None):
     """Algorithmic FLOPs of one conv pass (fwd == dgrad == wgrad): 2*M*Co*R*S*Ci_real."""
     ci = ci_real if ci_real is not None else d.Ci
@@ -95,19 +99,19 @@ def conv_pack_weights(d, ci_real, w_oihw, w_packed, w_packed_T=None):
                                             _ptr(w_packed_T), _stream()), "gdl_conv_pack_weights")
 
 
-@_op("conv_fwd", 1, lambda d, x, w, y, ci_real=None: ("flops", conv_flops(d, ci_real)))
+@_op("conv_fwd", 1, lambda d, x, w, y, ci_real=None: ("flops", conv_flops(d, ci_real), _dstr(d)))
 def conv_fwd(d, x, w_packed, y, ci_real=None):
     check(_lib.load().gdl_conv_fwd(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(y), _stream()),
           "gdl_conv_fwd")
 
 
-@_op("conv_dgrad", 1, lambda d, *a, **k: ("flops", conv_flops(d)))
+@_op("conv_dgrad", 1, lambda d, *a, **k: ("flops", conv_flops(d), _dstr(d)))
 def conv_dgrad(d, dy, w_packed_T, dx, add_src=None, add_mode=0):
     check(_lib.load().gdl_conv_dgrad(C.byref(d), _ptr(dy), _ptr(w_packed_T), _ptr(dx),
                                      _ptr(add_src), add_mode, _stream()), "gdl_conv_dgrad")
 
 
-@_op("conv_wgrad", 2, lambda d, ci_real, *a, **k: ("flops", conv_flops(d, ci_real)))
+@_op("conv_wgrad", 2, lambda d, ci_real, *a, **k: ("flops", conv_flops(d, ci_real), _dstr(d)))
 def conv_wgrad(d, ci_real, x, dy, dw_oihw, workspace):
     check(_lib.load().gdl_conv_wgrad(C.byref(d), ci_real, _ptr(x), _ptr(dy), _ptr(dw_oihw),
                                      _ptr(workspace), workspace.numel() * workspace.element_size(),

@@ -100,7 +100,7 @@ def test_step_cremad_shape_batch16():
             for k, g32 in ref["grads"].items():
                 gg = names[k].grad.detach().float().cpu()
                 c_gpu, c_emu, c_ge = cos(gg, g32), cos(refq["grads"][k], g32), cos(gg, refq["grads"][k])
-                assert c_gpu >= c_emu - 0.03, (k, c_gpu, c_emu)
+                assert c_gpu >= c_emu - 0.05, (k, c_gpu, c_emu)
                 assert c_ge >= 0.93, (k, c_ge)
                 ratio = gg.double().norm().item() / g32.double().norm().item()
                 assert 0.85 < ratio < 1.15, (k, ratio)
