@@ -227,18 +227,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const __grid_c
   } else if (tid == kProducerThreads) {
     // ------------------------------ MMA issuer ------------------------------
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t ab_hi = desc_hi_sw128(1024), ab_lo0 = desc_lo_sw128(smem_base, 16);
     for (int kb = 0; kb < p.KB; ++kb) {
       const int st = kb % STAGES;
       mbar_wait(&full[st], (kb / STAGES) & 1);
       tc_fence_after();
-      const uint32_t sA = smem_base + st * L::STAGE_BYTES;
-      const uint32_t sB = sA + L::A_BYTES;
+      const uint32_t a_lo = ab_lo0 + st * (L::STAGE_BYTES >> 4);
+      const uint32_t b_lo = a_lo + (L::A_BYTES >> 4);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint64_t da = make_desc_sw128(sA + k * 32, 16, 1024);
-        uint64_t db = make_desc_sw128(sB + k * 32, 16, 1024);
-        mma_bf16_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-      }
+      for (int k = 0; k < 4; ++k)
+        mma_bf16_ss(tmem_base, desc_join(a_lo + 2 * k, ab_hi), desc_join(b_lo + 2 * k, ab_hi), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
       mma_commit(&empty[st]);
     }
     mma_commit(tmem_full);
@@ -393,22 +392,22 @@ __global__ void __launch_bounds__(kConvThreads) conv_wgrad_kernel(const __grid_c
   } else if (tid == kProducerThreads) {
     // ------------------------------ MMA issuer ------------------------------
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    const uint32_t mn_hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo_sw128(smem_base, 8192), b_lo0 = desc_lo_sw128(smem_base + L::B_OFF, 8192);
     for (int kbi = 0; kbi < nkb; ++kbi) {
       mbar_wait(&b_full[kbi & 1], (kbi >> 1) & 1);
       tc_fence_after();
-      const uint32_t sB = smem_base + L::B_OFF + (kbi & 1) * L::B_BYTES;
+      const uint32_t b_lo = b_lo0 + (kbi & 1) * (L::B_BYTES >> 4);
       for (int gi = 0; gi < Gc; ++gi) {
         const int ac = kbi * Gc + gi;
         const int st = ac % AST;
         mbar_wait(&a_full[st], (ac / AST) & 1);
         tc_fence_after();
-        const uint32_t sA = smem_base + st * L::A_BYTES;
+        const uint32_t a_lo = a_lo0 + st * (L::A_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t da = make_desc_sw128(sA + k * 2048, 8192, 1024);
-          uint64_t db = make_desc_sw128(sB + k * 2048, 8192, 1024);
-          mma_bf16_ss(tmem_base + gi * BN, da, db, idesc, (kbi | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss(tmem_base + gi * BN, desc_join(a_lo + k * (2048 >> 4), mn_hi),
+                      desc_join(b_lo + k * (2048 >> 4), mn_hi), idesc, (kbi | k) != 0 ? 1u : 0u);
         mma_commit(&a_empty[st]);
       }
       mma_commit(&b_empty[kbi & 1]);

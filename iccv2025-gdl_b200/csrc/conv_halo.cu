@@ -104,78 +104,91 @@ const CUtensorMap* tmap_rows(const void* ptr, int64_t rows, int64_t K, int box_r
 // kernel
 // ------------------------------------------------------------------------------------------
 constexpr int kTileH = 16, kTileW = 8;
-constexpr int kHaloW = 16, kHaloH = 18;
-constexpr int kHaloBytes = kHaloW * kHaloH * 128;  // 36864, a multiple of 1024
+// Halo box = tile + 1-pixel border, stored densely: pitch 10 rows per image row.  8-pixel row
+// groups of a shifted view then start at arbitrary 128-byte rows and straddle 1024-byte swizzle
+// atoms — legal because the tensor core (like TMA) swizzles on absolute smem address bits.
+constexpr int kHaloW = 10, kHaloH = 18;
+constexpr int kHaloBoxBytes = kHaloW * kHaloH * 128;                       // 23040 delivered by TMA
+constexpr int kHaloBytes = (kHaloBoxBytes + 1023) / 1024 * 1024;           // 23552 per stage
 constexpr int kHaloThreads = 192;
+constexpr int kOutBlkBytes = 128 * 128;            // one 64-channel block of a 128-pixel tile
 
 struct HaloParams {
-  CUtensorMap tm_x;  // source activations {C, W, H, N}, box {64,16,18,1}
-  CUtensorMap tm_w;  // packed weights {K, rows}, box {64, BN}
-  bf16* dst;
-  const bf16* add_src;
+  CUtensorMap tm_x;    // source activations {C, W, H, N}, box {64,16,18,1}
+  CUtensorMap tm_w;    // packed weights {K, rows}, box {64, BN}
+  CUtensorMap tm_out;  // destination {Cd, W, H, N}, box {64,8,16,1}
+  CUtensorMap tm_res;  // residual gradient (same geometry as tm_out); valid when add_mode == 1
   int add_mode;
   int N, H, W, Cs, Cd;
-  int tiles_h, tiles_w;
-  int flip;       // 1: use tap (2-r, 2-s) of the weights (data gradient)
-  int desc_mode;  // 1: set the descriptor base-offset field from the start address
+  int tiles_h, tiles_w, tiles_total;  // tiles_total includes the N-tile dimension (slowest)
+  int flip;                           // 1: use tap (2-r, 2-s) of the weights (data gradient)
 };
 
 template <int BN, int WST>
 struct HaloSmem {
+  static constexpr int HST = BN == 64 ? 4 : 3;  // halo ring depth (covers the TMA round trip)
   static constexpr int W_BYTES = BN * 128;
-  static constexpr int W_OFF = 2 * kHaloBytes;
-  static constexpr int BAR_OFF = W_OFF + WST * W_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int OUT_BYTES = (BN / 64) * kOutBlkBytes;
+  static constexpr int W_OFF = HST * kHaloBytes;
+  static constexpr int OUT_OFF = W_OFF + WST * W_BYTES;
+  static constexpr int RES_OFF = OUT_OFF + OUT_BYTES;
+  static constexpr int BAR_OFF = RES_OFF + OUT_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+  static_assert(TOTAL <= 227 * 1024, "halo kernel shared memory budget");
 };
 
-__device__ __forceinline__ uint64_t desc_with_base(uint32_t addr, uint32_t lbo, uint32_t sbo, int mode) {
-  uint64_t d = make_desc_sw128(addr, lbo, sbo);
-  if (mode) d |= static_cast<uint64_t>((addr >> 7) & 7u) << 49;
-  return d;
-}
-
+// Persistent: one CTA per SM loops over output tiles.  Three pipelines run concurrently:
+// TMA producer (halo + weight rings, optional residual tile) -> MMA issuer (two TMEM accumulator
+// buffers) -> epilogue warps (TMEM -> registers -> swizzled smem -> TMA store).
 template <int BN, int WST>
-__global__ void __launch_bounds__(kHaloThreads) conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
   using L = HaloSmem<BN, WST>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* halo_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* halo_empty = halo_full + 2;
-  uint64_t* w_full = halo_empty + 2;
+  constexpr int HST = L::HST;
+  uint64_t* halo_empty = halo_full + HST;
+  uint64_t* w_full = halo_empty + HST;
   uint64_t* w_empty = w_full + WST;
   uint64_t* tmem_full = w_empty + WST;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_full = tmem_empty + 2;
+  uint64_t* res_empty = res_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w;
-  t /= p.tiles_w;
-  const int th = t % p.tiles_h;
-  const int n = t / p.tiles_h;
-  const int h0 = th * kTileH, w0 = tw * kTileW;
-  const int n0 = blockIdx.y * BN;
   const int slabs = p.Cs >> 6;
+  const int kbs = slabs * 9;                  // weight tiles per output tile
+  const bool resident = kbs <= WST && p.Cd == BN;  // all weight tiles stay in smem for the CTA lifetime
+  const int tiles_img = p.tiles_h * p.tiles_w;
+  const int tiles_n = p.N * tiles_img;        // tiles per N-tile
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < HST; ++i) {
       mbar_init(&halo_full[i], 1);
       mbar_init(&halo_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
     }
     for (int i = 0; i < WST; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(tmem_full, 1);
+    mbar_init(res_full, 1);
+    mbar_init(res_empty, 128);
     fence_mbar_init();
   }
   if (warp == 4) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   if (tid == 5 * 32) {
     tma_prefetch_desc(&p.tm_x);
     tma_prefetch_desc(&p.tm_w);
+    tma_prefetch_desc(&p.tm_out);
   }
   tc_fence_before();
   __syncthreads();
@@ -185,82 +198,152 @@ __global__ void __launch_bounds__(kHaloThreads) conv3x3_halo_kernel(const __grid
 
   if (tid == 5 * 32) {
     // ------------------------------ TMA producer ------------------------------
-    for (int slab = 0; slab < slabs; ++slab) {
-      const int hs = slab & 1;
-      if (slab >= 2) mbar_wait(&halo_empty[hs], ((slab >> 1) - 1) & 1);
-      mbar_arrive_expect_tx(&halo_full[hs], kHaloBytes);
-      tma_load_4d(smem_base + hs * kHaloBytes, &p.tm_x, &halo_full[hs], slab * 64, w0 - 1, h0 - 1, n);
-      for (int tap = 0; tap < 9; ++tap) {
-        const int kb = slab * 9 + tap;
-        const int st = kb % WST;
-        if (kb >= WST) mbar_wait(&w_empty[st], ((kb / WST) - 1) & 1);
-        const int wtap = p.flip ? 8 - tap : tap;
-        mbar_arrive_expect_tx(&w_full[st], L::W_BYTES);
-        tma_load_2d(smem_base + L::W_OFF + st * L::W_BYTES, &p.tm_w, &w_full[st], wtap * p.Cs + slab * 64, n0);
+    int hcount = 0, wcount = 0, it = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+      const int nt = t / tiles_n;
+      int rem = t - nt * tiles_n;
+      const int n = rem / tiles_img;
+      rem -= n * tiles_img;
+      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+      const int h0 = th * kTileH, w0 = tw * kTileW, n0 = nt * BN;
+      for (int slab = 0; slab < slabs; ++slab, ++hcount) {
+        const int hs = hcount % HST;
+        if (hcount >= HST) mbar_wait(&halo_empty[hs], ((hcount / HST) - 1) & 1);
+        mbar_arrive_expect_tx(&halo_full[hs], kHaloBoxBytes);
+        tma_load_4d(smem_base + hs * kHaloBytes, &p.tm_x, &halo_full[hs], slab * 64, w0 - 1, h0 - 1, n);
+        if (resident && it > 0) continue;
+        for (int tap = 0; tap < 9; ++tap, ++wcount) {
+          const int st = wcount % WST;
+          if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
+          const int wtap = p.flip ? 8 - tap : tap;
+          mbar_arrive_expect_tx(&w_full[st], L::W_BYTES);
+          tma_load_2d(smem_base + L::W_OFF + st * L::W_BYTES, &p.tm_w, &w_full[st], wtap * p.Cs + slab * 64, n0);
+        }
+      }
+      if (p.add_mode == 1) {  // residual-gradient tile, consumed by the epilogue of this tile
+        if (it >= 1) mbar_wait(res_empty, (it - 1) & 1);
+        mbar_arrive_expect_tx(res_full, L::OUT_BYTES);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_load_4d(smem_base + L::RES_OFF + b * kOutBlkBytes, &p.tm_res, res_full, n0 + b * 64, w0, h0, n);
       }
     }
   } else if (tid == 4 * 32) {
     // ------------------------------ MMA issuer ------------------------------
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-    for (int slab = 0; slab < slabs; ++slab) {
-      const int hs = slab & 1;
-      mbar_wait(&halo_full[hs], (slab >> 1) & 1);
-      tc_fence_after();
-      for (int tap = 0; tap < 9; ++tap) {
-        const int kb = slab * 9 + tap;
-        const int st = kb % WST;
-        mbar_wait(&w_full[st], (kb / WST) & 1);
+    const uint32_t a_hi = desc_hi_sw128(kHaloW * 128), b_hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo_sw128(smem_base, 16), b_lo0 = desc_lo_sw128(smem_base + L::W_OFF, 16);
+    int hcount = 0, wcount = 0, it = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      if (it >= 2) {
+        mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1);
         tc_fence_after();
-        const int r = tap / 3, s = tap - r * 3;
-        const uint32_t a_base = smem_base + hs * kHaloBytes + (r * kHaloW + s) * 128;
-        const uint32_t b_base = smem_base + L::W_OFF + st * L::W_BYTES;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t da = desc_with_base(a_base + k * 32, 16, kHaloW * 128, p.desc_mode);
-          uint64_t db = make_desc_sw128(b_base + k * 32, 16, 1024);
-          mma_bf16_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        mma_commit(&w_empty[st]);
       }
-      mma_commit(&halo_empty[hs]);
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int slab = 0; slab < slabs; ++slab, ++hcount) {
+        const int hs = hcount % HST;
+        mbar_wait(&halo_full[hs], (hcount / HST) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          int st;
+          if (resident) {
+            st = slab * 9 + tap;
+            if (it == 0) {
+              mbar_wait(&w_full[st], 0);
+              tc_fence_after();
+            }
+          } else {
+            st = wcount % WST;
+            mbar_wait(&w_full[st], (wcount / WST) & 1);
+            tc_fence_after();
+          }
+          // shifted view of the halo: the tensor core swizzles on absolute smem address bits,
+          // so a start address offset by whole 128-byte rows needs no base-offset field
+          const int r = tap / 3, s = tap - r * 3;
+          const uint32_t a_lo = a_lo0 + hs * (kHaloBytes >> 4) + (((r * kHaloW + s) * 128) >> 4);
+          const uint32_t b_lo = b_lo0 + st * (L::W_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_bf16_ss(d_tmem, desc_join(a_lo + 2 * k, a_hi), desc_join(b_lo + 2 * k, b_hi), idesc,
+                        (slab | tap | k) != 0 ? 1u : 0u);
+          if (!resident) {
+            mma_commit(&w_empty[st]);
+            ++wcount;
+          }
+        }
+        mma_commit(&halo_empty[hs]);
+      }
+      mma_commit(&tmem_full[acc]);
     }
-    mma_commit(tmem_full);
   } else if (warp < 4) {
     // ------------------------------ epilogue ------------------------------
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int row = tid;  // tile pixel: h = row / 8, w = row % 8
-    const int h = h0 + (row >> 3), w = w0 + (row & 7);
-    const bool valid = h < p.H && w < p.W;
-    const size_t pix = ((size_t)n * p.H + h) * p.W + w;
-    bf16* out = p.dst + pix * p.Cd + n0;
-    const bf16* add = (valid && p.add_mode == 1) ? p.add_src + pix * p.Cd + n0 : nullptr;
-    const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16);
+    const int row = tid;  // tile pixel: h = row / 8, w = row % 8  (== TMA box order)
+    const int sw = row & 7;
+    const uint32_t out_row = smem_base + L::OUT_OFF + row * 128;
+    const uint32_t res_row = smem_base + L::RES_OFF + row * 128;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+      const int nt = t / tiles_n;
+      int rem = t - nt * tiles_n;
+      const int n = rem / tiles_img;
+      rem -= n * tiles_img;
+      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (p.add_mode == 1) mbar_wait(res_full, it & 1);
+      if (tid == 0) tma_store_wait_read();  // previous tile's store has drained the staging buffer
+      named_bar_sync(1, 128);
+      const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16) + acc * BN;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(trow + c0, r);
-      tmem_ld_wait();
-      if (valid) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(trow + c0, r);
+        tmem_ld_wait();
+        const int blk = c0 >> 6;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[q * 8 + i]);
-          if (add != nullptr) {
+          const int chunk = ((c0 & 63) >> 3) + q;
+          const uint32_t off = blk * kOutBlkBytes + ((chunk ^ sw) << 4);
+          if (p.add_mode == 1) {
+            uint4 u;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                         : "r"(res_row + off));
             float a[8];
-            unpack8(*reinterpret_cast<const uint4*>(add + c0 + q * 8), a);
+            unpack8(u, a);
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] += a[i];
           }
-          *reinterpret_cast<uint4*>(out + c0 + q * 8) = pack8(f);
+          uint4 o = pack8(f);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(out_row + off), "r"(o.x), "r"(o.y),
+                       "r"(o.z), "r"(o.w)
+                       : "memory");
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (p.add_mode == 1) mbar_arrive(res_empty);
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_store_4d(&p.tm_out, smem_base + L::OUT_OFF + b * kOutBlkBytes, nt * BN + b * 64, tw * kTileW,
+                       th * kTileH, n);
+        tma_store_commit();
+      }
     }
+    if (tid == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, BN);
+  if (warp == 4) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 template <int BN, int WST>
@@ -273,7 +356,7 @@ static int launch_halo(const HaloParams& p, cudaStream_t s) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv3x3_halo)");
     attr_set = true;
   }
-  dim3 grid(p.N * p.tiles_h * p.tiles_w, p.Cd / BN);
+  int grid = p.tiles_total < kNumSMs ? p.tiles_total : kNumSMs;
   conv3x3_halo_kernel<BN, WST><<<grid, kHaloThreads, L::TOTAL, s>>>(p);
   GDL_CHECK_LAUNCH("conv3x3_halo_kernel");
   return GDL_OK;
@@ -288,8 +371,7 @@ static int env_int(const char* name, int dflt) {
 // through to the generic gather kernel), < 0 on error.
 int try_conv3x3_halo(int N, int H, int W, int Cs, int Cd, const void* src, const void* wt, int64_t wt_rows,
                      int64_t wt_k, void* dst, const void* add_src, int add_mode, int flip, cudaStream_t s) {
-  static const int impl = env_int("GDL_CONV_IMPL", 1);        // 0 = gather only
-  static const int desc_mode = env_int("GDL_HALO_DESC_MODE", 0);
+  static const int impl = env_int("GDL_CONV_IMPL", 1);  // 0 = generic gather kernel only
   static const int min_util = env_int("GDL_HALO_MIN_UTIL_PCT", 60);
   if (!impl) return 0;
   if (Cs % 64 != 0 || Cd % 64 != 0 || add_mode == 2) return 0;
@@ -299,18 +381,20 @@ int try_conv3x3_halo(int N, int H, int W, int Cs, int Cd, const void* src, const
   const int BN = (Cd % 128 == 0) ? 128 : 64;
   const CUtensorMap* tx = tmap_nhwc(src, N, H, W, Cs, kHaloW, kHaloH);
   const CUtensorMap* tw = tmap_rows(wt, wt_rows, wt_k, BN);
-  if (!tx || !tw) return GDL_ECUDA;
+  const CUtensorMap* to = tmap_nhwc(dst, N, H, W, Cd, kTileW, kTileH);
+  const CUtensorMap* tr = add_mode == 1 ? tmap_nhwc(add_src, N, H, W, Cd, kTileW, kTileH) : to;
+  if (!tx || !tw || !to || !tr) return GDL_ECUDA;
   HaloParams p;
   p.tm_x = *tx;
   p.tm_w = *tw;
-  p.dst = (bf16*)dst;
-  p.add_src = (const bf16*)add_src;
+  p.tm_out = *to;
+  p.tm_res = *tr;
   p.add_mode = add_mode;
   p.N = N; p.H = H; p.W = W; p.Cs = Cs; p.Cd = Cd;
   p.tiles_h = tiles_h; p.tiles_w = tiles_w;
+  p.tiles_total = (Cd / BN) * N * tiles_h * tiles_w;
   p.flip = flip;
-  p.desc_mode = desc_mode;
-  int rc = (BN == 128) ? launch_halo<128, 2>(p, s) : launch_halo<64, 4>(p, s);
+  int rc = (BN == 128) ? launch_halo<128, 5>(p, s) : launch_halo<64, 9>(p, s);
   return rc == GDL_OK ? 1 : rc;
 }
 
