@@ -57,7 +57,8 @@ static std::mutex g_tmap_mu;
 static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> g_tmaps;
 
 static const CUtensorMap* cached_tmap(const TmapKey& key, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
-                                      const cuuint64_t* strides, const cuuint32_t* box) {
+                                      const cuuint64_t* strides, const cuuint32_t* box,
+                                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   std::lock_guard<std::mutex> lk(g_tmap_mu);
   auto it = g_tmaps.find(key);
   if (it != g_tmaps.end()) return it->second;
@@ -70,7 +71,7 @@ static const CUtensorMap* cached_tmap(const TmapKey& key, cuuint32_t rank, void*
   if (posix_memalign(reinterpret_cast<void**>(&m), 64, sizeof(CUtensorMap)) != 0) return nullptr;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, ptr, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[128];
@@ -98,6 +99,23 @@ const CUtensorMap* tmap_rows(const void* ptr, int64_t rows, int64_t K, int box_r
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   return cached_tmap(key, 2, const_cast<void*>(ptr), dims, strides, box);
+}
+
+// 16-channel (32-byte rows, 32-byte swizzle) variants used by the space-to-depth stems.
+const CUtensorMap* tmap_nhwc16(const void* ptr, int N, int H, int W, int box_w, int box_h) {
+  TmapKey key{{(uint64_t)ptr, ((uint64_t)N << 32) | (uint32_t)H, ((uint64_t)W << 32) | 16u,
+               ((uint64_t)box_w << 32) | (uint32_t)box_h, 4, 32}};
+  cuuint64_t dims[4] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {32, (cuuint64_t)W * 32, (cuuint64_t)H * W * 32};
+  cuuint32_t box[4] = {16, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  return cached_tmap(key, 4, const_cast<void*>(ptr), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+}
+const CUtensorMap* tmap_rows16(const void* ptr, int64_t rows, int64_t K, int box_rows) {
+  TmapKey key{{(uint64_t)ptr, (uint64_t)rows, (uint64_t)K, (uint64_t)box_rows, 2, 32}};
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  return cached_tmap(key, 2, const_cast<void*>(ptr), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -116,6 +116,10 @@ __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr, uint32_t l
 __device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
+// 32-byte swizzle (rows of 32 bytes = 16 bf16; layout type 6)
+__device__ __forceinline__ uint32_t desc_hi_sw32(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (6u << 29);
+}
 __device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }

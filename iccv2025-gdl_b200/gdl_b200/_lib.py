@@ -39,6 +39,12 @@ SIGNATURES = {
     "gdl_conv_fwd": (_i, [_dp, _p, _p, _p, _p]),
     "gdl_conv_dgrad": (_i, [_dp, _p, _p, _p, _p, _i, _p]),
     "gdl_conv_wgrad": (_i, [_dp, _i, _p, _p, _p, _p, _l, _p]),
+    "gdl_stem_geometry": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "gdl_stem_layout": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "gdl_stem_pack_weights": (_i, [_p, _p, _i, _p]),
+    "gdl_stem_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "gdl_stem_wgrad_workspace_bytes": (_l, [_i, _i, _i]),
+    "gdl_stem_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _l, _p]),
     "gdl_layout_ncthw_to_nhwc8": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "gdl_bn_partial_floats": (_l, [_l, _i]),
     "gdl_bn_stats": (_i, [_p, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),

@@ -85,24 +85,26 @@ class _EncoderMapFn(torch.autograd.Function):
 
 
 def to_nhwc8(net, x):
-    """Input tensor of the reference contract -> bf16 [N,H,W,8] via gdl_layout_ncthw_to_nhwc8."""
+    """Input tensor of the reference contract -> the encoder's bf16 space-to-depth stem input
+    [N,Hp,Wp,16] via gdl_stem_layout (fuses the per-frame reshape of backbone.py:162-164)."""
     x = x.contiguous().float()
     if net.modality == 'visual':
         B, Cc, T, H, W = x.shape
     else:
         B, Cc, H, W = x.shape
         T = 1
-    x8 = torch.empty(B * T, H, W, 8, device=x.device, dtype=torch.bfloat16)
-    ops.layout_ncthw_to_nhwc8(x, x8, B, Cc, T, H, W)
-    return x8
+    _, _, Hp, Wp = ops.stem_geometry(H, W)
+    x16 = torch.empty(B * T, Hp, Wp, 16, device=x.device, dtype=torch.bfloat16)
+    ops.stem_layout(x, x16, B, Cc, T, H, W)
+    return x16, (B * T, H, W)
 
 
 def encoder_map(net, x):
     if not net.training:
         raise NotImplementedError("eval-mode forward (running statistics) is not built yet; "
                                   "see DESIGN.md 'next' rows")
-    x8 = to_nhwc8(net, x)
-    eng = net.engine(x8.shape[0], x8.shape[1], x8.shape[2])
+    x8, (N, H, W) = to_nhwc8(net, x)
+    eng = net.engine(N, H, W)
     eng.repack()
     params = eng.parameters()
     out = _EncoderMapFn.apply(net, x8, eng, *params)

@@ -80,6 +80,40 @@ class _ConvBN:
         return self.y
 
 
+class _StemBN(_ConvBN):
+    """The 7x7/s2 stem + BN: space-to-depth implicit GEMM (csrc/conv_stem.cu)."""
+
+    def __init__(self, eng, conv, bn, N, H, W):
+        Co, ci_real, R, S = conv.weight.shape
+        assert (Co, R, S) == (64, 7, 7) and conv.stride[0] == 2 and conv.padding[0] == 3
+        self.name, self.conv, self.bn, self.ci_real, self.relu = "conv1", conv, bn, ci_real, True
+        self.N, self.H, self.W = N, H, W
+        self.d = ops.conv_desc(N, H, W, 8, 64, 7, 7, 2, 3)  # geometry only (Ho, Wo)
+        self.Ho, self.Wo, self.Hp, self.Wp = ops.stem_geometry(H, W)
+        assert (self.Ho, self.Wo) == (self.d.Ho, self.d.Wo)
+        self.P, self.C = N * self.Ho * self.Wo, 64
+        dev = eng.device
+        self.wp = torch.zeros(64, 256, device=dev, dtype=torch.bfloat16)
+        self.wT = None
+        self.x = torch.empty(N, self.Ho, self.Wo, 64, device=dev, dtype=torch.bfloat16)
+        self.y = torch.empty_like(self.x)
+        self.mean, self.invstd, self.scale, self.shift = (torch.empty(64, device=dev) for _ in range(4))
+        eng.max_wgrad_ws = max(eng.max_wgrad_ws, ops.stem_wgrad_workspace_bytes(N, H, W))
+        eng.max_bn_partial = max(eng.max_bn_partial, ops.bn_partial_floats(self.P, 64))
+
+    def repack(self):
+        ops.stem_pack_weights(self.conv.weight.data, self.wp, self.ci_real)
+
+    def forward(self, eng, x16, res=None, training=True):
+        ops.stem_fwd(x16, self.wp, self.x, self.N, self.H, self.W, self.ci_real)
+        bn = self.bn
+        ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
+                     bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                     self.scale, self.shift)
+        ops.bn_apply(self.x, None, self.y, self.P, self.C, self.scale, self.shift, True)
+        return self.y
+
+
 class EncoderEngine:
     def __init__(self, net, N, H, W, device):
         """net: backbone.ResNet; N images of H x W (audio: N=B, visual: N=B*T)."""
@@ -91,7 +125,9 @@ class EncoderEngine:
         self.max_bn_partial = 0
         self.units = []
         self.blocks = []
-        self.stem = self._unit("conv1", net.conv1, net.bn1, N, H, W, 8, True)
+        self.stem = _StemBN(self, net.conv1, net.bn1, N, H, W)
+        self.units.append(self.stem)
+        self.input_shape = (N, self.stem.Hp, self.stem.Wp, 16)  # space-to-depth bf16 input (gdl_stem_layout)
         H1, W1 = self.stem.d.Ho, self.stem.d.Wo
         self.Hp, self.Wp = (H1 - 1) // 2 + 1, (W1 - 1) // 2 + 1
         self.pool_y = torch.empty(N, self.Hp, self.Wp, 64, device=device, dtype=torch.bfloat16)
@@ -126,10 +162,11 @@ class EncoderEngine:
             u.repack()
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x8):
-        """x8: bf16 [N,H,W,8] -> bf16 [N,Hf,Wf,512] (the layer4 map, reference backbone.py:175-181)."""
+    def forward(self, x16):
+        """x16: bf16 space-to-depth input [N,Hp,Wp,16] -> bf16 [N,Hf,Wf,512] (the layer4 map,
+        reference backbone.py:175-181)."""
         s = self.stem
-        y = s.forward(self, x8)
+        y = s.forward(self, x16)
         ops.maxpool_fwd(y, self.pool_y, self.pool_idx, self.N, s.d.Ho, s.d.Wo, 64, self.Hp, self.Wp)
         u = self.pool_y
         for (u1, u2, ud) in self.blocks:
@@ -193,9 +230,9 @@ class EncoderEngine:
         ops.bn_bwd(dy, u.y, u.x, dz, dx, u.P, u.C, bn.weight.data, u.mean, u.invstd, self.bn_partial,
                    self._grad(bn.weight), self._grad(bn.bias), relu)
 
-    def backward(self, x8):
+    def backward(self, x16):
         """Consumes self.g_feat (grad wrt the layer4 map, bf16) and writes every parameter
-        gradient of the encoder into p.grad (overwrite).  x8 is the stem input of the forward."""
+        gradient of the encoder into p.grad (overwrite).  x16 is the stem input of the forward."""
         for (u1, u2, ud), b, in_t in zip(reversed(self.blocks), self.bwd_plan, reversed(self._block_inputs())):
             g_out = b["g_out"]
             # out = relu(bn2(c2) + identity): dz = g_out * (out > 0), in place
@@ -217,7 +254,7 @@ class EncoderEngine:
         s = self.stem
         ops.maxpool_bwd(self.g_pool, self.pool_idx, self.g_y0, self.N, s.d.Ho, s.d.Wo, 64, self.Hp, self.Wp)
         self._bn_bwd(s, self.g_y0, self.g_y0, self.d_c0, True)
-        ops.conv_wgrad(s.d, s.ci_real, x8, self.d_c0, self._grad(s.conv.weight), self.wgrad_ws)
+        ops.stem_wgrad(x16, self.d_c0, self._grad(s.conv.weight), s.ci_real, self.N, self.H, self.W, self.wgrad_ws)
 
     def _block_inputs(self):
         ins = [self.pool_y]

@@ -118,6 +118,44 @@ def conv_wgrad(d, ci_real, x, dy, dw_oihw, workspace):
                                      _stream()), "gdl_conv_wgrad")
 
 
+# ---------------------------------------------------------------------------------- stems
+def stem_geometry(H, W):
+    ho, wo, hp, wp = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    check(_lib.load().gdl_stem_geometry(H, W, C.byref(ho), C.byref(wo), C.byref(hp), C.byref(wp)),
+          "gdl_stem_geometry")
+    return ho.value, wo.value, hp.value, wp.value
+
+
+def _stem_flops(N, H, W, Cc):
+    ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    return 2.0 * N * ho * wo * 64 * 49 * Cc
+
+
+@_op("stem_layout", 1, lambda src, dst, B, Cc, T, H, W: ("bytes", B * T * H * W * 4.0 * Cc + dst.numel() * 2.0))
+def stem_layout(src, dst, B, Cc, T, H, W):
+    check(_lib.load().gdl_stem_layout(_ptr(src), _ptr(dst), B, Cc, T, H, W, _stream()), "gdl_stem_layout")
+
+
+@_op("pack_weights", 1)
+def stem_pack_weights(w_oihw, w_packed, Cc):
+    check(_lib.load().gdl_stem_pack_weights(_ptr(w_oihw), _ptr(w_packed), Cc, _stream()), "gdl_stem_pack_weights")
+
+
+@_op("conv_fwd", 1, lambda x16, w, y, N, H, W, Cc: ("flops", _stem_flops(N, H, W, Cc), "N%d %dx%d stem C%d s2d" % (N, H, W, Cc)))
+def stem_fwd(x16, w_packed, y, N, H, W, Cc):
+    check(_lib.load().gdl_stem_fwd(_ptr(x16), _ptr(w_packed), _ptr(y), N, H, W, _stream()), "gdl_stem_fwd")
+
+
+def stem_wgrad_workspace_bytes(N, H, W):
+    return int(_lib.load().gdl_stem_wgrad_workspace_bytes(N, H, W))
+
+
+@_op("conv_wgrad", 2, lambda x16, dy, dw, Cc, N, H, W, ws: ("flops", _stem_flops(N, H, W, Cc), "N%d %dx%d stem C%d s2d" % (N, H, W, Cc)))
+def stem_wgrad(x16, dy, dw_oihw, Cc, N, H, W, workspace):
+    check(_lib.load().gdl_stem_wgrad(_ptr(x16), _ptr(dy), _ptr(dw_oihw), Cc, N, H, W, _ptr(workspace),
+                                     workspace.numel() * workspace.element_size(), _stream()), "gdl_stem_wgrad")
+
+
 # ---------------------------------------------------------------------------------- elementwise
 @_op("layout", 1, lambda src, dst, B, Cc, T, H, W: ("bytes", B * T * H * W * (4.0 * Cc + 16.0)))
 def layout_ncthw_to_nhwc8(src, dst, B, Cc, T, H, W):

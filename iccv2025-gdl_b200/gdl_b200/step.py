@@ -113,8 +113,8 @@ class DGLStep:
         self.spec_in = torch.zeros(B, self.F_, self.Tt, device=dev)
         self.image_in = torch.zeros(B, 3, T, self.H, self.W, device=dev)
         self.label_in = torch.zeros(B, device=dev, dtype=torch.int64)
-        self.a8 = torch.empty(B, self.F_, self.Tt, 8, device=dev, dtype=torch.bfloat16)
-        self.v8 = torch.empty(B * T, self.H, self.W, 8, device=dev, dtype=torch.bfloat16)
+        self.a8 = torch.empty(self.enc_a.input_shape, device=dev, dtype=torch.bfloat16)  # space-to-depth
+        self.v8 = torch.empty(self.enc_v.input_shape, device=dev, dtype=torch.bfloat16)
         D = 512
         self.a_feat, self.v_feat = torch.empty(B, D, device=dev), torch.empty(B, D, device=dev)
         self.da, self.dv = torch.empty(B, D, device=dev), torch.empty(B, D, device=dev)
@@ -192,11 +192,11 @@ class DGLStep:
         sa.wait_stream(main)
         sv.wait_stream(main)
         with torch.cuda.stream(sa):
-            ops.layout_ncthw_to_nhwc8(self.spec_in, self.a8, B, 1, 1, self.F_, self.Tt)
+            ops.stem_layout(self.spec_in, self.a8, B, 1, 1, self.F_, self.Tt)
             fa = self.enc_a.forward(self.a8)
             ops.gap_fwd(fa, self.a_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
         with torch.cuda.stream(sv):
-            ops.layout_ncthw_to_nhwc8(self.image_in, self.v8, B, 3, T, self.H, self.W)
+            ops.stem_layout(self.image_in, self.v8, B, 3, T, self.H, self.W)
             fv = self.enc_v.forward(self.v8)
             ops.gap_fwd(fv, self.v_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
         main.wait_stream(sa)

@@ -72,6 +72,21 @@ int gdl_conv_dgrad(const gdl_conv_desc* d, const void* dy, const void* w_packed_
 int gdl_conv_wgrad(const gdl_conv_desc* d, int ci_real, const void* x, const void* dy,
                    float* dw_oihw, void* workspace, int64_t workspace_bytes, gdl_stream_t s);
 
+/* ---- stem convolutions (reference models/backbone.py:97-100: Conv2d(1|3 -> 64, 7, stride 2, pad 3))
+ * as a space-to-depth 4x4/s1 implicit GEMM: see csrc/conv_stem.cu.  x16 is the bf16 tensor
+ * [N, Hp, Wp, 16] written by gdl_stem_layout (Hp = Ho + 3, Wp = Wo + 3). */
+int gdl_stem_geometry(int H, int W, int* Ho, int* Wo, int* Hp, int* Wp);
+/* src f32 [B,C,T,H,W] (C <= 4; audio: C = T = 1) -> x16; replaces backbone.py:162-164 + the cast. */
+int gdl_stem_layout(const float* src, void* x16, int B, int C, int T, int H, int W, gdl_stream_t s);
+/* fp32 OIHW [64][C][7][7] -> bf16 [64][256]. */
+int gdl_stem_pack_weights(const float* w_oihw, void* w_packed, int C, gdl_stream_t s);
+/* y bf16 [N,Ho,Wo,64]. */
+int gdl_stem_fwd(const void* x16, const void* w_packed, void* y, int N, int H, int W, gdl_stream_t s);
+int64_t gdl_stem_wgrad_workspace_bytes(int N, int H, int W);
+/* dw fp32 OIHW [64][C][7][7] from x16 and dy bf16 [N,Ho,Wo,64]; deterministic split-K. */
+int gdl_stem_wgrad(const void* x16, const void* dy, float* dw_oihw, int C, int N, int H, int W,
+                   void* workspace, int64_t workspace_bytes, gdl_stream_t s);
+
 /* ---- layout (reference models/backbone.py:162-164 permute/contiguous/view, and
  *      main_dgl.py:100 spec.unsqueeze(1).float()) ---------------------------------------- */
 /* src f32 [B,C,T,H,W] -> dst bf16 [B*T,H,W,8] (channels >= C zero). */

@@ -94,6 +94,39 @@ def test_conv_fwd_stem(ci_real, H, W):
     assert rel_err(dw, ref_dw) < 2e-3, rel_err(dw, ref_dw)
 
 
+@pytest.mark.parametrize("ci_real,T,H,W", [(3, 2, 37, 29), (1, 1, 41, 30), (3, 3, 224, 224), (1, 1, 257, 188)])
+def test_stem_space_to_depth(ci_real, T, H, W):
+    """7x7/s2 stem as a 4x4/s1 space-to-depth implicit GEMM: layout + fwd + wgrad vs torch."""
+    ops = _ops()
+    B, Co = 2, 64
+    N = B * T
+    g = torch.Generator(device="cuda").manual_seed(11)
+    src = torch.randn(B, ci_real, T, H, W, device="cuda", generator=g)
+    w = (torch.randn(Co, ci_real, 7, 7, device="cuda", generator=g) * 0.1).to(torch.bfloat16).float()
+    Ho, Wo, Hp, Wp = ops.stem_geometry(H, W)
+    x16 = torch.full((N, Hp, Wp, 16), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.stem_layout(src, x16, B, ci_real, T, H, W)
+    wp = torch.empty(Co, 256, device="cuda", dtype=torch.bfloat16)
+    ops.stem_pack_weights(w, wp, ci_real)
+    y = torch.full((N, Ho, Wo, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.stem_fwd(x16, wp, y, N, H, W, ci_real)
+    torch.cuda.synchronize()
+    x = src.permute(0, 2, 1, 3, 4).reshape(N, ci_real, H, W).to(torch.bfloat16).float()
+    ref = F.conv2d(x, w, stride=2, padding=3)
+    assert torch.isfinite(x16.float()).all() and torch.isfinite(y.float()).all()
+    assert rel_err(nchw(y), ref) < 6e-3, rel_err(nchw(y), ref)
+    dy = torch.randn(N, Co, Ho, Wo, device="cuda", generator=g).to(torch.bfloat16).float()
+    ws = torch.empty(ops.stem_wgrad_workspace_bytes(N, H, W) // 4, device="cuda")
+    dw = torch.full((Co, ci_real, 7, 7), float("nan"), device="cuda")
+    ops.stem_wgrad(x16, nhwc(dy), dw, ci_real, N, H, W, ws)
+    torch.cuda.synchronize()
+    ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2, padding=3)
+    assert rel_err(dw, ref_dw) < 2e-3, rel_err(dw, ref_dw)
+    dw2 = torch.empty_like(dw)
+    ops.stem_wgrad(x16, nhwc(dy), dw2, ci_real, N, H, W, ws)
+    assert torch.equal(dw, dw2)
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("add_mode", [0, 1])
 def test_conv_dgrad(case, add_mode):
