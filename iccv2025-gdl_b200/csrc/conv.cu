@@ -540,6 +540,11 @@ static int launch_wgrad(const WgradParams& p, const WgradPlan& w, cudaStream_t s
 int try_conv3x3_halo(int N, int H, int W, int Cs, int Cd, const void* src, const void* wt, int64_t wt_rows,
                      int64_t wt_k, void* dst, const void* add_src, int add_mode, int flip, cudaStream_t s);
 
+// conv_wgrad_halo.cu
+int64_t wgrad_halo_workspace_bytes(int N, int H, int W, int Ci, int Co);
+int try_wgrad3x3_halo(int N, int H, int W, int Ci, int Co, const void* x, const void* dy, float* partial,
+                      int64_t workspace_bytes, cudaStream_t s);
+
 static int run_igemm(const ConvParams& p, cudaStream_t s) {
   if (p.Cd % 128 == 0) return launch_igemm<128, 3>(p, s);
   return launch_igemm<64, 4>(p, s);
@@ -554,7 +559,12 @@ extern "C" int64_t gdl_conv_packed_k(const gdl_conv_desc* d) { return desc_ok(d)
 extern "C" int64_t gdl_conv_wgrad_workspace_bytes(const gdl_conv_desc* d) {
   if (!desc_ok(d)) return GDL_EINVAL;
   WgradPlan w = plan_wgrad(d);
-  return (int64_t)w.splits * w.Kp * d->Co * (int64_t)sizeof(float);
+  int64_t need = (int64_t)w.splits * w.Kp * d->Co * (int64_t)sizeof(float);
+  if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1) {
+    int64_t h = wgrad_halo_workspace_bytes(d->N, d->Hi, d->Wi, d->Ci, d->Co);
+    if (h > need) need = h;
+  }
+  return need;
 }
 
 extern "C" int gdl_conv_pack_weights(const gdl_conv_desc* d, int ci_real, const float* w_oihw,
@@ -636,6 +646,19 @@ extern "C" int gdl_conv_wgrad(const gdl_conv_desc* d, int ci_real, const void* x
   GDL_REQUIRE(desc_ok(d), "gdl_conv_wgrad: bad descriptor");
   GDL_REQUIRE(x && dy && dw_oihw && workspace, "gdl_conv_wgrad: null pointer");
   GDL_REQUIRE(ci_real > 0 && ci_real <= d->Ci, "gdl_conv_wgrad: ci_real out of range");
+  if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1 && d->Ci % 64 == 0 && ci_real == d->Ci) {
+    int ns = try_wgrad3x3_halo(d->N, d->Hi, d->Wi, d->Ci, d->Co, x, dy, (float*)workspace, workspace_bytes,
+                               (cudaStream_t)s);
+    if (ns < 0) return ns;
+    if (ns > 0) {
+      int Kp = 9 * d->Ci;
+      int64_t total = (int64_t)Kp * d->Co;
+      wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)s>>>(
+          (const float*)workspace, dw_oihw, ns, Kp, d->Co, d->Ci, ci_real, d->R, d->S);
+      GDL_CHECK_LAUNCH("wgrad_reduce_kernel");
+      return GDL_OK;
+    }
+  }
   WgradPlan w = plan_wgrad(d);
   int64_t need = (int64_t)w.splits * w.Kp * d->Co * (int64_t)sizeof(float);
   if (workspace_bytes < need) {
