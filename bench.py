@@ -153,6 +153,12 @@ def run_gpu(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def say(msg):
+        if os.environ.get("GDL_BENCH_VERBOSE"):
+            sys.stderr.write("[rank %d %.1fs] %s\n" % (rank, time.perf_counter() - T0, msg))
+            sys.stderr.flush()
+    T0 = time.perf_counter()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     pg = None
@@ -172,8 +178,10 @@ def run_gpu(a):
     spec, image, label = make_batch(B, n_cls, a.dataset, seed=1 + rank)
     spec_h, image_h, label_h = spec.pin_memory(), image.pin_memory(), label.pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in (spec_h, image_h, label_h))
+    say("model + step built")
     step.load_inputs(spec_h, image_h, label_h)
     torch.cuda.synchronize()
+    say("inputs loaded")
 
     def barrier():
         if world > 1:
@@ -201,8 +209,11 @@ def run_gpu(a):
         return t[0].item(), t[1].item()
 
     launches0 = ops.LAUNCHES
-    for _ in range(max(a.warmup, 3)):
+    for i in range(max(a.warmup, 3)):
         step.step()
+        if os.environ.get("GDL_BENCH_VERBOSE"):
+            torch.cuda.synchronize()
+            say("warmup step %d done" % i)
     torch.cuda.synchronize()
     per_step_launches = None
     if a.no_graph:
@@ -215,6 +226,7 @@ def run_gpu(a):
     if rank == 0:
         sampler.start()
     ms, wall_ms = timed(a.steps, e2e=False)
+    say("timed region done")
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step.step(spec_h, image_h, label_h)

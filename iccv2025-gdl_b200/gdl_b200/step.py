@@ -128,6 +128,7 @@ class DGLStep:
         self.stream_a, self.stream_v = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.steps_done = 0
         self._graph = None
+        self._graph_update = None
         self._graph_lr = None
         self.launches_per_step = None
 
@@ -185,7 +186,13 @@ class DGLStep:
 
     # ------------------------------------------------------------------ the step
     def _enqueue(self, lr, first):
-        """Enqueue one full step on the current stream (+ the two encoder streams)."""
+        self._enqueue_compute()
+        if self.world_size > 1:
+            self._allreduce()
+        self._enqueue_update(lr, first)
+
+    def _enqueue_compute(self):
+        """Forward + head + backward on the current stream (+ the two encoder streams)."""
         B, T = self.B, self.T
         main = torch.cuda.current_stream()
         sa, sv = self.stream_a, self.stream_v
@@ -212,11 +219,16 @@ class DGLStep:
             self.enc_v.backward(self.v8)
         main.wait_stream(sa)
         main.wait_stream(sv)
+
+    def _allreduce(self):
+        # each rank scaled its CE by 1/B_global, so a plain SUM reproduces the reference's
+        # full-batch mean (DataParallel gathers logits, main_dgl.py:102-104); BN stays per replica.
+        # The 3 losses ride in the tail of the gradient arena (one collective per step).
+        torch.distributed.all_reduce(self.arena.grad, group=self.pg)
+
+    def _enqueue_update(self, lr, first):
+        """Clip statistics + diagnostics + SGD + bf16 shadow refresh (after the all-reduce)."""
         ar = self.arena
-        if self.world_size > 1:
-            # each rank scaled its CE by 1/B_global, so a plain SUM reproduces the reference's
-            # full-batch mean (DataParallel gathers logits, main_dgl.py:102-104); BN stays per replica
-            torch.distributed.all_reduce(ar.grad, group=self.pg)
         ops.grad_stats(ar.grad, ar.numel, ar.seg_end, ar.seg_group, ar.seg_inv, ar.nseg, self.max_norm,
                        ar.scratch, self.stats[4:8])
         ops.sgd_momentum(ar.param, ar.grad, ar.momentum, ar.numel, lr, self.mu, self.wd, first, self.stats[4:8])
@@ -248,12 +260,25 @@ class DGLStep:
         else:
             if self._graph is None or self._graph_lr != self.lr:
                 torch.cuda.synchronize()
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph):
-                    self._enqueue(self.lr, False)
+                if self.world_size == 1:
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph):
+                        self._enqueue(self.lr, False)
+                    self._graph_update = None
+                else:
+                    # NCCL stays outside the captured region: graph(compute) -> all-reduce -> graph(update)
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph):
+                        self._enqueue_compute()
+                    self._graph_update = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph_update):
+                        self._enqueue_update(self.lr, False)
                 self._graph_lr = self.lr
-                # capture does not execute: replay below runs this step
+                # capture does not execute: the replay below runs this step
             self._graph.replay()
+            if self._graph_update is not None:
+                self._allreduce()
+                self._graph_update.replay()
         self.steps_done += 1
         return self.stats
 

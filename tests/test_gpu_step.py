@@ -166,3 +166,17 @@ def test_kinetics_shape_head_width():
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_two_gpu_data_parallel_step():
+    """N=2 DGLStep (NCCL all-reduce between the two captured graphs) vs the oracle's two-shard
+    simulation; skipped on single-GPU boxes (run it with `gpurun --gpus 2`)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(os.path.dirname(__file__), "dist_step_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       capture_output=True, text=True, timeout=300)
+    assert "DIST_STEP_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
