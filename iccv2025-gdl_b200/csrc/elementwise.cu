@@ -134,6 +134,17 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int 
   }
 }
 
+// eval mode: fused affine from the running statistics (reference model.eval(), main_dgl.py:186)
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc = gamma[c] * rsqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
 // y = [relu](x*scale + shift [+ res])
 __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x,
                                                        const bf16* __restrict__ res,
@@ -430,6 +441,16 @@ extern "C" int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, con
   bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(
       partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
   GDL_CHECK_LAUNCH("bn_stats_finalize_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, float* scale, float* shift, int C,
+                                  gdl_stream_t s) {
+  GDL_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && C > 0, "gdl_bn_eval_affine: bad arguments");
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(gamma, beta, running_mean, running_var, eps,
+                                                                     scale, shift, C);
+  GDL_CHECK_LAUNCH("bn_eval_affine_kernel");
   return GDL_OK;
 }
 

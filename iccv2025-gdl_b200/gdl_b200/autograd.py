@@ -100,12 +100,14 @@ def to_nhwc8(net, x):
 
 
 def encoder_map(net, x):
-    if not net.training:
-        raise NotImplementedError("eval-mode forward (running statistics) is not built yet; "
-                                  "see DESIGN.md 'next' rows")
     x8, (N, H, W) = to_nhwc8(net, x)
     eng = net.engine(N, H, W)
     eng.repack()
+    if not net.training or not torch.is_grad_enabled():
+        # eval / no-grad: BN uses the running statistics when the module is in eval mode
+        with torch.no_grad():
+            feat = eng.forward(x8, training=net.training)
+            return feat.permute(0, 3, 1, 2).float()
     params = eng.parameters()
     out = _EncoderMapFn.apply(net, x8, eng, *params)
     with torch.no_grad():

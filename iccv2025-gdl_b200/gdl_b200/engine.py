@@ -75,7 +75,8 @@ class _ConvBN:
                          bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
                          self.scale, self.shift)
         else:
-            raise NotImplementedError("eval-mode forward goes through EncoderEngine.forward_eval")
+            ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
+                               self.scale, self.shift, self.C)
         ops.bn_apply(self.x, res, self.y, self.P, self.C, self.scale, self.shift, self.relu)
         return self.y
 
@@ -107,9 +108,13 @@ class _StemBN(_ConvBN):
     def forward(self, eng, x16, res=None, training=True):
         ops.stem_fwd(x16, self.wp, self.x, self.N, self.H, self.W, self.ci_real)
         bn = self.bn
-        ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
-                     bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
-                     self.scale, self.shift)
+        if training:
+            ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
+                         bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                         self.scale, self.shift)
+        else:
+            ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
+                               self.scale, self.shift, self.C)
         ops.bn_apply(self.x, None, self.y, self.P, self.C, self.scale, self.shift, True)
         return self.y
 
@@ -162,20 +167,20 @@ class EncoderEngine:
             u.repack()
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x16):
+    def forward(self, x16, training=True):
         """x16: bf16 space-to-depth input [N,Hp,Wp,16] -> bf16 [N,Hf,Wf,512] (the layer4 map,
-        reference backbone.py:175-181)."""
+        reference backbone.py:175-181).  training=False uses the BN running statistics."""
         s = self.stem
-        y = s.forward(self, x16)
+        y = s.forward(self, x16, training=training)
         ops.maxpool_fwd(y, self.pool_y, self.pool_idx, self.N, s.d.Ho, s.d.Wo, 64, self.Hp, self.Wp)
         u = self.pool_y
         for (u1, u2, ud) in self.blocks:
-            y1 = u1.forward(self, u)
+            y1 = u1.forward(self, u, training=training)
             ident = u
             if ud is not None:
-                ident = ud.forward(self, u)
+                ident = ud.forward(self, u, training=training)
             # bn2 + residual + relu (reference backbone.py:62-66)
-            u = u2.forward(self, y1, res=ident)
+            u = u2.forward(self, y1, res=ident, training=training)
         return u
 
     # ------------------------------------------------------------------ backward

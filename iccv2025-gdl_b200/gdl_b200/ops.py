@@ -175,6 +175,12 @@ def bn_stats(x, P, Cc, partial, gamma, beta, eps, momentum, running_mean, runnin
                                    _ptr(invstd), _ptr(scale), _ptr(shift), _stream()), "gdl_bn_stats")
 
 
+@_op("bn_eval_affine", 1)
+def bn_eval_affine(gamma, beta, rm, rv, eps, scale, shift, Cc):
+    check(_lib.load().gdl_bn_eval_affine(_ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), eps, _ptr(scale),
+                                         _ptr(shift), Cc, _stream()), "gdl_bn_eval_affine")
+
+
 @_op("bn_apply", 1, lambda x, res, y, P, Cc, *a: ("bytes", (4.0 + (2.0 if res is not None else 0.0)) * P * Cc))
 def bn_apply(x, res, y, P, Cc, scale, shift, relu):
     check(_lib.load().gdl_bn_apply(_ptr(x), _ptr(res), _ptr(y), P, Cc, _ptr(scale), _ptr(shift),

@@ -1,0 +1,105 @@
+"""Drop-ins for the reference's `train_epoch` (main_dgl.py:69-165) and `valid` (:168-222) with
+the same signatures, return values, prints and CSV side effects, running on the fused DGLStep.
+
+Differences that are invisible to the caller: the 123 per-step host syncs of the reference
+(120 `.item()` for the diagnostics + 3 losses) become one 8-float D2H per LOG_EVERY steps
+(the per-step values are kept in a device ring and flushed in order), and the optimizer passed
+in is only read for its hyper-parameters / lr schedule — the update itself is the fused
+SGD-momentum kernel over the parameter arena (its momentum is exposed through
+`optimizer.state[p]['momentum_buffer']` so reference-format checkpoints still carry it).
+"""
+import csv
+
+import torch
+
+from .step import DGLStep
+
+LOG_EVERY = 100  # the reference prints every 100 steps (main_dgl.py:125,144)
+GRAD_CSV = 'audio_visual_grad_vanilla.csv'  # main_dgl.py:148
+
+
+def _get_step(args, model, optimizer, spec, image):
+    inner = getattr(model, "module", model)
+    B = spec.shape[0]
+    key = (B, tuple(spec.shape[1:]), tuple(image.shape[2:]))
+    st = getattr(inner, "_gdl_step", None)
+    if st is not None and getattr(inner, "_gdl_step_key", None) == key:
+        return st
+    g = optimizer.param_groups[0]
+    world = torch.distributed.get_world_size() if torch.distributed.is_available() and \
+        torch.distributed.is_initialized() else 1
+    st = DGLStep(inner, B, tuple(spec.shape[1:]), tuple(image.shape[2:]), alpha=args.alpha, lr=g['lr'],
+                 momentum=g.get('momentum', 0.9), weight_decay=g.get('weight_decay', 1e-4), max_norm=40.0,
+                 world_size=world, process_group=torch.distributed.group.WORLD if world > 1 else None)
+    for p, o in zip(st.arena.params, st.arena.offsets):  # checkpoint compatibility
+        optimizer.state[p]['momentum_buffer'] = st.arena.momentum[o:o + p.numel()].view(p.shape)
+    inner._gdl_step, inner._gdl_step_key = st, key
+    return st
+
+
+def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler, writer=None):
+    if scheduler is not None:
+        scheduler.step()  # stepped at epoch START like the reference (main_dgl.py:73-74)
+    if epoch < 20:
+        print(epoch, optimizer.param_groups[0]['lr'])
+    model.train()
+    print("Start training ... ")
+    rank0 = not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+        torch.distributed.get_rank() == 0
+    hist, pending, totals, nsteps = None, [], [0.0, 0.0, 0.0], 0
+
+    def flush():
+        if not pending:
+            return
+        rows = hist[:len(pending)].tolist()  # ONE D2H for up to LOG_EVERY steps
+        if rank0:
+            with open(GRAD_CSV, 'a', newline='') as f:
+                w = csv.writer(f)
+                for r in rows:
+                    w.writerow([r[6], r[7]])
+        for r in rows:
+            totals[0] += r[0]
+            totals[1] += r[1]
+            totals[2] += r[2]
+        del pending[:]
+
+    for step_i, (spec, image, label) in enumerate(dataloader):
+        st = _get_step(args, model, optimizer, spec, image)
+        if hist is None:
+            hist = torch.zeros(LOG_EVERY, 8, device=st.device)
+        stats = st.step(spec, image, label, lr=optimizer.param_groups[0]['lr'])
+        hist[len(pending)].copy_(stats)
+        pending.append(step_i)
+        nsteps += 1
+        if step_i % LOG_EVERY == 0:
+            s = st.read_stats()
+            print("unimodal_loss:", s[1] + s[2], "cls_loss:", s[0])
+            print("grad:", s[5], s[6])
+            print("unimodal", st.logits[1].abs().mean().item(), st.logits[2].abs().mean().item())
+        if len(pending) == LOG_EVERY:
+            flush()
+    flush()
+    n = max(len(dataloader), 1) if hasattr(dataloader, "__len__") else max(nsteps, 1)
+    return totals[0] / n, totals[1] / n, totals[2] / n, 0.0, 0.0, 0.0, 0.0
+
+
+def valid(args, model, device, dataloader):
+    """reference main_dgl.py:168-222: eval-mode forward (BN running statistics), softmax,
+    arg-max accuracy of the fused / audio / visual heads.  The per-sample host loop becomes
+    on-device counting with one D2H at the end; `drop_last` behaviour is the loader's."""
+    inner = getattr(model, "module", model)
+    inner.args.drop = 0
+    correct = torch.zeros(3, device=device, dtype=torch.float64)
+    total = 0
+    with torch.no_grad():
+        model.eval()
+        print(inner.args.drop)
+        for spec, image, label in dataloader:
+            spec, image, label = spec.to(device), image.to(device), label.to(device)
+            out, out_a, out_v = model(spec.unsqueeze(1).float(), image.float())
+            for i, o in enumerate((out, out_a, out_v)):  # softmax is monotone: arg-max of the logits
+                correct[i] += (o.argmax(1) == label).sum()
+            total += label.shape[0]
+    inner.args.drop = 1
+    acc = (correct / max(total, 1)).tolist()
+    return acc[0], acc[1], acc[2]

@@ -102,6 +102,10 @@ int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, const float* g
                  const float* beta, float eps, float momentum, float* running_mean,
                  float* running_var, float* mean, float* invstd, float* scale, float* shift,
                  gdl_stream_t s);
+/* Eval mode (reference model.eval() in valid(), main_dgl.py:186): scale/shift from the running stats. */
+int gdl_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, int C,
+                       gdl_stream_t s);
 /* y = [relu](x*scale + shift [+ res])  (BN-apply fused with ReLU backbone.py:46,57,66 and
  * the residual add backbone.py:65). */
 int gdl_bn_apply(const void* x, const void* res, void* y, int64_t P, int C, const float* scale,
