@@ -540,6 +540,69 @@ static int launch_wgrad(const WgradParams& p, const WgradPlan& w, cudaStream_t s
 int try_conv3x3_halo(int N, int H, int W, int Cs, int Cd, const void* src, const void* wt, int64_t wt_rows,
                      int64_t wt_k, void* dst, const void* add_src, int add_mode, int flip, cudaStream_t s);
 
+// conv_flat.cu
+int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t sH, int64_t sN, const void* src,
+                  const void* wt, int64_t wt_rows, int64_t wt_k, void* dst, int Hd, int Wd, int Cd,
+                  const void* add_src, int add_mode, cudaStream_t s);
+
+// Which TMA kernel serves a 3x3/s1 convolution.  Measured at the bench geometry (tools/conv_bench.py) the
+// flat-window kernel beats the 16x8-tile halo kernel on every layer (1.1x at 56x56 ... 2.1x at 7x7), so it
+// is the default; GDL_FLAT: 0 off, 1 only where the halo tiles are poorly filled, 2 always.
+static int flat_policy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GDL_FLAT");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+static bool prefer_flat_s1(int H, int W) {
+  const int pol = flat_policy();
+  if (pol == 0) return false;
+  if (pol >= 2) return true;
+  static int thr = -1;
+  if (thr < 0) {
+    const char* e = getenv("GDL_FLAT_HALO_UTIL_PCT");
+    thr = e ? atoi(e) : 80;
+  }
+  const int th = (H + 15) / 16, tw = (W + 7) / 8;
+  return 100 * H * W < thr * (th * 16 * tw * 8);
+}
+
+// conv_wgrad_flat.cu
+int64_t wgrad_flat_workspace_bytes(int N, int Ho, int Wo, int Ci, int Co, int R, int stride);
+int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R, int stride, const void* x,
+                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s);
+// GDL_WFLAT: 0 off, 1 where the halo wgrad kernel is not eligible or its 16x8 tiles are poorly filled, 2 always.
+static int wflat_policy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GDL_WFLAT");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static bool wflat_shape_ok(const gdl_conv_desc* d) {
+  if (d->Ci % 64 != 0 || d->R != d->S) return false;
+  if (d->R == 3) return d->pad == 1 && (d->stride == 1 || d->stride == 2);
+  return d->R == 1 && d->pad == 0 && (d->stride == 1 || d->stride == 2);
+}
+static bool prefer_wflat(const gdl_conv_desc* d) {
+  const int pol = wflat_policy();
+  if (pol == 0 || !wflat_shape_ok(d)) return false;
+  if (pol >= 2) return true;
+  if (d->R == 3 && d->stride == 1) {
+    static int thr = -1;
+    if (thr < 0) {
+      const char* e = getenv("GDL_FLAT_HALO_UTIL_PCT");
+      thr = e ? atoi(e) : 80;
+    }
+    const int th = (d->Hi + 15) / 16, tw = (d->Wi + 7) / 8;
+    return 100 * d->Hi * d->Wi < thr * (th * 16 * tw * 8);
+  }
+  return true;
+}
+
 // conv_wgrad_halo.cu
 int64_t wgrad_halo_workspace_bytes(int N, int H, int W, int Ci, int Co);
 int try_wgrad3x3_halo(int N, int H, int W, int Ci, int Co, const void* x, const void* dy, float* partial,
@@ -564,6 +627,10 @@ extern "C" int64_t gdl_conv_wgrad_workspace_bytes(const gdl_conv_desc* d) {
     int64_t h = wgrad_halo_workspace_bytes(d->N, d->Hi, d->Wi, d->Ci, d->Co);
     if (h > need) need = h;
   }
+  if (wflat_shape_ok(d)) {
+    int64_t f = wgrad_flat_workspace_bytes(d->N, d->Ho, d->Wo, d->Ci, d->Co, d->R, d->stride);
+    if (f > need) need = f;
+  }
   return need;
 }
 
@@ -586,8 +653,21 @@ extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w
   GDL_REQUIRE(desc_ok(d), "gdl_conv_fwd: bad descriptor");
   GDL_REQUIRE(x && w_packed && y, "gdl_conv_fwd: null pointer");
   if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1 && d->Ci % 64 == 0) {
+    if (prefer_flat_s1(d->Hi, d->Wi)) {
+      int rc = try_conv_flat(0, d->N, d->Hi, d->Wi, d->Ci, d->Ci, (int64_t)d->Wi * d->Ci,
+                             (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y, d->Ho, d->Wo,
+                             d->Co, nullptr, 0, (cudaStream_t)s);
+      if (rc != 0) return rc < 0 ? rc : GDL_OK;
+    }
     int rc = try_conv3x3_halo(d->N, d->Hi, d->Wi, d->Ci, d->Co, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y,
                               nullptr, 0, 0, (cudaStream_t)s);
+    if (rc != 0) return rc < 0 ? rc : GDL_OK;
+  }
+  if (d->R == 1 && d->S == 1 && d->pad == 0 && d->Ci % 64 == 0 && d->Ci <= 128 && flat_policy() != 0) {
+    // 1x1 (stride 1 or 2): a single tap over the strided view x[:, ::stride, ::stride, :]
+    int rc = try_conv_flat(3, d->N, d->Ho, d->Wo, d->Ci, (int64_t)d->stride * d->Ci,
+                           (int64_t)d->stride * d->Wi * d->Ci, (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co,
+                           (int64_t)d->Ci, y, d->Ho, d->Wo, d->Co, nullptr, 0, (cudaStream_t)s);
     if (rc != 0) return rc < 0 ? rc : GDL_OK;
   }
   ConvParams p{};
@@ -615,8 +695,27 @@ extern "C" int gdl_conv_dgrad(const gdl_conv_desc* d, const void* dy, const void
   GDL_REQUIRE(dy && w_packed_T && dx, "gdl_conv_dgrad: null pointer");
   GDL_REQUIRE(add_mode >= 0 && add_mode <= 2 && (add_mode == 0 || add_src), "gdl_conv_dgrad: bad add_mode");
   if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1) {
+    if (prefer_flat_s1(d->Hi, d->Wi) && add_mode != 2) {
+      int rc = try_conv_flat(1, d->N, d->Ho, d->Wo, d->Co, d->Co, (int64_t)d->Wo * d->Co,
+                             (int64_t)d->Ho * d->Wo * d->Co, dy, w_packed_T, d->Ci, 9 * (int64_t)d->Co, dx, d->Hi,
+                             d->Wi, d->Ci, add_src, add_mode, (cudaStream_t)s);
+      if (rc != 0) return rc < 0 ? rc : GDL_OK;
+    }
     int rc = try_conv3x3_halo(d->N, d->Hi, d->Wi, d->Co, d->Ci, dy, w_packed_T, d->Ci, 9 * (int64_t)d->Co, dx,
                               add_src, add_mode, 1, (cudaStream_t)s);
+    if (rc != 0) return rc < 0 ? rc : GDL_OK;
+  }
+  if (d->R == 3 && d->S == 3 && d->stride == 2 && d->pad == 1 && add_mode != 1 && flat_policy() != 0) {
+    // four output-parity classes, 1+2+2+4 taps instead of 9 zero-stuffed ones
+    int rc = try_conv_flat(2, d->N, d->Ho, d->Wo, d->Co, d->Co, (int64_t)d->Wo * d->Co,
+                           (int64_t)d->Ho * d->Wo * d->Co, dy, w_packed_T, d->Ci, 9 * (int64_t)d->Co, dx, d->Hi,
+                           d->Wi, d->Ci, add_src, add_mode, (cudaStream_t)s);
+    if (rc != 0) return rc < 0 ? rc : GDL_OK;
+  }
+  if (d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0 && add_mode != 2 && flat_policy() != 0) {
+    int rc = try_conv_flat(3, d->N, d->Ho, d->Wo, d->Co, d->Co, (int64_t)d->Wo * d->Co,
+                           (int64_t)d->Ho * d->Wo * d->Co, dy, w_packed_T, d->Ci, (int64_t)d->Co, dx, d->Hi, d->Wi,
+                           d->Ci, add_src, add_mode, (cudaStream_t)s);
     if (rc != 0) return rc < 0 ? rc : GDL_OK;
   }
   ConvParams p{};
@@ -646,6 +745,19 @@ extern "C" int gdl_conv_wgrad(const gdl_conv_desc* d, int ci_real, const void* x
   GDL_REQUIRE(desc_ok(d), "gdl_conv_wgrad: bad descriptor");
   GDL_REQUIRE(x && dy && dw_oihw && workspace, "gdl_conv_wgrad: null pointer");
   GDL_REQUIRE(ci_real > 0 && ci_real <= d->Ci, "gdl_conv_wgrad: ci_real out of range");
+  if (ci_real == d->Ci && prefer_wflat(d)) {
+    int ns = try_wgrad_flat(d->N, d->Hi, d->Wi, d->Ho, d->Wo, d->Ci, d->Co, d->R, d->stride, x, dy, (float*)workspace,
+                            workspace_bytes, (cudaStream_t)s);
+    if (ns < 0) return ns;
+    if (ns > 0) {
+      int Kp = d->R * d->S * d->Ci;
+      int64_t total = (int64_t)Kp * d->Co;
+      wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)s>>>(
+          (const float*)workspace, dw_oihw, ns, Kp, d->Co, d->Ci, ci_real, d->R, d->S);
+      GDL_CHECK_LAUNCH("wgrad_reduce_kernel");
+      return GDL_OK;
+    }
+  }
   if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1 && d->Ci % 64 == 0 && ci_real == d->Ci) {
     int ns = try_wgrad3x3_halo(d->N, d->Hi, d->Wi, d->Ci, d->Co, x, dy, (float*)workspace, workspace_bytes,
                                (cudaStream_t)s);

@@ -1,0 +1,373 @@
+// conv_flat.cu — "flat window" TMA implicit GEMM for every convolution whose taps are pure
+// shifts on ONE pixel grid: 3x3/s1 forward and data-gradient at any map size (reference
+// models/backbone.py:44,47 conv3x3), the data-gradient of the 3x3/s2 convolutions
+// (backbone.py:44 with stride 2, split into its four output-parity classes so that only the
+// structurally non-zero taps are multiplied), the 1x1/s2 downsample forward (backbone.py:142-145,
+// through a strided tensor-map view) and the 1x1 data-gradient on the compact grid.
+//
+// The source grid [N,Hs,Ws] is indexed by ONE flat pixel index with a single zero pad column and
+// a single zero pad row per image:
+//        q = n*IS + h*P + w,   P = Ws+1,  IS = (Hs+1)*P,   h in [0,Hs], w in [0,Ws]
+// (w == Ws is the pad column shared by the right edge of row h and the left edge of row h+1; h == Hs
+// is the pad row shared by image n's bottom and image n+1's top).  A filter tap (dh,dw) is then the
+// constant row shift dh*P+dw, for every pixel, across row and image boundaries.  An output tile is
+// 128 (or 2x128) CONSECUTIVE q; its operand window [q0+smin, q0+M+smax) is brought into shared memory
+// by one TMA box per padded row ({64 ch, P px}: the pad column/row are TMA out-of-bounds zero fill),
+// and each tap's A operand is a row-shifted view of that window (the tensor core, like TMA, swizzles on
+// absolute shared-memory address bits, so starts offset by whole 128-byte rows need no re-layout).
+// Utilisation is Hs*Ws/((Hs+1)(Ws+1)) for every map size — 77 % at 7x7 and 9x6 where 16x8 pixel tiles
+// reach 38-42 % — and the input is fetched from L2 once per 64-channel slab instead of once per tap.
+//   warp 5 lane 0 : TMA producer (window ring + weight ring)
+//   warp 4 lane 0 : tcgen05.mma issuer; MT accumulators share every weight tile
+//   warps 0-3     : epilogue (TMEM -> registers -> bf16 NHWC, optional residual add), double-buffered
+#include <string.h>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace gdl {
+using namespace tc05;
+
+constexpr int kFlatThreads = 192;
+constexpr int kFlatMaxTaps = 9;
+constexpr int kFlatSmemBudget = 227 * 1024 - 2048;
+
+struct FlatTap {
+  int shift;  // row shift on the flat grid (may be negative)
+  int wk;     // k offset of the tap's weight columns in the packed matrix
+};
+
+struct FlatParams {
+  CUtensorMap tm_x;  // {Cs, Ws, Hs, N} view of the source, box {64, P, 1, 1}
+  CUtensorMap tm_w;  // {K, rows} packed weights, box {64, BN}
+  bf16* dst;
+  const bf16* add_src;
+  int add_mode;  // 0 none; 1 add_src has dst's shape; 2 add_src lives on the source grid (parity class (0,0) only)
+  int N, Hs, Ws, Cs;
+  int Hd, Wd, Cd;
+  int P, IS;
+  int dscale;  // dst pixel = (h*dscale + ph, w*dscale + pw)
+  int nclass;
+  int ntaps[4];
+  int ph[4], pw[4];
+  FlatTap taps[4][kFlatMaxTaps];
+  int smin, smax;
+  int mtiles, ntiles, items_total;
+  int win_stage_bytes, win_stages;
+};
+
+__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
+  int q = a / b;
+  return (a - q * b < 0) ? q - 1 : q;
+}
+
+template <int BN, int MT, int WST>
+__global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid_constant__ FlatParams p) {
+  constexpr int W_BYTES = BN * 128;
+  constexpr int TM = MT * 128;
+  constexpr int kMaxWin = 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int w_off = p.win_stages * p.win_stage_bytes;
+  const int bar_off = w_off + WST * W_BYTES;
+  uint64_t* win_full = reinterpret_cast<uint64_t*>(smem + bar_off);
+  uint64_t* win_empty = win_full + kMaxWin;
+  uint64_t* w_full = win_empty + kMaxWin;
+  uint64_t* w_empty = w_full + WST;
+  uint64_t* tmem_full = w_empty + WST;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int slabs = p.Cs >> 6;
+  const int WS = p.win_stages;
+  const int per_class = p.ntiles * p.mtiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < kMaxWin; ++i) {
+      mbar_init(&win_full[i], 1);
+      mbar_init(&win_empty[i], 1);
+    }
+    for (int i = 0; i < WST; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 2 * MT * BN);
+    tmem_relinquish();
+  }
+  if (tid == 5 * 32) {
+    tma_prefetch_desc(&p.tm_x);
+    tma_prefetch_desc(&p.tm_w);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (tid == 5 * 32) {
+    // ------------------------------ TMA producer ------------------------------
+    const int rows_img = p.Hs + 1;
+    const uint32_t row_bytes = (uint32_t)p.P * 128u;
+    int wincount = 0, wcount = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
+      const int cls = item / per_class;
+      const int rem = item - cls * per_class;
+      const int nt = rem / p.mtiles;
+      const int q0 = (rem - nt * p.mtiles) * TM;
+      const int n0 = nt * BN;
+      const int rho_a = floor_div(q0 + p.smin, p.P);
+      const int rho_b = floor_div(q0 + TM + p.smax - 1, p.P);
+      const int nrows = rho_b - rho_a + 1;
+      const int ntap = p.ntaps[cls];
+      for (int slab = 0; slab < slabs; ++slab, ++wincount) {
+        const int ws = wincount % WS;
+        if (wincount >= WS) mbar_wait(&win_empty[ws], ((wincount / WS) - 1) & 1);
+        mbar_arrive_expect_tx(&win_full[ws], (uint32_t)nrows * row_bytes);
+        const uint32_t sdst = smem_base + ws * p.win_stage_bytes;
+        for (int i = 0; i < nrows; ++i) {
+          const int rho = rho_a + i;
+          const int n = floor_div(rho, rows_img);
+          const int h = rho - n * rows_img;
+          tma_load_4d(sdst + i * row_bytes, &p.tm_x, &win_full[ws], slab * 64, 0, h, n);
+        }
+        for (int t = 0; t < ntap; ++t, ++wcount) {
+          const int st = wcount % WST;
+          if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
+          mbar_arrive_expect_tx(&w_full[st], W_BYTES);
+          tma_load_2d(smem_base + w_off + st * W_BYTES, &p.tm_w, &w_full[st], p.taps[cls][t].wk + slab * 64, n0);
+        }
+      }
+    }
+  } else if (tid == 4 * 32) {
+    // ------------------------------ MMA issuer ------------------------------
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t ab_hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo_sw128(smem_base, 16), b_lo0 = desc_lo_sw128(smem_base + w_off, 16);
+    int wincount = 0, wcount = 0, it = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++it) {
+      const int cls = item / per_class;
+      const int rem = item - cls * per_class;
+      const int nt = rem / p.mtiles;
+      const int q0 = (rem - nt * p.mtiles) * TM;
+      const int rho_a = floor_div(q0 + p.smin, p.P);
+      const int o = q0 + p.smin - rho_a * p.P;  // first window row inside the stage
+      const int ntap = p.ntaps[cls];
+      const int acc = it & 1;
+      if (it >= 2) {
+        mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+      for (int slab = 0; slab < slabs; ++slab, ++wincount) {
+        const int ws = wincount % WS;
+        mbar_wait(&win_full[ws], (wincount / WS) & 1);
+        tc_fence_after();
+        const uint32_t a_win = a_lo0 + ((ws * p.win_stage_bytes) >> 4) + (o - p.smin) * 8;
+        for (int t = 0; t < ntap; ++t, ++wcount) {
+          const int st = wcount % WST;
+          mbar_wait(&w_full[st], (wcount / WST) & 1);
+          tc_fence_after();
+          const uint32_t a_lo = a_win + p.taps[cls][t].shift * 8;
+          const uint32_t b_lo = b_lo0 + st * (W_BYTES >> 4);
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_bf16_ss(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi), desc_join(b_lo + 2 * k, ab_hi),
+                          idesc, (slab | t | k) != 0 ? 1u : 0u);
+          }
+          mma_commit(&w_empty[st]);
+        }
+        mma_commit(&win_empty[ws]);
+      }
+      mma_commit(&tmem_full[acc]);
+    }
+  } else if (warp < 4) {
+    // ------------------------------ epilogue ------------------------------
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++it) {
+      const int cls = item / per_class;
+      const int rem = item - cls * per_class;
+      const int nt = rem / p.mtiles;
+      const int q0 = (rem - nt * p.mtiles) * TM;
+      const int n0 = nt * BN;
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16) + acc * (MT * BN);
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        const int q = q0 + j * 128 + tid;
+        const int n = q / p.IS;
+        const int r2 = q - n * p.IS;
+        const int h = r2 / p.P, w = r2 - h * p.P;
+        const int hd = h * p.dscale + p.ph[cls], wd = w * p.dscale + p.pw[cls];
+        const bool valid = n < p.N && h < p.Hs && w < p.Ws && hd < p.Hd && wd < p.Wd;
+        bf16* out = p.dst + ((size_t)((size_t)n * p.Hd + hd) * p.Wd + wd) * p.Cd + n0;
+        const bf16* add = nullptr;
+        if (valid && p.add_mode == 1)
+          add = p.add_src + ((size_t)((size_t)n * p.Hd + hd) * p.Wd + wd) * p.Cd + n0;
+        else if (valid && p.add_mode == 2 && (p.ph[cls] | p.pw[cls]) == 0)
+          add = p.add_src + ((size_t)((size_t)n * p.Hs + h) * p.Ws + w) * p.Cd + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + j * BN + c0, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[g * 8 + i]);
+              if (add != nullptr) {
+                float a[8];
+                uint4 u = *reinterpret_cast<const uint4*>(add + c0 + g * 8);
+                unpack8(u, a);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += a[i];
+              }
+              *reinterpret_cast<uint4*>(out + c0 + g * 8) = pack8(f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 2 * MT * BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <int BN, int MT, int WST>
+static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
+  constexpr int TM = MT * 128;
+  const int nrows_max = (TM + p.smax - p.smin - 1 + p.P - 1) / p.P + 1;
+  p.win_stage_bytes = (nrows_max * p.P * 128 + 1023) / 1024 * 1024;
+  const int fixed = WST * BN * 128 + 512;
+  int ws = (kFlatSmemBudget - fixed) / p.win_stage_bytes;
+  if (ws > 4) ws = 4;
+  if (ws < 2) return 0;  // window does not fit twice: not eligible
+  p.win_stages = ws;
+  p.mtiles = int((Q + TM - 1) / TM);
+  p.ntiles = p.Cd / BN;
+  p.items_total = p.nclass * p.ntiles * p.mtiles;
+  const int total = ws * p.win_stage_bytes + fixed + 1024;
+  static int attr_set = 0;
+  if (attr_set < total) {
+    cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_flat)");
+    attr_set = 227 * 1024;
+  }
+  int grid = p.items_total < kNumSMs ? p.items_total : kNumSMs;
+  conv_flat_kernel<BN, MT, WST><<<grid, kFlatThreads, total, s>>>(p);
+  GDL_CHECK_LAUNCH("conv_flat_kernel");
+  return 1;
+}
+
+static int env_int3(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// kind: 0 forward 3x3/s1, 1 dgrad 3x3/s1, 2 dgrad 3x3/s2 (parity classes), 3 single tap (1x1).
+// src is the tensor the taps slide over, viewed as [N,Hs,Ws,Cs] with element strides (sW,sH,sN);
+// wt is [Cd rows][K] bf16 with k = tap*Cs + c.  Returns 1 when launched, 0 when not eligible, <0 on error.
+int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t sH, int64_t sN, const void* src,
+                  const void* wt, int64_t wt_rows, int64_t wt_k, void* dst, int Hd, int Wd, int Cd,
+                  const void* add_src, int add_mode, cudaStream_t s) {
+  static const int mt_force = env_int3("GDL_FLAT_MT", 0);
+  if (Cs % 64 != 0 || Cd % 64 != 0) return 0;
+  const int P = Ws + 1;
+  if (P > 256) return 0;
+  const int64_t IS = (int64_t)(Hs + 1) * P;
+  const int64_t Q = (int64_t)N * IS;
+  if (Q + 2 * P + 1024 >= ((int64_t)1 << 31)) return 0;
+  FlatParams p;
+  memset(&p, 0, sizeof(p));
+  p.dst = (bf16*)dst;
+  p.add_src = (const bf16*)add_src;
+  p.add_mode = add_mode;
+  p.N = N; p.Hs = Hs; p.Ws = Ws; p.Cs = Cs;
+  p.Hd = Hd; p.Wd = Wd; p.Cd = Cd;
+  p.P = P; p.IS = (int)IS;
+  p.dscale = 1;
+  p.nclass = 1;
+  if (kind == 0 || kind == 1) {
+    p.ntaps[0] = 9;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        FlatTap& t = p.taps[0][r * 3 + c];
+        t.shift = kind == 0 ? (r - 1) * P + (c - 1) : (1 - r) * P + (1 - c);
+        t.wk = (r * 3 + c) * Cs;
+      }
+  } else if (kind == 2) {
+    p.dscale = 2;
+    p.nclass = 4;
+    // order the classes heavy-first so the persistent loop's tail is made of cheap items
+    const int cph[4] = {1, 1, 0, 0}, cpw[4] = {1, 0, 1, 0};
+    for (int c = 0; c < 4; ++c) {
+      p.ph[c] = cph[c];
+      p.pw[c] = cpw[c];
+      int nr = 0, rr[2], dh[2];
+      if (cph[c] == 0) { rr[0] = 1; dh[0] = 0; nr = 1; } else { rr[0] = 0; dh[0] = 1; rr[1] = 2; dh[1] = 0; nr = 2; }
+      int nc = 0, cc[2], dw[2];
+      if (cpw[c] == 0) { cc[0] = 1; dw[0] = 0; nc = 1; } else { cc[0] = 0; dw[0] = 1; cc[1] = 2; dw[1] = 0; nc = 2; }
+      int k = 0;
+      for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < nc; ++b) {
+          p.taps[c][k].shift = dh[a] * P + dw[b];
+          p.taps[c][k].wk = (rr[a] * 3 + cc[b]) * Cs;
+          ++k;
+        }
+      p.ntaps[c] = k;
+    }
+  } else {
+    p.ntaps[0] = 1;
+    p.taps[0][0].shift = 0;
+    p.taps[0][0].wk = 0;
+  }
+  p.smin = 0;
+  p.smax = 0;
+  for (int c = 0; c < p.nclass; ++c)
+    for (int t = 0; t < p.ntaps[c]; ++t) {
+      if (p.taps[c][t].shift < p.smin) p.smin = p.taps[c][t].shift;
+      if (p.taps[c][t].shift > p.smax) p.smax = p.taps[c][t].shift;
+    }
+  const int BN = (Cd % 128 == 0) ? 128 : 64;
+  const CUtensorMap* tx = tmap_view4(src, Cs, Ws, Hs, N, sW, sH, sN, P);
+  const CUtensorMap* tw = tmap_rows(wt, wt_rows, wt_k, BN);
+  if (!tx || !tw) return GDL_ECUDA;
+  p.tm_x = *tx;
+  p.tm_w = *tw;
+  // MT = 2 halves the weight traffic per MMA (measured 1.2-1.4x on every layer of the bench geometry);
+  // MT = 1 only when the problem would not fill one wave of CTAs otherwise
+  const int64_t items2 = (int64_t)p.nclass * (Cd / BN) * ((Q + 255) / 256);
+  int mt = items2 >= kNumSMs ? 2 : 1;
+  if (mt_force) mt = mt_force;
+  int rc = 0;
+  if (BN == 128) {
+    if (mt == 2) rc = launch_flat<128, 2, 4>(p, Q, s);
+    if (rc == 0) rc = launch_flat<128, 1, 4>(p, Q, s);
+  } else {
+    if (mt == 2) rc = launch_flat<64, 2, 6>(p, Q, s);
+    if (rc == 0) rc = launch_flat<64, 1, 6>(p, Q, s);
+  }
+  return rc;
+}
+
+}  // namespace gdl

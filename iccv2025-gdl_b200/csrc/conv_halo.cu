@@ -101,6 +101,19 @@ const CUtensorMap* tmap_rows(const void* ptr, int64_t rows, int64_t K, int box_r
   return cached_tmap(key, 2, const_cast<void*>(ptr), dims, strides, box);
 }
 
+// Strided 4-D view {C, W, H, N} of a bf16 tensor (element strides sW, sH, sN; channels contiguous),
+// box {64, box_w, 1, 1}: one padded pixel row per TMA operation (conv_flat.cu).  box_w may exceed W:
+// the surplus pixels are out-of-bounds zero fill.
+const CUtensorMap* tmap_view4(const void* ptr, int C, int W, int H, int N, int64_t sW, int64_t sH, int64_t sN,
+                              int box_w) {
+  TmapKey key{{(uint64_t)ptr, ((uint64_t)N << 32) | (uint32_t)H, ((uint64_t)W << 32) | (uint32_t)C,
+               ((uint64_t)box_w << 32) | 0x40001u, (uint64_t)sW ^ ((uint64_t)sH << 24), (uint64_t)sN}};
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  return cached_tmap(key, 4, const_cast<void*>(ptr), dims, strides, box);
+}
+
 // 16-channel (32-byte rows, 32-byte swizzle) variants used by the space-to-depth stems.
 const CUtensorMap* tmap_nhwc16(const void* ptr, int N, int H, int W, int box_w, int box_h) {
   TmapKey key{{(uint64_t)ptr, ((uint64_t)N << 32) | (uint32_t)H, ((uint64_t)W << 32) | 16u,

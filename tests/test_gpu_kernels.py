@@ -35,6 +35,11 @@ CONV_CASES = [
     (4, 17, 12, 128, 256, 3, 2, 1),
     (2, 7, 7, 512, 512, 3, 1, 1),
     (5, 56, 56, 64, 64, 3, 1, 1),
+    (3, 7, 5, 128, 256, 1, 1, 0),
+    (6, 28, 28, 128, 128, 3, 1, 1),
+    (3, 65, 47, 64, 64, 3, 1, 1),
+    (5, 14, 14, 128, 256, 3, 2, 1),
+    (40, 9, 6, 512, 512, 3, 1, 1),
 ]
 
 
