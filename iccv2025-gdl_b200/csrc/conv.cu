@@ -573,12 +573,13 @@ static bool prefer_flat_s1(int H, int W) {
 int64_t wgrad_flat_workspace_bytes(int N, int Ho, int Wo, int Ci, int Co, int R, int stride);
 int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R, int stride, const void* x,
                    const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s);
-// GDL_WFLAT: 0 off, 1 where the halo wgrad kernel is not eligible or its 16x8 tiles are poorly filled, 2 always.
+// GDL_WFLAT: 0 off, 1 where the halo wgrad kernel is not eligible or its 16x8 tiles are poorly filled, 2 always
+// (default: measured equal or faster than the halo kernel on every layer of the bench geometry).
 static int wflat_policy() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GDL_WFLAT");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 2;
   }
   return v;
 }

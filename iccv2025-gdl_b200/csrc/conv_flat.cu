@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = warp_uniform_idx();
   const int slabs = p.Cs >> 6;
   const int WS = p.win_stages;
   const int per_class = p.ntiles * p.mtiles;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
 
-  if (tid == 5 * 32) {
+  if (warp == 5 && elect_one()) {
     // ------------------------------ TMA producer ------------------------------
     const int rows_img = p.Hs + 1;
     const uint32_t row_bytes = (uint32_t)p.P * 128u;
@@ -146,8 +146,16 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
         }
       }
     }
-  } else if (tid == 4 * 32) {
+  } else if (warp == 4 && elect_one()) {
     // ------------------------------ MMA issuer ------------------------------
+    // The single issuing thread is instruction-latency bound (an N=64 MMA retires in 32 clocks), so every
+    // operand must live in uniform registers.  The TMEM base read from shared memory would not (ptxas emits
+    // an ELECT/R2UR waterfall per MMA), but with one CTA per SM (>= 116 KB of shared memory, enforced at
+    // launch) the allocation always starts at column 0: check it once and use the constant.
+    if (tmem_base != 0) {
+      printf("gdl: conv_flat expects TMEM base 0, got %u\n", tmem_base);
+      __trap();
+    }
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
     const uint32_t ab_hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo_sw128(smem_base, 16), b_lo0 = desc_lo_sw128(smem_base + w_off, 16);
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
         mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1);
         tc_fence_after();
       }
-      const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+      const uint32_t d_tmem = acc * (MT * BN);
       for (int slab = 0; slab < slabs; ++slab, ++wincount) {
         const int ws = wincount % WS;
         mbar_wait(&win_full[ws], (wincount / WS) & 1);
@@ -177,12 +185,14 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
           tc_fence_after();
           const uint32_t a_lo = a_win + p.taps[cls][t].shift * 8;
           const uint32_t b_lo = b_lo0 + st * (W_BYTES >> 4);
+          const uint32_t first = (slab | t) != 0 ? 1u : 0u;
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
+            mma_bf16_ss(d_tmem + j * BN, desc_join(a_lo + j * 1024, ab_hi), desc_join(b_lo, ab_hi), idesc, first);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_bf16_ss(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi), desc_join(b_lo + 2 * k, ab_hi),
-                          idesc, (slab | t | k) != 0 ? 1u : 0u);
+            for (int k = 1; k < 4; ++k)
+              mma_bf16_acc(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi), desc_join(b_lo + 2 * k, ab_hi),
+                           idesc);
           }
           mma_commit(&w_empty[st]);
         }
@@ -265,7 +275,8 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   p.mtiles = int((Q + TM - 1) / TM);
   p.ntiles = p.Cd / BN;
   p.items_total = p.nclass * p.ntiles * p.mtiles;
-  const int total = ws * p.win_stage_bytes + fixed + 1024;
+  int total = ws * p.win_stage_bytes + fixed + 1024;
+  if (total < 116 * 1024) total = 116 * 1024;  // one CTA per SM: the kernel relies on TMEM base 0
   static int attr_set = 0;
   if (attr_set < total) {
     cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST>, cudaFuncAttributeMaxDynamicSharedMemorySize,

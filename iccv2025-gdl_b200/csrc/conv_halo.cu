@@ -102,15 +102,16 @@ const CUtensorMap* tmap_rows(const void* ptr, int64_t rows, int64_t K, int box_r
 }
 
 // Strided 4-D view {C, W, H, N} of a bf16 tensor (element strides sW, sH, sN; channels contiguous),
-// box {64, box_w, 1, 1}: one padded pixel row per TMA operation (conv_flat.cu).  box_w may exceed W:
-// the surplus pixels are out-of-bounds zero fill.
+// box {64, box_w, box_h, box_n}: whole padded pixel rows / row bands / images per TMA operation
+// (conv_flat.cu, conv_wgrad_flat.cu).  box_w may exceed W: the surplus pixels are out-of-bounds zero fill.
 const CUtensorMap* tmap_view4(const void* ptr, int C, int W, int H, int N, int64_t sW, int64_t sH, int64_t sN,
-                              int box_w) {
+                              int box_w, int box_h, int box_n) {
   TmapKey key{{(uint64_t)ptr, ((uint64_t)N << 32) | (uint32_t)H, ((uint64_t)W << 32) | (uint32_t)C,
-               ((uint64_t)box_w << 32) | 0x40001u, (uint64_t)sW ^ ((uint64_t)sH << 24), (uint64_t)sN}};
+               ((uint64_t)box_w << 32) | ((uint64_t)box_h << 16) | (uint64_t)box_n | 0x80000000ull,
+               (uint64_t)sW ^ ((uint64_t)sH << 24), (uint64_t)sN}};
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
   return cached_tmap(key, 4, const_cast<void*>(ptr), dims, strides, box);
 }
 

@@ -1,18 +1,23 @@
-// conv_wgrad_flat.cu — weight gradient on the flat pixel grid of conv_flat.cu (reference
-// models/backbone.py:44,47,142-145 conv3x3 / conv1x1 backward, reached from main_dgl.py:110):
+// conv_wgrad_flat.cu — weight gradient on flat pixel windows (reference models/backbone.py:44,47,
+// 142-145 conv3x3 / conv1x1 backward, reached from main_dgl.py:110):
 //
-//   dW[co][tap][ci] = sum over flat pixels q   dY[q][co] * X_plane(tap)[q + shift(tap)][ci]
+//   dW[co][tap][ci] = sum over pixels   dY[pix][co] * X_plane(tap)[pix + (dr,dc)(tap)][ci]
 //
-// q enumerates the OUTPUT grid with one zero pad column per row and one zero pad row per image
-// (q = n*IS + h*P + w, P = Wo+1, IS = (Ho+1)*P), so a filter tap is a constant row shift and the
-// reduction runs over consecutive q regardless of the map size: 7x7 and 9x6 maps fill 77 % of every
-// 128-pixel step where 16x8 pixel tiles fill 38-42 %.  Pad pixels contribute nothing because both
-// windows are written by TMA with out-of-bounds zero fill.  Stride-2 convolutions read X through its
-// four parity planes (strided tensor-map views on the output grid): tap (r,s) lives in plane
-// ((r+1)&1, (s+1)&1) at shift floor((r-1)/2)*P + floor((s-1)/2).
-//   Both operands are MN-major views of the row windows (rows = pixels = the reduction dimension);
-//   D[(tap,ci) 128 rows][BN co] accumulates in TMEM over the CTA's pixel range (split-K), fp32
-//   partials are written once per CTA and reduced in a fixed order (deterministic).
+// One pipeline stage is ONE TMA box per operand slab: either a band of RB full-width rows of one
+// image, or (small maps) NI whole images.  Boxes are P = Wo+1 pixels wide — the extra column is TMA
+// out-of-bounds zero fill and serves as the right pad of a row and the left pad of the next — and the
+// X box starts rmin rows above the dY box, so inside shared memory pixel i of the dY window meets its
+// tap (dr,dc) at X row i + (dr-rmin)*P + dc: a constant row shift, for every pixel of the stage.  Rows
+// above/below an image are out-of-bounds zero fill as well; whole-image boxes are Ho+1 rows per image so
+// that one zero row is both the bottom pad of image n and the top pad of image n+1.  Zero pixels (pads,
+// rows past the image, the 16-row K-step tail) contribute nothing; the slack rows around the windows are
+// zeroed once at kernel start and never written again.  7x7 maps fill 77 % of every K step (16x8 pixel
+// tiles: 38 %), 14x14 87 %, 65x47 98 %.
+//   Stride-2 convolutions read X through its four parity planes (strided tensor-map views on the
+//   output grid): tap (r,s) lives in plane ((r+1)&1, (s+1)&1) at (dr,dc) = (r==0 ? -1 : 0, s==0 ? -1 : 0).
+//   Both operands are MN-major (rows = pixels = the reduction dimension); D[(tap,ci) 128][BN co]
+//   accumulates in TMEM over the CTA's stage range (split-K); fp32 partials are written once per CTA and
+//   reduced in a fixed order (deterministic).
 //   MODE 0 (Ci == 64): an M tile is TWO taps x 64 ci (second block = same window, LBO rows further).
 //   MODE 1 (Ci >= 128): an M tile is one tap x 128 ci (two slab windows, LBO = slab stride).
 #include <string.h>
@@ -23,35 +28,33 @@ namespace gdl {
 using namespace tc05;
 
 constexpr int kWfThreads = 192;
-constexpr int kWfTM = 128;  // pixels per pipeline stage
 constexpr int kWfMaxUnits = 5;
+constexpr int kWfMaxPx = 256;
 
 struct WfUnit {
-  int shift0;  // row shift of block 0
-  int lbo;     // MODE 0: byte distance to the second tap's rows; MODE 1: unused
+  int shift;       // X row of block 0 relative to the dY pixel, in the stage's row units
+  int lbo;         // MODE 0: byte distance to the second tap's rows
   int tap0, tap1;  // linear tap indices (r*S+s) of the two 64-row blocks; tap1 < 0: unused block
 };
 struct WfJobType {
-  int plane, nunits, smin, smax;
+  int plane, nunits, rmin;
   WfUnit u[kWfMaxUnits];
 };
 struct WfParams {
-  CUtensorMap tm_x[4];
-  CUtensorMap tm_dy;
-  float* partial;  // [splits][Kp][Co]
-  int N, Hs, Ws, Ci, Co, P, IS;
+  CUtensorMap tm_x[4];  // box {64, P, xrows, NI}
+  CUtensorMap tm_dy;    // box {64, P, dyrows, NI}
+  float* partial;       // [splits][Kp][Co]
+  int Ci, Co, Kp;
   int ntypes;
   WfJobType jt[4];
   int ci_tiles, co_tiles;
+  int NI, RB, nbands;   // stage = NI whole images (nbands == 1, RB == Ho+1) or one RB-row band of one image
+  int ksteps;           // ceil(stage pixels / 16)
   int tiles_total, tiles_per_split;
   int xwin_bytes, dywin_bytes, stage_bytes, stages;
-  int Kp;
+  uint32_t tx_bytes;
+  int smem_bytes;
 };
-
-__device__ __forceinline__ int wf_floor_div(int a, int b) {
-  int q = a / b;
-  return (a - q * b < 0) ? q - 1 : q;
-}
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __grid_constant__ WfParams p) {
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
   uint64_t* empty = full + kMaxSt;
   uint64_t* tmem_full = empty + kMaxSt;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = warp_uniform_idx();
   const int ST = p.stages;
   const int t0 = blockIdx.x * p.tiles_per_split;
   const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
@@ -75,6 +78,12 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
   const int ci0 = (y / p.co_tiles) * (NS * 64);
   const WfJobType& jt = p.jt[type];
 
+  // zero the stage buffers once: the slack rows around the TMA boxes must read as zero forever
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (p.stages * p.stage_bytes) >> 4;
+    for (int i = tid; i < n16; i += kWfThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
   if (tid == 0) {
     for (int i = 0; i < kMaxSt; ++i) {
       mbar_init(&full[i], 1);
@@ -91,6 +100,7 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
     tma_prefetch_desc(&p.tm_x[jt.plane]);
     tma_prefetch_desc(&p.tm_dy);
   }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -98,63 +108,79 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
   const uint32_t smem_base = smem_u32(smem);
   const int dy_off = NS * p.xwin_bytes;
 
-  if (tid == 5 * 32) {
+  if (warp == 5 && elect_one()) {
     // ------------------------------ TMA producer ------------------------------
-    const int rows_img = p.Hs + 1;
-    const uint32_t row_bytes = (uint32_t)p.P * 128u;
     const CUtensorMap* tmx = &p.tm_x[jt.plane];
     int it = 0;
     for (int t = t0; t < t1; ++t, ++it) {
-      const int q0 = t * kWfTM;
+      int n0, h0;
+      if (p.nbands == 1) {
+        n0 = t * p.NI;
+        h0 = 0;
+      } else {
+        n0 = t / p.nbands;
+        h0 = (t - n0 * p.nbands) * p.RB;
+      }
       const int st = it % ST;
       if (it >= ST) mbar_wait(&empty[st], ((it / ST) - 1) & 1);
-      const int xa = wf_floor_div(q0 + jt.smin, p.P), xb = wf_floor_div(q0 + kWfTM + jt.smax - 1, p.P);
-      const int da = q0 / p.P, db = (q0 + kWfTM - 1) / p.P;
-      const int nx = xb - xa + 1, nd = db - da + 1;
-      mbar_arrive_expect_tx(&full[st], (uint32_t)(NS * nx + NB * nd) * row_bytes);
+      mbar_arrive_expect_tx(&full[st], p.tx_bytes);
       const uint32_t sbase = smem_base + st * p.stage_bytes;
-      for (int i = 0; i < nx; ++i) {
-        const int rho = xa + i;
-        const int n = wf_floor_div(rho, rows_img);
-        const int h = rho - n * rows_img;
 #pragma unroll
-        for (int sl = 0; sl < NS; ++sl)
-          tma_load_4d(sbase + sl * p.xwin_bytes + i * row_bytes, tmx, &full[st], ci0 + sl * 64, 0, h, n);
-      }
-      for (int i = 0; i < nd; ++i) {
-        const int rho = da + i;
-        const int n = rho / rows_img;
-        const int h = rho - n * rows_img;
+      for (int sl = 0; sl < NS; ++sl)  // +128: one zero row in front of the X box
+        tma_load_4d(sbase + sl * p.xwin_bytes + 128, tmx, &full[st], ci0 + sl * 64, 0, h0 + jt.rmin, n0);
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
-          tma_load_4d(sbase + dy_off + b * p.dywin_bytes + i * row_bytes, &p.tm_dy, &full[st], co0 + b * 64, 0, h, n);
-      }
+      for (int b = 0; b < NB; ++b)
+        tma_load_4d(sbase + dy_off + b * p.dywin_bytes, &p.tm_dy, &full[st], co0 + b * 64, 0, h0, n0);
     }
-  } else if (tid == 4 * 32) {
+  } else if (warp == 4 && elect_one()) {
     // ------------------------------ MMA issuer ------------------------------
+    // One thread issues every MMA and is instruction-latency bound: all operands stay in uniform registers
+    // (the kernel owns all 512 TMEM columns, so the base is column 0 — checked), the unit loop is unrolled
+    // per unit count, and only the very first K step carries the "overwrite" predicate.
+    if (tmem_base != 0) {
+      printf("gdl: conv_wgrad_flat expects TMEM base 0, got %u\n", tmem_base);
+      __trap();
+    }
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
     const uint32_t hi = desc_hi_sw128(1024);  // 8-pixel K groups are dense rows in both windows
+    // per-unit descriptor constants: (row shift + 1 front row) in 16-byte units, LBO in bits 16+
+    uint32_t ua[kWfMaxUnits];
+#pragma unroll
+    for (int u = 0; u < kWfMaxUnits; ++u) {
+      const uint32_t lbo = MODE == 0 ? (uint32_t)jt.u[u].lbo : (uint32_t)p.xwin_bytes;
+      ua[u] = (uint32_t)((jt.u[u].shift + 1) * 8) + (((lbo >> 4) & 0x3FFFu) << 16);
+    }
+    const uint32_t ub = ((uint32_t)(p.dywin_bytes >> 4) & 0x3FFFu) << 16;
     const int nunits = jt.nunits;
+    const int ksteps = p.ksteps;
     int it = 0;
     for (int t = t0; t < t1; ++t, ++it) {
-      const int q0 = t * kWfTM;
       const int st = it % ST;
-      const int xa = wf_floor_div(q0 + jt.smin, p.P);
-      const int ox = q0 - xa * p.P;            // stage row of pixel q0 in the X window
-      const int od = q0 - (q0 / p.P) * p.P;    // stage row of pixel q0 in the dY window
       mbar_wait(&full[st], (it / ST) & 1);
       tc_fence_after();
-      const uint32_t sbase = smem_base + st * p.stage_bytes;
-      const uint32_t b_lo0 = desc_lo_sw128(sbase + dy_off + od * 128, p.dywin_bytes);
-#pragma unroll 1
-      for (int j = 0; j < kWfTM / 16; ++j) {
-        for (int u = 0; u < nunits; ++u) {
-          const uint32_t a_lo = desc_lo_sw128(sbase + (ox + jt.u[u].shift0 + 16 * j) * 128,
-                                              MODE == 0 ? jt.u[u].lbo : p.xwin_bytes);
-          mma_bf16_ss(tmem_base + u * BN, desc_join(a_lo, hi), desc_join(b_lo0 + j * (2048 >> 4), hi), idesc,
-                      (it | j) != 0 ? 1u : 0u);
-        }
+      const uint32_t sa = ((smem_base + st * p.stage_bytes) & 0x3FFFFu) >> 4;
+      const uint32_t sb = sa + (dy_off >> 4) + ub;
+      int j0 = 0;
+      if (it == 0) {  // first K step of the CTA overwrites the accumulators
+#pragma unroll
+        for (int u = 0; u < kWfMaxUnits; ++u)
+          if (u < nunits) mma_bf16_ss(u * BN, desc_join(sa + ua[u], hi), desc_join(sb, hi), idesc, 0u);
+        j0 = 1;
       }
+#define WF_ISSUE(NU)                                                                                          \
+  for (int j = j0; j < ksteps; ++j) {                                                                         \
+    const uint32_t b_lo = sb + j * 128;                                                                       \
+    _Pragma("unroll") for (int u = 0; u < NU; ++u)                                                            \
+        mma_bf16_acc(u * BN, desc_join(sa + ua[u] + j * 128, hi), desc_join(b_lo, hi), idesc);                \
+  }
+      switch (nunits) {
+        case 1: WF_ISSUE(1) break;
+        case 2: WF_ISSUE(2) break;
+        case 3: WF_ISSUE(3) break;
+        case 4: WF_ISSUE(4) break;
+        default: WF_ISSUE(5) break;
+      }
+#undef WF_ISSUE
       mma_commit(&empty[st]);
     }
     mma_commit(tmem_full);
@@ -199,19 +225,24 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
 // ------------------------------------------------------------------------------------------
 struct WfPlan {
   int mode, BN, ntypes, ci_tiles, co_tiles, gy, splits, tiles_total, tiles_per_split;
-  int xwin_bytes, dywin_bytes, stage_bytes, stages, P, IS, taps;
+  int xwin_bytes, dywin_bytes, stage_bytes, stages, P, taps;
+  int NI, RB, nbands, ksteps, xrows, dyrows, rspan;
   WfJobType jt[4];
 };
 
-static void add_unit(WfJobType& t, int shift0, int lbo, int tap0, int tap1) {
+struct WfTap {
+  int tap, plane, dr, dc;
+};
+
+static void wf_add_unit(WfJobType& t, int P, const WfTap& a, const WfTap* b) {
   WfUnit& u = t.u[t.nunits++];
-  u.shift0 = shift0;
-  u.lbo = lbo;
-  u.tap0 = tap0;
-  u.tap1 = tap1;
+  u.shift = (a.dr - t.rmin) * P + a.dc;
+  u.tap0 = a.tap;
+  u.tap1 = b ? b->tap : -1;
+  u.lbo = b ? (((b->dr - t.rmin) * P + b->dc) - u.shift) * 128 : 128;
 }
 
-// R in {1,3}, stride in {1,2}; (Ho, Wo) is the output grid the flat index runs over.
+// R in {1,3}, stride in {1,2}; (Ho, Wo) is the output grid the pixel windows run over.
 static bool plan_wgrad_flat(int N, int Ho, int Wo, int Ci, int Co, int R, int stride, WfPlan& w) {
   if (Ci % 64 != 0 || Co % 64 != 0) return false;
   if (!(R == 3 || R == 1) || !(stride == 1 || stride == 2)) return false;
@@ -219,9 +250,6 @@ static bool plan_wgrad_flat(int N, int Ho, int Wo, int Ci, int Co, int R, int st
   const int P = Wo + 1;
   if (P > 256) return false;
   w.P = P;
-  w.IS = (Ho + 1) * P;
-  const int64_t Q = (int64_t)N * w.IS;
-  if (Q + 4 * P + 1024 >= ((int64_t)1 << 31)) return false;
   w.taps = R * R;
   if (Ci == 64) {
     w.mode = 0;
@@ -235,81 +263,95 @@ static bool plan_wgrad_flat(int N, int Ho, int Wo, int Ci, int Co, int R, int st
     return false;
   }
   w.co_tiles = Co / w.BN;
-  // --- job types: which taps share one X window ---
-  struct T { int tap, plane, shift; };
-  T taps[9];
+  // --- taps and the job types (taps sharing one X window) ---
+  WfTap taps[9];
   int nt = 0;
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < R; ++s) {
-      T t;
+      WfTap t;
       t.tap = r * R + s;
       if (R == 1) {
-        t.plane = 0;
-        t.shift = 0;
+        t.plane = 0; t.dr = 0; t.dc = 0;
       } else if (stride == 1) {
-        t.plane = 0;
-        t.shift = (r - 1) * P + (s - 1);
+        t.plane = 0; t.dr = r - 1; t.dc = s - 1;
       } else {
         t.plane = ((r + 1) & 1) * 2 + ((s + 1) & 1);
-        t.shift = (r == 0 ? -1 : 0) * P + (s == 0 ? -1 : 0);
+        t.dr = r == 0 ? -1 : 0;
+        t.dc = s == 0 ? -1 : 0;
       }
       taps[nt++] = t;
     }
+  w.rspan = 0;
   if (stride == 1 && w.mode == 1 && R == 3) {
     w.ntypes = 3;  // one filter row per CTA: 3 accumulators, narrow window
     for (int r = 0; r < 3; ++r) {
       w.jt[r].plane = 0;
-      for (int s = 0; s < 3; ++s) add_unit(w.jt[r], taps[r * 3 + s].shift, 0, r * 3 + s, -1);
+      w.jt[r].rmin = r - 1;
+      for (int s = 0; s < 3; ++s) wf_add_unit(w.jt[r], P, taps[r * 3 + s], nullptr);
     }
   } else {
-    // group by plane (stride 1: a single plane); MODE 0 pairs consecutive taps of the group
     const int nplanes = (stride == 2 && R == 3) ? 4 : 1;
-    w.ntypes = 0;
     for (int pl = 0; pl < nplanes; ++pl) {
-      T g[9];
-      int ng = 0;
+      WfTap g[9];
+      int ng = 0, rmin = 9, rmax = -9;
       for (int i = 0; i < nt; ++i)
-        if (taps[i].plane == pl) g[ng++] = taps[i];
+        if (taps[i].plane == pl) {
+          g[ng++] = taps[i];
+          if (taps[i].dr < rmin) rmin = taps[i].dr;
+          if (taps[i].dr > rmax) rmax = taps[i].dr;
+        }
       if (ng == 0) continue;
       WfJobType& jt = w.jt[w.ntypes++];
       jt.plane = pl;
+      jt.rmin = rmin;
+      if (rmax - rmin > w.rspan) w.rspan = rmax - rmin;
       if (w.mode == 0) {
-        for (int i = 0; i < ng; i += 2) {
-          if (i + 1 < ng)
-            add_unit(jt, g[i].shift, (g[i + 1].shift - g[i].shift) * 128, g[i].tap, g[i + 1].tap);
-          else
-            add_unit(jt, g[i].shift, 128, g[i].tap, -1);
-        }
+        for (int i = 0; i < ng; i += 2) wf_add_unit(jt, P, g[i], i + 1 < ng ? &g[i + 1] : nullptr);
       } else {
-        for (int i = 0; i < ng; ++i) add_unit(jt, g[i].shift, 0, g[i].tap, -1);
+        for (int i = 0; i < ng; ++i) wf_add_unit(jt, P, g[i], nullptr);
       }
     }
   }
-  int span = 0;
   for (int k = 0; k < w.ntypes; ++k) {
-    WfJobType& jt = w.jt[k];
-    if (jt.nunits * w.BN > 512) return false;
-    jt.smin = 1 << 30;
-    jt.smax = -(1 << 30);
-    for (int i = 0; i < jt.nunits; ++i) {
-      int lo = jt.u[i].shift0, hi = jt.u[i].shift0;
-      if (w.mode == 0) hi += jt.u[i].lbo / 128;  // second block (also covers the ignored block of a single)
-      if (lo < jt.smin) jt.smin = lo;
-      if (hi > jt.smax) jt.smax = hi;
-      if (w.mode == 0 && jt.u[i].lbo <= 0) return false;
-    }
-    if (jt.smax - jt.smin > span) span = jt.smax - jt.smin;
+    if (w.jt[k].nunits * w.BN > 512) return false;
+    for (int i = 0; i < w.jt[k].nunits; ++i)
+      if (w.mode == 0 && w.jt[k].u[i].lbo <= 0) return false;
   }
-  const int nx_max = (kWfTM + span - 1 + P - 1) / P + 1, nd_max = (kWfTM - 1 + P - 1) / P + 1;
-  w.xwin_bytes = (nx_max * P * 128 + 1023) / 1024 * 1024;
-  w.dywin_bytes = (nd_max * P * 128 + 1023) / 1024 * 1024;
-  const int NS = w.mode == 0 ? 1 : 2;
-  w.stage_bytes = NS * w.xwin_bytes + (w.BN / 64) * w.dywin_bytes;
+  // --- stage geometry: NI whole images, or a band of RB rows; minimise K steps (+ per-stage overhead) ---
+  const int NS = w.mode == 0 ? 1 : 2, NB = w.BN / 64;
+  const int budget = 227 * 1024 - 2048;
+  double best = 1e30;
+  for (int whole = 0; whole < 2; ++whole) {
+    for (int v = 1; v <= (whole ? 8 : Ho); whole ? v *= 2 : ++v) {
+      const int NI = whole ? v : 1, RB = whole ? Ho + 1 : v;
+      if (whole && w.rspan > 1) continue;
+      const int px = NI * RB * P;
+      if (px > kWfMaxPx) break;
+      const int xrows = whole ? RB : RB + w.rspan;
+      const int ks = (px + 15) / 16;
+      // X window: 1 zero row + box + tail reachable by the largest shift from the last K step
+      const int xwin = ((1 + ks * 16 + (w.rspan + 1) * P + 2) * 128 + 1023) / 1024 * 1024;
+      const int xbox = NI * xrows * P * 128;
+      if (xbox + 128 > xwin) continue;
+      const int dywin = (ks * 16 * 128 + 1023) / 1024 * 1024;
+      const int stage = NS * xwin + NB * dywin;
+      int stages = budget / stage;
+      if (stages > 4) stages = 4;
+      if (stages < 2) continue;
+      const int nb = whole ? 1 : (Ho + RB - 1) / RB;
+      const int64_t tiles = whole ? (N + NI - 1) / NI : (int64_t)N * nb;
+      double cost = (double)tiles * (ks + 1.5) * (stages >= 3 ? 1.0 : 1.25);
+      if (cost < best) {
+        best = cost;
+        w.NI = NI; w.RB = RB; w.nbands = nb; w.ksteps = ks;
+        w.xrows = xrows; w.dyrows = RB;
+        w.xwin_bytes = xwin; w.dywin_bytes = dywin; w.stage_bytes = stage; w.stages = stages;
+        w.tiles_total = (int)tiles;
+      }
+    }
+  }
+  if (best >= 1e30) return false;
   if (w.xwin_bytes >= (1 << 18) || w.dywin_bytes >= (1 << 18)) return false;  // LBO field
-  w.stages = (227 * 1024 - 2048) / w.stage_bytes;
-  if (w.stages > 4) w.stages = 4;
-  if (w.stages < 2) return false;
-  w.tiles_total = int((Q + kWfTM - 1) / kWfTM);
   w.gy = w.ci_tiles * w.co_tiles * w.ntypes;
   int splits = (2 * kNumSMs) / w.gy;
   if (splits < 1) splits = 1;
@@ -358,26 +400,30 @@ int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R,
       for (int b = 0; b < 2; ++b) {
         const int ph = (Hi - a + 1) / 2, pw = (Wi - b + 1) / 2;
         if (ph <= 0 || pw <= 0) return 0;
-        const CUtensorMap* t = tmap_view4(xb + ((int64_t)a * Wi + b) * Ci, Ci, pw, ph, N, sW, sH, sN, w.P);
+        const CUtensorMap* t =
+            tmap_view4(xb + ((int64_t)a * Wi + b) * Ci, Ci, pw, ph, N, sW, sH, sN, w.P, w.xrows, w.NI);
         if (!t) return GDL_ECUDA;
         p.tm_x[a * 2 + b] = *t;
       }
   } else {
-    const CUtensorMap* t = tmap_view4(xb, Ci, Wo, Ho, N, sW, sH, sN, w.P);
+    const CUtensorMap* t = tmap_view4(xb, Ci, Wo, Ho, N, sW, sH, sN, w.P, w.xrows, w.NI);
     if (!t) return GDL_ECUDA;
     p.tm_x[0] = *t;
   }
-  const CUtensorMap* td = tmap_view4(dy, Co, Wo, Ho, N, Co, (int64_t)Wo * Co, (int64_t)Ho * Wo * Co, w.P);
+  const CUtensorMap* td =
+      tmap_view4(dy, Co, Wo, Ho, N, Co, (int64_t)Wo * Co, (int64_t)Ho * Wo * Co, w.P, w.dyrows, w.NI);
   if (!td) return GDL_ECUDA;
   p.tm_dy = *td;
   p.partial = partial;
-  p.N = N; p.Hs = Ho; p.Ws = Wo; p.Ci = Ci; p.Co = Co; p.P = w.P; p.IS = w.IS;
+  p.Ci = Ci; p.Co = Co; p.Kp = w.taps * Ci;
   p.ntypes = w.ntypes;
   for (int i = 0; i < 4; ++i) p.jt[i] = w.jt[i];
   p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles;
+  p.NI = w.NI; p.RB = w.RB; p.nbands = w.nbands; p.ksteps = w.ksteps;
   p.tiles_total = w.tiles_total; p.tiles_per_split = w.tiles_per_split;
   p.xwin_bytes = w.xwin_bytes; p.dywin_bytes = w.dywin_bytes; p.stage_bytes = w.stage_bytes; p.stages = w.stages;
-  p.Kp = w.taps * Ci;
+  const int NS = w.mode == 0 ? 1 : 2, NB = w.BN / 64;
+  p.tx_bytes = (uint32_t)((NS * w.xrows + NB * w.dyrows) * w.NI * w.P * 128);
   int rc;
   if (w.mode == 0)
     rc = w.BN == 64 ? launch_wf<64, 0>(p, w, s) : launch_wf<128, 0>(p, w, s);

@@ -16,9 +16,9 @@ const CUtensorMap* tmap_nhwc(const void* ptr, int N, int H, int W, int C, int bo
 // bf16 row-major matrix [rows][K] viewed as {K, rows}; box {64, box_rows}, 128-byte swizzle.
 const CUtensorMap* tmap_rows(const void* ptr, int64_t rows, int64_t K, int box_rows);
 
-// Strided {C, W, H, N} view (element strides), box {64, box_w, 1, 1} — one padded pixel row per TMA op.
+// Strided {C, W, H, N} view (element strides), box {64, box_w, box_h, box_n}.
 const CUtensorMap* tmap_view4(const void* ptr, int C, int W, int H, int N, int64_t sW, int64_t sH, int64_t sN,
-                              int box_w);
+                              int box_w, int box_h = 1, int box_n = 1);
 
 // 16-channel tensors (space-to-depth stem input, 32-byte rows): box {16, bw, bh, 1} / {16, box_rows},
 // 32-byte swizzle.

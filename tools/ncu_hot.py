@@ -7,7 +7,13 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-i
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
-data = rows[2:]
+data = []
+for r in rows[2:]:
+    if len(r) != len(hdr):
+        continue
+    if r[hdr.index('# Samples')] == '# Samples':
+        break
+    data.append(r)
 si = hdr.index("# Samples"); so = hdr.index("Source"); ie = hdr.index("Instructions Executed")
 tot = sum(int(r[si] or 0) for r in data)
 print(rows[0][1][:100], "total samples", tot, "SASS lines", len(data))
