@@ -664,6 +664,13 @@ extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w
                               nullptr, 0, 0, (cudaStream_t)s);
     if (rc != 0) return rc < 0 ? rc : GDL_OK;
   }
+  if (d->R == 3 && d->S == 3 && d->stride == 2 && d->pad == 1 && d->Ci % 64 == 0 && flat_policy() != 0) {
+    // stride 2: the four parity planes of x are stride-1 sources on the output grid
+    int rc = try_conv_flat(4, d->N, d->Ho, d->Wo, d->Ci, d->Ci, (int64_t)d->Wi * d->Ci,
+                           (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y, d->Ho, d->Wo,
+                           d->Co, nullptr, 0, (cudaStream_t)s);
+    if (rc != 0) return rc < 0 ? rc : GDL_OK;
+  }
   if (d->R == 1 && d->S == 1 && d->pad == 0 && d->Ci % 64 == 0 && d->Ci <= 128 && flat_policy() != 0) {
     // 1x1 (stride 1 or 2): a single tap over the strided view x[:, ::stride, ::stride, :]
     int rc = try_conv_flat(3, d->N, d->Ho, d->Wo, d->Ci, (int64_t)d->stride * d->Ci,

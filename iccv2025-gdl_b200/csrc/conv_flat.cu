@@ -37,7 +37,7 @@ struct FlatTap {
 };
 
 struct FlatParams {
-  CUtensorMap tm_x;  // {Cs, Ws, Hs, N} view of the source, box {64, P, 1, 1}
+  CUtensorMap tm_x[4];  // {Cs, Ws, Hs, N} views of the source (one per parity plane), box {64, P, 1, 1}
   CUtensorMap tm_w;  // {K, rows} packed weights, box {64, BN}
   bf16* dst;
   const bf16* add_src;
@@ -50,6 +50,10 @@ struct FlatParams {
   int ntaps[4];
   int ph[4], pw[4];
   FlatTap taps[4][kFlatMaxTaps];
+  // taps of a class are ordered by group; a group = the taps that slide over ONE source view (plane)
+  int ngroups[4];
+  int gplane[4][4];
+  int gtap0[4][5];  // group g of class c owns taps [gtap0[c][g], gtap0[c][g+1])
   int smin, smax;
   int mtiles, ntiles, items_total;
   int win_stage_bytes, win_stages;
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
     tmem_relinquish();
   }
   if (tid == 5 * 32) {
-    tma_prefetch_desc(&p.tm_x);
+    tma_prefetch_desc(&p.tm_x[0]);
     tma_prefetch_desc(&p.tm_w);
   }
   tc_fence_before();
@@ -126,23 +130,26 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int rho_a = floor_div(q0 + p.smin, p.P);
       const int rho_b = floor_div(q0 + TM + p.smax - 1, p.P);
       const int nrows = rho_b - rho_a + 1;
-      const int ntap = p.ntaps[cls];
-      for (int slab = 0; slab < slabs; ++slab, ++wincount) {
-        const int ws = wincount % WS;
-        if (wincount >= WS) mbar_wait(&win_empty[ws], ((wincount / WS) - 1) & 1);
-        mbar_arrive_expect_tx(&win_full[ws], (uint32_t)nrows * row_bytes);
-        const uint32_t sdst = smem_base + ws * p.win_stage_bytes;
-        for (int i = 0; i < nrows; ++i) {
-          const int rho = rho_a + i;
-          const int n = floor_div(rho, rows_img);
-          const int h = rho - n * rows_img;
-          tma_load_4d(sdst + i * row_bytes, &p.tm_x, &win_full[ws], slab * 64, 0, h, n);
-        }
-        for (int t = 0; t < ntap; ++t, ++wcount) {
-          const int st = wcount % WST;
-          if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
-          mbar_arrive_expect_tx(&w_full[st], W_BYTES);
-          tma_load_2d(smem_base + w_off + st * W_BYTES, &p.tm_w, &w_full[st], p.taps[cls][t].wk + slab * 64, n0);
+      const int ngrp = p.ngroups[cls];
+      for (int slab = 0; slab < slabs; ++slab) {
+        for (int g = 0; g < ngrp; ++g, ++wincount) {
+          const int ws = wincount % WS;
+          if (wincount >= WS) mbar_wait(&win_empty[ws], ((wincount / WS) - 1) & 1);
+          mbar_arrive_expect_tx(&win_full[ws], (uint32_t)nrows * row_bytes);
+          const uint32_t sdst = smem_base + ws * p.win_stage_bytes;
+          const CUtensorMap* tmx = &p.tm_x[p.gplane[cls][g]];
+          for (int i = 0; i < nrows; ++i) {
+            const int rho = rho_a + i;
+            const int n = floor_div(rho, rows_img);
+            const int h = rho - n * rows_img;
+            tma_load_4d(sdst + i * row_bytes, tmx, &win_full[ws], slab * 64, 0, h, n);
+          }
+          for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
+            const int st = wcount % WST;
+            if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
+            mbar_arrive_expect_tx(&w_full[st], W_BYTES);
+            tma_load_2d(smem_base + w_off + st * W_BYTES, &p.tm_w, &w_full[st], p.taps[cls][t].wk + slab * 64, n0);
+          }
         }
       }
     }
@@ -167,36 +174,38 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int q0 = (rem - nt * p.mtiles) * TM;
       const int rho_a = floor_div(q0 + p.smin, p.P);
       const int o = q0 + p.smin - rho_a * p.P;  // first window row inside the stage
-      const int ntap = p.ntaps[cls];
       const int acc = it & 1;
       if (it >= 2) {
         mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1);
         tc_fence_after();
       }
       const uint32_t d_tmem = acc * (MT * BN);
-      for (int slab = 0; slab < slabs; ++slab, ++wincount) {
-        const int ws = wincount % WS;
-        mbar_wait(&win_full[ws], (wincount / WS) & 1);
-        tc_fence_after();
-        const uint32_t a_win = a_lo0 + ((ws * p.win_stage_bytes) >> 4) + (o - p.smin) * 8;
-        for (int t = 0; t < ntap; ++t, ++wcount) {
-          const int st = wcount % WST;
-          mbar_wait(&w_full[st], (wcount / WST) & 1);
+      const int ngrp = p.ngroups[cls];
+      for (int slab = 0; slab < slabs; ++slab) {
+        for (int g = 0; g < ngrp; ++g, ++wincount) {
+          const int ws = wincount % WS;
+          mbar_wait(&win_full[ws], (wincount / WS) & 1);
           tc_fence_after();
-          const uint32_t a_lo = a_win + p.taps[cls][t].shift * 8;
-          const uint32_t b_lo = b_lo0 + st * (W_BYTES >> 4);
-          const uint32_t first = (slab | t) != 0 ? 1u : 0u;
+          const uint32_t a_win = a_lo0 + ((ws * p.win_stage_bytes) >> 4) + (o - p.smin) * 8;
+          for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
+            const int st = wcount % WST;
+            mbar_wait(&w_full[st], (wcount / WST) & 1);
+            tc_fence_after();
+            const uint32_t a_lo = a_win + p.taps[cls][t].shift * 8;
+            const uint32_t b_lo = b_lo0 + st * (W_BYTES >> 4);
+            const uint32_t first = (slab | t) != 0 ? 1u : 0u;
 #pragma unroll
-          for (int j = 0; j < MT; ++j) {
-            mma_bf16_ss(d_tmem + j * BN, desc_join(a_lo + j * 1024, ab_hi), desc_join(b_lo, ab_hi), idesc, first);
+            for (int j = 0; j < MT; ++j) {
+              mma_bf16_ss(d_tmem + j * BN, desc_join(a_lo + j * 1024, ab_hi), desc_join(b_lo, ab_hi), idesc, first);
 #pragma unroll
-            for (int k = 1; k < 4; ++k)
-              mma_bf16_acc(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi), desc_join(b_lo + 2 * k, ab_hi),
-                           idesc);
+              for (int k = 1; k < 4; ++k)
+                mma_bf16_acc(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi),
+                             desc_join(b_lo + 2 * k, ab_hi), idesc);
+            }
+            mma_commit(&w_empty[st]);
           }
-          mma_commit(&w_empty[st]);
+          mma_commit(&win_empty[ws]);
         }
-        mma_commit(&win_empty[ws]);
       }
       mma_commit(&tmem_full[acc]);
     }
@@ -295,7 +304,9 @@ static int env_int3(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-// kind: 0 forward 3x3/s1, 1 dgrad 3x3/s1, 2 dgrad 3x3/s2 (parity classes), 3 single tap (1x1).
+// kind: 0 forward 3x3/s1, 1 dgrad 3x3/s1, 2 dgrad 3x3/s2 (parity classes), 3 single tap (1x1),
+// 4 forward 3x3/s2: (Hs,Ws) is the OUTPUT grid, src is the whole input [N,Hi,Wi,Cs] (sH = Wi*Cs, sN = Hi*Wi*Cs)
+// read through its four parity planes x[:, a::2, b::2, :]; tap (r,s) lives in plane ((r+1)&1, (s+1)&1).
 // src is the tensor the taps slide over, viewed as [N,Hs,Ws,Cs] with element strides (sW,sH,sN);
 // wt is [Cd rows][K] bf16 with k = tap*Cs + c.  Returns 1 when launched, 0 when not eligible, <0 on error.
 int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t sH, int64_t sN, const void* src,
@@ -347,11 +358,36 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
         }
       p.ntaps[c] = k;
     }
+  } else if (kind == 4) {
+    // taps grouped by plane, heavy groups first: (1,1) 4 taps, (1,0) 2, (0,1) 2, (0,0) 1
+    const int pa[4] = {1, 1, 0, 0}, pb[4] = {1, 0, 1, 0};
+    int k = 0;
+    p.ngroups[0] = 4;
+    for (int g = 0; g < 4; ++g) {
+      p.gplane[0][g] = pa[g] * 2 + pb[g];
+      p.gtap0[0][g] = k;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          if (((r + 1) & 1) != pa[g] || ((c + 1) & 1) != pb[g]) continue;
+          p.taps[0][k].shift = (r == 0 ? -1 : 0) * P + (c == 0 ? -1 : 0);
+          p.taps[0][k].wk = (r * 3 + c) * Cs;
+          ++k;
+        }
+    }
+    p.gtap0[0][4] = k;
+    p.ntaps[0] = k;
   } else {
     p.ntaps[0] = 1;
     p.taps[0][0].shift = 0;
     p.taps[0][0].wk = 0;
   }
+  if (kind != 4)
+    for (int c = 0; c < p.nclass; ++c) {
+      p.ngroups[c] = 1;
+      p.gplane[c][0] = 0;
+      p.gtap0[c][0] = 0;
+      p.gtap0[c][1] = p.ntaps[c];
+    }
   p.smin = 0;
   p.smax = 0;
   for (int c = 0; c < p.nclass; ++c)
@@ -360,10 +396,24 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
       if (p.taps[c][t].shift > p.smax) p.smax = p.taps[c][t].shift;
     }
   const int BN = (Cd % 128 == 0) ? 128 : 64;
-  const CUtensorMap* tx = tmap_view4(src, Cs, Ws, Hs, N, sW, sH, sN, P);
+  if (kind == 4) {
+    const int Wi = int(sH / Cs), Hi = int(sN / sH);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int ph = (Hi - a + 1) / 2, pw = (Wi - b + 1) / 2;
+        if (ph <= 0 || pw <= 0) return 0;
+        const CUtensorMap* t =
+            tmap_view4((const bf16*)src + ((int64_t)a * Wi + b) * Cs, Cs, pw, ph, N, 2 * (int64_t)Cs, 2 * sH, sN, P);
+        if (!t) return GDL_ECUDA;
+        p.tm_x[a * 2 + b] = *t;
+      }
+  } else {
+    const CUtensorMap* tx = tmap_view4(src, Cs, Ws, Hs, N, sW, sH, sN, P);
+    if (!tx) return GDL_ECUDA;
+    p.tm_x[0] = *tx;
+  }
   const CUtensorMap* tw = tmap_rows(wt, wt_rows, wt_k, BN);
-  if (!tx || !tw) return GDL_ECUDA;
-  p.tm_x = *tx;
+  if (!tw) return GDL_ECUDA;
   p.tm_w = *tw;
   // MT = 2 halves the weight traffic per MMA (measured 1.2-1.4x on every layer of the bench geometry);
   // MT = 1 only when the problem would not fill one wave of CTAs otherwise
