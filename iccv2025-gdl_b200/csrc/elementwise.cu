@@ -360,6 +360,280 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// BatchNorm backward for units WITHOUT a residual input (conv1 of a BasicBlock, reference
+// models/backbone.py:44-46): the ReLU mask is recomputed from x (y > 0  <=>  x*scale+shift > 0), so
+// neither y is read nor the masked gradient written: 10 B/element instead of 14.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, int64_t P, int C, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
+    float* __restrict__ partial) {
+  const int groups = C / 8;
+  const int lanes = kBnThreads / groups;
+  const int cg = threadIdx.x % groups;
+  const int lane = threadIdx.x / groups;
+  float mu[8], is[8], sc[8], sh[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    mu[c] = mean[cg * 8 + c];
+    is[c] = invstd[cg * 8 + c];
+    sc[c] = scale[cg * 8 + c];
+    sh[c] = shift[cg * 8 + c];
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[0][c] = acc[1][c] = 0.f;
+  for (int64_t pix = (int64_t)blockIdx.x * lanes + lane; pix < P; pix += (int64_t)gridDim.x * lanes) {
+    const int64_t off = pix * C + cg * 8;
+    float g[8], xv[8];
+    unpack8(ld_stream16(dy + off), g);
+    unpack8(ld_stream16(x + off), xv);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float gz = fmaf(xv[c], sc[c], sh[c]) > 0.f ? g[c] : 0.f;
+      acc[0][c] += gz;
+      acc[1][c] = fmaf(gz, (xv[c] - mu[c]) * is[c], acc[1][c]);
+    }
+  }
+  block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_nores_apply_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, int64_t nvec, int C,
+    float invP, const float* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ dgamma, const float* __restrict__ dbeta) {
+  __shared__ float s_a[512], s_b[512], s_c[512], s_sc[512], s_sh[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = gamma[c] * invstd[c];
+    float b = -a * invstd[c] * dgamma[c] * invP;
+    s_a[c] = a;
+    s_b[c] = b;
+    s_c[c] = -a * dbeta[c] * invP - b * mean[c];
+    s_sc[c] = scale[c];
+    s_sh[c] = shift[c];
+  }
+  __syncthreads();
+  const int groups = C / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = int(i % groups);
+    float g[8], xv[8];
+    unpack8(ld_stream16(dy + i * 8), g);
+    unpack8(ld_stream16(x + i * 8), xv);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ch = cg * 8 + c;
+      const float gz = fmaf(xv[c], s_sc[ch], s_sh[ch]) > 0.f ? g[c] : 0.f;
+      g[c] = fmaf(s_a[ch], gz, fmaf(s_b[ch], xv[c], s_c[ch]));
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stem tail fused: BN-apply + ReLU + MaxPool(3, s2, p1) forward (reference models/backbone.py:104-106)
+// and its backward (max-pool scatter + ReLU mask + BN backward).  The stem activation
+// y0 = relu(bn(x0)) — the largest tensor of the step — and its gradient are never materialised:
+// forward reads x0 and writes the pooled map + 1-byte arg-max; backward gathers the pooled gradient
+// through the arg-max and recomputes the ReLU mask from x0.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+    bf16* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C, int Ho, int Wo) {
+  __shared__ float s_scale[512], s_shift[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_scale[c] = scale[c];
+    s_shift[c] = shift[c];
+  }
+  __syncthreads();
+  const int groups = C / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int cg = int(i % groups);
+    int64_t pix = i / groups;
+    int wo = int(pix % Wo);
+    int64_t t = pix / Wo;
+    int ho = int(t % Ho);
+    int n = int(t / Ho);
+    float sc[8], sh[8], best[8];
+    int bi[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      sc[c] = s_scale[cg * 8 + c];
+      sh[c] = s_shift[cg * 8 + c];
+      best[c] = -INFINITY;
+      bi[c] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int h = ho * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int w = wo * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + (((int64_t)n * H + h) * W + w) * C + cg * 8), f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          // the value the unfused path would have stored: bf16(relu(x*scale+shift))
+          const float v = bf16_round(fmaxf(fmaf(f[c], sc[c], sh[c]), 0.f));
+          if (v > best[c]) {  // strict: the first maximum in scan order wins (ATen rule)
+            best[c] = v;
+            bi[c] = r * 3 + s;
+          }
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(y + pix * C + cg * 8) = pack8(best);
+    uint2 packed;
+    packed.x = uint32_t(bi[0]) | (uint32_t(bi[1]) << 8) | (uint32_t(bi[2]) << 16) | (uint32_t(bi[3]) << 24);
+    packed.y = uint32_t(bi[4]) | (uint32_t(bi[5]) << 8) | (uint32_t(bi[6]) << 16) | (uint32_t(bi[7]) << 24);
+    *reinterpret_cast<uint2*>(amax + pix * C + cg * 8) = packed;
+  }
+}
+
+// Backward works on 2x2 blocks of stem pixels (rows 2i,2i+1 x cols 2j,2j+1; 8 channels per thread): the
+// block is covered by the four pooling windows (i,j), (i,j+1), (i+1,j), (i+1,j+1), and which tap of which
+// window each of the four pixels is follows from the parities alone, so one thread loads 4 windows for 4
+// pixels (a per-pixel gather loads 9) with compile-time tap indices.
+struct PoolWin {
+  float g[8];
+  uint32_t a0, a1;  // 8 one-byte arg-max indices
+};
+__device__ __forceinline__ void load_win(const bf16* __restrict__ gpool, const uint8_t* __restrict__ amax,
+                                         int64_t off, bool ok, PoolWin& w) {
+  if (ok) {
+    unpack8(*reinterpret_cast<const uint4*>(gpool + off), w.g);
+    const uint2 am = *reinterpret_cast<const uint2*>(amax + off);
+    w.a0 = am.x;
+    w.a1 = am.y;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w.g[c] = 0.f;
+    w.a0 = w.a1 = 0xffffffffu;  // matches no tap
+  }
+}
+__device__ __forceinline__ float win_pick(const PoolWin& w, int c, int tap) {
+  const uint32_t word = c < 4 ? w.a0 : w.a1;
+  return ((word >> ((c & 3) * 8)) & 0xffu) == (uint32_t)tap ? w.g[c] : 0.f;
+}
+// dy (gradient wrt relu output) of the four pixels of block (i,j): p[0]=(2i,2j) p[1]=(2i,2j+1) p[2]=(2i+1,2j) p[3]=(2i+1,2j+1).
+// Summation order per pixel = ascending (ho, wo), the order of the unfused max-pool backward.
+__device__ __forceinline__ void block_pool_grad(const bf16* __restrict__ gpool, const uint8_t* __restrict__ amax,
+                                                int n, int i, int j, int cg, int C, int Ho, int Wo,
+                                                float (&p)[4][8]) {
+  PoolWin w00, w01, w10, w11;
+  const int64_t base = (((int64_t)n * Ho + i) * Wo + j) * C + cg * 8;
+  const bool okj = j + 1 < Wo, oki = i + 1 < Ho;
+  load_win(gpool, amax, base, true, w00);
+  load_win(gpool, amax, base + C, okj, w01);
+  load_win(gpool, amax, base + (int64_t)Wo * C, oki, w10);
+  load_win(gpool, amax, base + (int64_t)Wo * C + C, oki && okj, w11);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    p[0][c] = win_pick(w00, c, 4);
+    p[1][c] = win_pick(w00, c, 5) + win_pick(w01, c, 3);
+    p[2][c] = win_pick(w00, c, 7) + win_pick(w10, c, 1);
+    p[3][c] = ((win_pick(w00, c, 8) + win_pick(w01, c, 6)) + win_pick(w10, c, 2)) + win_pick(w11, c, 0);
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads) bn_relu_maxpool_bwd_reduce_kernel(
+    const bf16* __restrict__ gpool, const uint8_t* __restrict__ amax, const bf16* __restrict__ x, int N, int H,
+    int W, int C, int Ho, int Wo, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ partial) {
+  const int groups = C / 8;
+  const int lanes = kBnThreads / groups;
+  const int cg = threadIdx.x % groups;
+  const int lane = threadIdx.x / groups;
+  float mu[8], is[8], sc[8], sh[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    mu[c] = mean[cg * 8 + c];
+    is[c] = invstd[cg * 8 + c];
+    sc[c] = scale[cg * 8 + c];
+    sh[c] = shift[cg * 8 + c];
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[0][c] = acc[1][c] = 0.f;
+  const int64_t nblk = (int64_t)N * Ho * Wo;  // one 2x2 block per pooling-window origin
+  for (int64_t b = (int64_t)blockIdx.x * lanes + lane; b < nblk; b += (int64_t)gridDim.x * lanes) {
+    const int j = int(b % Wo);
+    const int64_t t = b / Wo;
+    const int i = int(t % Ho), n = int(t / Ho);
+    float p[4][8];
+    block_pool_grad(gpool, amax, n, i, j, cg, C, Ho, Wo, p);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int h = 2 * i + (q >> 1), w = 2 * j + (q & 1);
+      if (h >= H || w >= W) continue;
+      float xv[8];
+      unpack8(ld_stream16(x + (((int64_t)n * H + h) * W + w) * C + cg * 8), xv);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        // the pooled gradient was stored in bf16 by the unfused path; keep that rounding point
+        const float gz = fmaf(xv[c], sc[c], sh[c]) > 0.f ? bf16_round(p[q][c]) : 0.f;
+        acc[0][c] += gz;
+        acc[1][c] = fmaf(gz, (xv[c] - mu[c]) * is[c], acc[1][c]);
+      }
+    }
+  }
+  block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
+}
+
+__global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_apply_kernel(
+    const bf16* __restrict__ gpool, const uint8_t* __restrict__ amax, const bf16* __restrict__ x,
+    bf16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, float invP,
+    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ dgamma,
+    const float* __restrict__ dbeta) {
+  __shared__ float s_a[512], s_b[512], s_c[512], s_sc[512], s_sh[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = gamma[c] * invstd[c];
+    float b = -a * invstd[c] * dgamma[c] * invP;
+    s_a[c] = a;
+    s_b[c] = b;
+    s_c[c] = -a * dbeta[c] * invP - b * mean[c];
+    s_sc[c] = scale[c];
+    s_sh[c] = shift[c];
+  }
+  __syncthreads();
+  const int groups = C / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = int(idx % groups);
+    const int64_t b = idx / groups;
+    const int j = int(b % Wo);
+    const int64_t t = b / Wo;
+    const int i = int(t % Ho), n = int(t / Ho);
+    float p[4][8];
+    block_pool_grad(gpool, amax, n, i, j, cg, C, Ho, Wo, p);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int h = 2 * i + (q >> 1), w = 2 * j + (q & 1);
+      if (h >= H || w >= W) continue;
+      const int64_t off = (((int64_t)n * H + h) * W + w) * C + cg * 8;
+      float xv[8], o[8];
+      unpack8(ld_stream16(x + off), xv);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int ch = cg * 8 + c;
+        const float gz = fmaf(xv[c], s_sc[ch], s_sh[ch]) > 0.f ? bf16_round(p[q][c]) : 0.f;
+        o[c] = fmaf(s_a[ch], gz, fmaf(s_b[ch], xv[c], s_c[ch]));
+      }
+      *reinterpret_cast<uint4*>(dx + off) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // global average pool   (reference models/basic_model.py:73-82)
 // ------------------------------------------------------------------------------------------
 __global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ out, int B, int G,
@@ -483,6 +757,60 @@ extern "C" int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz
   bn_bwd_apply_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>(
       dzp, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_apply_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_bn_bwd_nores(const void* dy, const void* x, void* dx, int64_t P, int C, const float* gamma,
+                                const float* mean, const float* invstd, const float* scale, const float* shift,
+                                float* partial, float* dgamma, float* dbeta, gdl_stream_t s) {
+  GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_bwd_nores: bad shape");
+  GDL_REQUIRE(dy && x && dx && gamma && mean && invstd && scale && shift && partial && dgamma && dbeta,
+              "gdl_bn_bwd_nores: null pointer");
+  int nblk = bn_blocks(P, C);
+  bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)dy, (const bf16*)x, P, C, mean,
+                                                                      invstd, scale, shift, partial);
+  GDL_CHECK_LAUNCH("bn_bwd_nores_reduce_kernel");
+  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
+  GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  int64_t nvec = P * C / 8;
+  bn_bwd_nores_apply_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>(
+      (const bf16*)dy, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, scale, shift, dgamma,
+      dbeta);
+  GDL_CHECK_LAUNCH("bn_bwd_nores_apply_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const float* shift, void* y,
+                                       uint8_t* argmax, int N, int H, int W, int C, int Ho, int Wo,
+                                       gdl_stream_t s) {
+  GDL_REQUIRE(x && scale && shift && y && argmax, "gdl_bn_relu_maxpool_fwd: null pointer");
+  GDL_REQUIRE(chan_ok(C) && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_bn_relu_maxpool_fwd: bad shape");
+  int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  bn_relu_maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(
+      (const bf16*)x, scale, shift, (bf16*)y, argmax, N, H, W, C, Ho, Wo);
+  GDL_CHECK_LAUNCH("bn_relu_maxpool_fwd_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax, const void* x, void* dx, int N,
+                                       int H, int W, int C, int Ho, int Wo, const float* gamma, const float* mean,
+                                       const float* invstd, const float* scale, const float* shift, float* partial,
+                                       float* dgamma, float* dbeta, gdl_stream_t s) {
+  GDL_REQUIRE(gpool && argmax && x && dx && gamma && mean && invstd && scale && shift && partial && dgamma && dbeta,
+              "gdl_bn_relu_maxpool_bwd: null pointer");
+  GDL_REQUIRE(chan_ok(C) && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_bn_relu_maxpool_bwd: bad shape");
+  const int64_t P = (int64_t)N * H * W;
+  int nblk = bn_blocks((int64_t)N * Ho * Wo * 4, C);
+  bn_relu_maxpool_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
+      (const bf16*)gpool, argmax, (const bf16*)x, N, H, W, C, Ho, Wo, mean, invstd, scale, shift, partial);
+  GDL_CHECK_LAUNCH("bn_relu_maxpool_bwd_reduce_kernel");
+  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
+  GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  bn_relu_maxpool_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(
+      (const bf16*)gpool, argmax, (const bf16*)x, (bf16*)dx, N, H, W, C, Ho, Wo, 1.f / (float)P, gamma, mean, invstd,
+      scale, shift, dgamma, dbeta);
+  GDL_CHECK_LAUNCH("bn_relu_maxpool_bwd_apply_kernel");
   return GDL_OK;
 }
 

@@ -97,7 +97,7 @@ class _StemBN(_ConvBN):
         self.wp = torch.zeros(64, 256, device=dev, dtype=torch.bfloat16)
         self.wT = None
         self.x = torch.empty(N, self.Ho, self.Wo, 64, device=dev, dtype=torch.bfloat16)
-        self.y = torch.empty_like(self.x)
+        self.y = None  # relu(bn(x)) is never materialised: the stem tail is fused with the max-pool
         self.mean, self.invstd, self.scale, self.shift = (torch.empty(64, device=dev) for _ in range(4))
         eng.max_wgrad_ws = max(eng.max_wgrad_ws, ops.stem_wgrad_workspace_bytes(N, H, W))
         eng.max_bn_partial = max(eng.max_bn_partial, ops.bn_partial_floats(self.P, 64))
@@ -115,8 +115,10 @@ class _StemBN(_ConvBN):
         else:
             ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
                                self.scale, self.shift, self.C)
-        ops.bn_apply(self.x, None, self.y, self.P, self.C, self.scale, self.shift, True)
-        return self.y
+        # BN-apply + ReLU + MaxPool(3,2,1) in one pass (reference backbone.py:104-106)
+        ops.bn_relu_maxpool_fwd(self.x, self.scale, self.shift, eng.pool_y, eng.pool_idx, self.N, self.Ho, self.Wo,
+                                64, eng.Hp, eng.Wp)
+        return eng.pool_y
 
 
 class EncoderEngine:
@@ -171,9 +173,7 @@ class EncoderEngine:
         """x16: bf16 space-to-depth input [N,Hp,Wp,16] -> bf16 [N,Hf,Wf,512] (the layer4 map,
         reference backbone.py:175-181).  training=False uses the BN running statistics."""
         s = self.stem
-        y = s.forward(self, x16, training=training)
-        ops.maxpool_fwd(y, self.pool_y, self.pool_idx, self.N, s.d.Ho, s.d.Wo, 64, self.Hp, self.Wp)
-        u = self.pool_y
+        u = s.forward(self, x16, training=training)  # stem conv + BN + ReLU + max-pool -> pool_y
         for (u1, u2, ud) in self.blocks:
             y1 = u1.forward(self, u, training=training)
             ident = u
@@ -209,8 +209,7 @@ class EncoderEngine:
             g_out = g_u
         s = self.stem
         self.g_pool = g_out                      # grad wrt maxpool output
-        self.g_y0 = pool.get(s.y.shape)          # grad wrt stem relu output
-        self.d_c0 = pool.get(s.x.shape)
+        self.d_c0 = pool.get(s.x.shape)          # grad wrt the stem conv output
         self.bwd_plan = plan
         self.grad_buffer_bytes = pool.total_bytes
 
@@ -244,7 +243,9 @@ class EncoderEngine:
             self._bn_bwd(u2, g_out, g_out, b["d_c2"], True)
             ops.conv_wgrad(u2.d, u2.ci_real, u1.y, b["d_c2"], self._grad(u2.conv.weight), self.wgrad_ws)
             ops.conv_dgrad(u2.d, b["d_c2"], u2.wT, b["g_y1"])
-            self._bn_bwd(u1, b["g_y1"], b["g_y1"], b["d_c1"], True)
+            # bn1 + relu has no residual input: mask recomputed from x, no y read / dz write
+            ops.bn_bwd_nores(b["g_y1"], u1.x, b["d_c1"], u1.P, u1.C, u1.bn.weight.data, u1.mean, u1.invstd,
+                             u1.scale, u1.shift, self.bn_partial, self._grad(u1.bn.weight), self._grad(u1.bn.bias))
             ops.conv_wgrad(u1.d, u1.ci_real, in_t, b["d_c1"], self._grad(u1.conv.weight), self.wgrad_ws)
             if ud is not None:
                 # identity = bn_d(conv1x1_s2(u)), no relu: its output gradient is dz (= g_out now)
@@ -257,8 +258,10 @@ class EncoderEngine:
             else:
                 ops.conv_dgrad(u1.d, b["d_c1"], u1.wT, b["g_u"], g_out, 1)
         s = self.stem
-        ops.maxpool_bwd(self.g_pool, self.pool_idx, self.g_y0, self.N, s.d.Ho, s.d.Wo, 64, self.Hp, self.Wp)
-        self._bn_bwd(s, self.g_y0, self.g_y0, self.d_c0, True)
+        # max-pool scatter + ReLU mask + BN backward in one pair of passes over the stem conv output
+        ops.bn_relu_maxpool_bwd(self.g_pool, self.pool_idx, s.x, self.d_c0, self.N, s.d.Ho, s.d.Wo, 64, self.Hp,
+                                self.Wp, s.bn.weight.data, s.mean, s.invstd, s.scale, s.shift, self.bn_partial,
+                                self._grad(s.bn.weight), self._grad(s.bn.bias))
         ops.stem_wgrad(x16, self.d_c0, self._grad(s.conv.weight), s.ci_real, self.N, self.H, self.W, self.wgrad_ws)
 
     def _block_inputs(self):

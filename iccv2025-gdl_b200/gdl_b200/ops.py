@@ -194,6 +194,29 @@ def bn_bwd(dy, y, x, dz, dx, P, Cc, gamma, mean, invstd, partial, dgamma, dbeta,
                                  int(relu), _stream()), "gdl_bn_bwd")
 
 
+@_op("bn_bwd", 3, lambda dy, x, dx, P, Cc, *a: ("bytes", 10.0 * P * Cc))
+def bn_bwd_nores(dy, x, dx, P, Cc, gamma, mean, invstd, scale, shift, partial, dgamma, dbeta):
+    """BN+ReLU backward without a residual input: mask recomputed from x (no y read, no dz write)."""
+    check(_lib.load().gdl_bn_bwd_nores(_ptr(dy), _ptr(x), _ptr(dx), P, Cc, _ptr(gamma), _ptr(mean), _ptr(invstd),
+                                       _ptr(scale), _ptr(shift), _ptr(partial), _ptr(dgamma), _ptr(dbeta),
+                                       _stream()), "gdl_bn_bwd_nores")
+
+
+@_op("stem_tail_fwd", 1, lambda x, sc, sh, y, am, N, H, W, Cc, Ho, Wo: ("bytes", N * Cc * (2.0 * H * W + 3.0 * Ho * Wo)))
+def bn_relu_maxpool_fwd(x, scale, shift, y, argmax, N, H, W, Cc, Ho, Wo):
+    check(_lib.load().gdl_bn_relu_maxpool_fwd(_ptr(x), _ptr(scale), _ptr(shift), _ptr(y), _ptr(argmax), N, H, W, Cc,
+                                              Ho, Wo, _stream()), "gdl_bn_relu_maxpool_fwd")
+
+
+@_op("stem_tail_bwd", 3, lambda g, am, x, dx, N, H, W, Cc, Ho, Wo, *a: ("bytes", N * Cc * (6.0 * H * W + 6.0 * Ho * Wo)))
+def bn_relu_maxpool_bwd(gpool, argmax, x, dx, N, H, W, Cc, Ho, Wo, gamma, mean, invstd, scale, shift, partial,
+                        dgamma, dbeta):
+    check(_lib.load().gdl_bn_relu_maxpool_bwd(_ptr(gpool), _ptr(argmax), _ptr(x), _ptr(dx), N, H, W, Cc, Ho, Wo,
+                                              _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
+                                              _ptr(partial), _ptr(dgamma), _ptr(dbeta), _stream()),
+          "gdl_bn_relu_maxpool_bwd")
+
+
 def _pool_bytes(a, b, c, N, H, W, Cc, Ho, Wo):
     return ("bytes", N * Cc * (2.0 * H * W + 3.0 * Ho * Wo))
 

@@ -117,6 +117,26 @@ int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz, void* dx,
                int C, const float* gamma, const float* mean, const float* invstd,
                float* partial, float* dgamma, float* dbeta, int relu, gdl_stream_t s);
 
+/* Same for units WITHOUT a residual input and WITH ReLU (backbone.py:44-46 conv1/bn1/relu): the mask is
+ * recomputed from x (y > 0 <=> x*scale+shift > 0 with the forward's scale/shift), so y is not read and no
+ * masked gradient is written: 10 B/element instead of 14. */
+int gdl_bn_bwd_nores(const void* dy, const void* x, void* dx, int64_t P, int C, const float* gamma,
+                     const float* mean, const float* invstd, const float* scale, const float* shift,
+                     float* partial, float* dgamma, float* dbeta, gdl_stream_t s);
+
+/* ---- stem tail fused: BN-apply + ReLU + MaxPool2d(3,2,1) (reference models/backbone.py:104-106) ----
+ * Forward reads the stem conv output x [N,H,W,C] and writes the pooled map y [N,Ho,Wo,C] + 1-byte arg-max;
+ * the activation relu(bn(x)) — the largest tensor of the step — is never materialised.  Backward gathers the
+ * pooled gradient through the arg-max, recomputes the ReLU mask from x and does the BN backward
+ * (dgamma/dbeta fp32 overwritten, dx bf16).  Results are bit-identical to gdl_bn_apply + gdl_maxpool_fwd
+ * and gdl_maxpool_bwd + gdl_bn_bwd. */
+int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const float* shift, void* y,
+                            uint8_t* argmax, int N, int H, int W, int C, int Ho, int Wo, gdl_stream_t s);
+int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax, const void* x, void* dx, int N,
+                            int H, int W, int C, int Ho, int Wo, const float* gamma, const float* mean,
+                            const float* invstd, const float* scale, const float* shift, float* partial,
+                            float* dgamma, float* dbeta, gdl_stream_t s);
+
 /* ---- MaxPool2d(3,2,1) (reference models/backbone.py:106) ------------------------------ */
 int gdl_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C, int Ho,
                     int Wo, gdl_stream_t s);

@@ -284,6 +284,71 @@ def test_maxpool(N, H, W, Cc):
     assert abs(nchw(dx).sum().item() - xf.grad.sum().item()) < 1e-1 * (1 + abs(xf.grad.sum().item()))
 
 
+@pytest.mark.parametrize("P,Cc", [(1000, 64), (50000, 256), (98, 512)])
+def test_bn_bwd_nores_matches_masked_path(P, Cc):
+    """BN+ReLU backward with the mask recomputed from x == the path that reads y and writes dz."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(15)
+    x = (torch.randn(P, Cc, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    gamma = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cc, device="cuda", generator=g) * 0.1
+    partial = torch.empty(ops.bn_partial_floats(P, Cc), device="cuda")
+    mean, invstd, scale, shift = (torch.empty(Cc, device="cuda") for _ in range(4))
+    ops.bn_stats(x, P, Cc, partial, gamma, beta, 1e-5, 0.1, None, None, mean, invstd, scale, shift)
+    y = torch.empty_like(x)
+    ops.bn_apply(x, None, y, P, Cc, scale, shift, 1)
+    dy = torch.randn(P, Cc, device="cuda", generator=g).to(torch.bfloat16)
+    dz, dx1, dx2 = torch.empty_like(dy), torch.empty_like(dy), torch.empty_like(dy)
+    dg1, db1, dg2, db2 = (torch.empty(Cc, device="cuda") for _ in range(4))
+    ops.bn_bwd(dy, y, x, dz, dx1, P, Cc, gamma, mean, invstd, partial, dg1, db1, 1)
+    ops.bn_bwd_nores(dy, x, dx2, P, Cc, gamma, mean, invstd, scale, shift, partial, dg2, db2)
+    torch.cuda.synchronize()
+    assert torch.equal(dg1, dg2) and torch.equal(db1, db2)
+    assert torch.equal(dx1, dx2)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 129, 94), (3, 112, 112), (1, 7, 9)])
+def test_stem_tail_fused_matches_unfused(N, H, W):
+    """bn_relu_maxpool_fwd/bwd == bn_apply + maxpool_fwd and maxpool_bwd + bn_bwd, bit for bit."""
+    ops = _ops()
+    Cc = 64
+    g = torch.Generator(device="cuda").manual_seed(16)
+    P = N * H * W
+    x = (torch.randn(N, H, W, Cc, device="cuda", generator=g) * 2 + 0.3).to(torch.bfloat16)
+    gamma = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cc, device="cuda", generator=g) * 0.1
+    partial = torch.empty(ops.bn_partial_floats(P, Cc), device="cuda")
+    mean, invstd, scale, shift = (torch.empty(Cc, device="cuda") for _ in range(4))
+    ops.bn_stats(x, P, Cc, partial, gamma, beta, 1e-5, 0.1, None, None, mean, invstd, scale, shift)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y0 = torch.empty_like(x)
+    ops.bn_apply(x, None, y0, P, Cc, scale, shift, 1)
+    y1 = torch.empty(N, Ho, Wo, Cc, device="cuda", dtype=torch.bfloat16)
+    am1 = torch.empty(N, Ho, Wo, Cc, device="cuda", dtype=torch.uint8)
+    ops.maxpool_fwd(y0, y1, am1, N, H, W, Cc, Ho, Wo)
+    y2, am2 = torch.empty_like(y1), torch.empty_like(am1)
+    ops.bn_relu_maxpool_fwd(x, scale, shift, y2, am2, N, H, W, Cc, Ho, Wo)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2) and torch.equal(am1, am2)
+    gp = torch.randn(N, Ho, Wo, Cc, device="cuda", generator=g).to(torch.bfloat16)
+    g0 = torch.empty_like(x)
+    ops.maxpool_bwd(gp, am1, g0, N, H, W, Cc, Ho, Wo)
+    dx1, dx2 = torch.empty_like(x), torch.empty_like(x)
+    dg1, db1, dg2, db2 = (torch.empty(Cc, device="cuda") for _ in range(4))
+    ops.bn_bwd(g0, y0, x, g0, dx1, P, Cc, gamma, mean, invstd, partial, dg1, db1, 1)
+    ops.bn_relu_maxpool_bwd(gp, am2, x, dx2, N, H, W, Cc, Ho, Wo, gamma, mean, invstd, scale, shift, partial,
+                            dg2, db2)
+    torch.cuda.synchronize()
+    # same per-pixel values; the channel sums are accumulated in a different (fixed) order
+    assert rel_err(dg2, dg1) < 1e-5 and rel_err(db2, db1) < 1e-5
+    assert rel_err(dx2.float(), dx1.float()) < 1e-3
+    dx3, dg3, db3 = torch.empty_like(x), torch.empty_like(dg2), torch.empty_like(db2)
+    ops.bn_relu_maxpool_bwd(gp, am2, x, dx3, N, H, W, Cc, Ho, Wo, gamma, mean, invstd, scale, shift, partial,
+                            dg3, db3)
+    torch.cuda.synchronize()
+    assert torch.equal(dg2, dg3) and torch.equal(db2, db3) and torch.equal(dx2, dx3)  # deterministic
+
+
 def test_gap():
     ops = _ops()
     B, G, Cc = 5, 147, 512
