@@ -280,6 +280,53 @@ def softmax_ce(logits, labels, loss_scale, grad_scale, loss_out, dlogits, scratc
                                      _ptr(dlogits), _ptr(scratch), B, n, _stream()), "gdl_softmax_ce")
 
 
+# ---------------------------------------------------------------------------------- FiLM head
+@_op("gemm_nt", 1, lambda A, lda, Bm, Cm, M, N, K: ("flops", 2.0 * M * N * K))
+def gemm_nt_bf16(A, lda, Bm, Cm, M, N, K):
+    """C[M][N] bf16 = A[M][K] (row stride lda) * B[N][K]^T on the flat-window conv kernel."""
+    check(_lib.load().gdl_gemm_nt_bf16(_addr(A), lda, _ptr(Bm), _ptr(Cm), M, N, K, _stream()), "gdl_gemm_nt_bf16")
+
+
+def gemm_tn_workspace_bytes(M, N, K):
+    return int(_lib.load().gdl_gemm_tn_workspace_bytes(M, N, K))
+
+
+@_op("gemm_tn", 2, lambda At, Bt, bias, Cm, M, N, K, ws: ("flops", 2.0 * M * N * K))
+def gemm_tn_f32(At, Bt, bias, Cm, M, N, K, ws):
+    """C[M][N] f32 = At[K][M]^T * Bt[K][N] (+ bias) on the flat-window wgrad kernel (split-K)."""
+    check(_lib.load().gdl_gemm_tn_f32(_ptr(At), _ptr(Bt), _ptr(bias), _ptr(Cm), M, N, K, _ptr(ws),
+                                      ws.numel() * ws.element_size(), _stream()), "gdl_gemm_tn_f32")
+
+
+@_op("film_outer", 1, lambda a, v, Zt, B, D, ZB, variants: ("bytes", 2.0 * D * D * ZB))
+def film_outer(a, v, Zt, B, D, ZB, variants):
+    check(_lib.load().gdl_film_outer(_ptr(a), _ptr(v), _ptr(Zt), B, D, ZB, variants, _stream()), "gdl_film_outer")
+
+
+@_op("cast_pad", 1)
+def cast_pad_bf16(src0, r0, src1, r1, cols, ld, transpose, dst, drows, dcols):
+    check(_lib.load().gdl_cast_pad_bf16(_ptr(src0), r0, _ptr(src1), r1, cols, ld, int(transpose), _ptr(dst),
+                                        drows, dcols, _stream()), "gdl_cast_pad_bf16")
+
+
+@_op("film_contract", 1, lambda G, ldg, c0, x, y, dx, dy, B, D, sum_mode: ("bytes", 4.0 * D * D * B))
+def film_contract(G, ldg, c0, x, y, dx, dy, B, D, sum_mode):
+    check(_lib.load().gdl_film_contract(_ptr(G), ldg, c0, _ptr(x), _ptr(y), _ptr(dx), _ptr(dy), B, D,
+                                        int(sum_mode), _stream()), "gdl_film_contract")
+
+
+@_op("transpose", 1, lambda src, dst, R, Cn: ("bytes", 6.0 * R * Cn))
+def transpose_f32_to_bf16(src, dst, R, Cn):
+    check(_lib.load().gdl_transpose_f32_to_bf16(_ptr(src), _ptr(dst), R, Cn, _stream()),
+          "gdl_transpose_f32_to_bf16")
+
+
+@_op("transpose", 1, lambda src, dst, R, Cn: ("bytes", 6.0 * R * Cn))
+def transpose_bf16_to_f32(src, dst, R, Cn):
+    check(_lib.load().gdl_transpose_bf16_to_f32(_ptr(src), _ptr(dst), R, Cn, _stream()),
+          "gdl_transpose_bf16_to_f32")
+
+
 @_op("gated_fwd", 1)
 def gated_fwd(hx, hy, m_out, m_x, m_y):
     check(_lib.load().gdl_gated_fwd(_ptr(hx), _ptr(hy), _ptr(m_out), _ptr(m_x), _ptr(m_y), hx.numel(),

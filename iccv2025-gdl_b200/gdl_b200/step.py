@@ -135,6 +135,7 @@ class DGLStep:
     # ------------------------------------------------------------------ heads
     def _init_head(self):
         fm, B, n, dev = self.model.fusion_module, self.B, self.n, self.device
+        self.film = None
         if isinstance(fm, GatedFusion_DGL):
             z = lambda *s: torch.empty(*s, device=dev)
             self.g = dict(hx=z(B, 512), hy=z(B, 512), mo=z(B, 512), mx=z(B, 512), my=z(B, 512),
@@ -234,6 +235,8 @@ class DGLStep:
         ops.sgd_momentum(ar.param, ar.grad, ar.momentum, ar.numel, lr, self.mu, self.wd, first, self.stats[4:8])
         self.enc_a.repack()
         self.enc_v.repack()
+        if self.film is not None:
+            self.film.refresh()
         self.stats[0:3].copy_(self.losses)
         torch._foreach_add_(self._bn_counters, 1)
 

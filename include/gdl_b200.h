@@ -188,6 +188,32 @@ int gdl_gated_fwd(const float* hx, const float* hy, float* m_out, float* m_x, fl
 int gdl_gated_bwd(const float* hx, const float* hy, const float* dm_x, const float* dm_y,
                   float* dhx, float* dhy, int64_t numel, gdl_stream_t s);
 
+/* ---- FiLM_DGL head (reference models/fusion_modules.py:126-178: fc(512*512 -> 512) on the outer products
+ * a (x) v, a (x) a, v (x) v, then fc_out).  Dense contractions on the tcgen05 flat-window kernels, operands
+ * stored feature-major (see csrc/film.cu). -------------------------------------------------------------- */
+/* C[M][N] bf16 = A[M][K] (row stride lda elements) * B[N][K]^T.  M % 128 == 0, N % 64 == 0, K % 64 == 0. */
+int gdl_gemm_nt_bf16(const void* A, int64_t lda, const void* B, void* C, int64_t M, int N, int K,
+                     gdl_stream_t s);
+/* C[M][N] f32 = At[K][M]^T * Bt[K][N] (+ bias[N]); reduction over K (K % 128 == 0) with deterministic split-K.
+ * M, N multiples of 128 (or M == 64).  workspace: gdl_gemm_tn_workspace_bytes(M, N, K). */
+int64_t gdl_gemm_tn_workspace_bytes(int M, int N, int64_t K);
+int gdl_gemm_tn_f32(const void* At, const void* Bt, const float* bias, float* C, int M, int N, int64_t K,
+                    void* workspace, int64_t workspace_bytes, gdl_stream_t s);
+/* Zt bf16 [D*D][ZB]: column b of variant 0 = a_b (x) v_b, variant 1 = a_b (x) a_b, variant 2 = v_b (x) v_b
+ * (columns var*B + b; the rest zero).  a, v f32 [B][D]. */
+int gdl_film_outer(const float* a, const float* v, void* Zt, int B, int D, int ZB, int variants, gdl_stream_t s);
+/* dst bf16 [drows][dcols], zero padded, from f32 rows [src0 (r0 rows); src1 (r1 rows)] of `cols` columns
+ * (row stride ld); transpose != 0 writes dst[c][r]. */
+int gdl_cast_pad_bf16(const float* src0, int r0, const float* src1, int r1, int cols, int ld, int transpose,
+                      void* dst, int drows, int dcols, gdl_stream_t s);
+/* G bf16 [D*D][ldg], batch row b in column c0+b: dx[b][i] = sum_j G[i*D+j]*y[b][j], dy[b][j] = sum_i G[i*D+j]*x[b][i];
+ * sum_mode != 0: dx <- dx + dy (x == y), dy untouched. */
+int gdl_film_contract(const void* G, int ldg, int c0, const float* x, const float* y, float* dx, float* dy,
+                      int B, int D, int sum_mode, gdl_stream_t s);
+/* fp32 [R][Cn] <-> bf16 [Cn][R] (the feature-major shadow of fc.weight and its gradient). */
+int gdl_transpose_f32_to_bf16(const float* src, void* dst, int R, int64_t Cn, gdl_stream_t s);
+int gdl_transpose_bf16_to_f32(const void* src, float* dst, int R, int64_t Cn, gdl_stream_t s);
+
 /* ---- optimizer / clipping / diagnostics (reference main_dgl.py:129-154,249) ---------- */
 /* Flat fp32 gradient arena with a segment table: seg_end[nseg] (exclusive end offsets,
  * padding belongs to the preceding segment), seg_group[nseg] (0 = audio_net, 1 = visual_net,

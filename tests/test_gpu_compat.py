@@ -35,7 +35,7 @@ def cos(a, b):
     return F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
 
 
-@pytest.mark.parametrize("fusion", ["concat", "sum", "gated"])
+@pytest.mark.parametrize("fusion", ["concat", "sum", "gated", "film"])
 def test_reference_two_backward_loop_runs_on_the_modules(fusion):
     """The reference's step, verbatim in structure (main_dgl.py:97-154): zero_grad, forward,
     3x CE, (La+Lv)*alpha backward with retain_graph, wipe `fusion` grads, Lf backward, clip, SGD."""

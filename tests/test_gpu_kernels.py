@@ -349,6 +349,63 @@ def test_stem_tail_fused_matches_unfused(N, H, W):
     assert torch.equal(dg2, dg3) and torch.equal(db2, db3) and torch.equal(dx2, dx3)  # deterministic
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 128, 64), (4096, 512, 256), (2048, 64, 512)])
+def test_gemm_nt_bf16(M, N, K):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(21)
+    lda = K + 64
+    A = torch.randn(M, lda, device="cuda", generator=g).to(torch.bfloat16)
+    Bm = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    Cm = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm_nt_bf16(A, lda, Bm, Cm, M, N, K)
+    torch.cuda.synchronize()
+    ref = A[:, :K].float() @ Bm.float().t()
+    assert rel_err(Cm.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 4096), (384, 512, 16384), (64, 128, 2048)])
+def test_gemm_tn_f32(M, N, K):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(22)
+    At = torch.randn(K, M, device="cuda", generator=g).to(torch.bfloat16)
+    Bt = torch.randn(K, N, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ws = torch.empty(ops.gemm_tn_workspace_bytes(M, N, K) // 4, device="cuda")
+    Cm = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm_tn_f32(At, Bt, bias, Cm, M, N, K, ws)
+    torch.cuda.synchronize()
+    ref = At.float().t() @ Bt.float() + bias
+    assert rel_err(Cm, ref) < 2e-3
+    C2 = torch.empty_like(Cm)
+    ops.gemm_tn_f32(At, Bt, bias, C2, M, N, K, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(Cm, C2)
+
+
+def test_film_fn_matches_torch():
+    """FilmFn (outer product -> Linear(262144 -> 512)) forward and backward vs plain torch."""
+    from gdl_b200.film import FilmFn
+    _ops()
+    B, D = 5, 512
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn(B, D, device="cuda", generator=g, requires_grad=True)
+    y = torch.randn(B, D, device="cuda", generator=g, requires_grad=True)
+    W = (torch.randn(D, D * D, device="cuda", generator=g) * 0.002).requires_grad_(True)
+    b = torch.randn(D, device="cuda", generator=g).requires_grad_(True)
+    h = FilmFn.apply(x, y, W, b)
+    dh = torch.randn(B, D, device="cuda", generator=g)
+    gx, gy, gW, gb = torch.autograd.grad(h, (x, y, W, b), dh)
+    z = torch.bmm(x.detach().unsqueeze(2), y.detach().unsqueeze(1)).flatten(1)
+    x2, y2 = x.detach().clone().requires_grad_(True), y.detach().clone().requires_grad_(True)
+    W2, b2 = W.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    h2 = torch.nn.functional.linear(torch.bmm(x2.unsqueeze(2), y2.unsqueeze(1)).flatten(1), W2, b2)
+    rx, ry, rW, rb = torch.autograd.grad(h2, (x2, y2, W2, b2), dh)
+    assert rel_err(h, h2.detach()) < 6e-3
+    assert rel_err(gx, rx) < 1e-2 and rel_err(gy, ry) < 1e-2
+    assert rel_err(gW, rW) < 1e-2 and rel_err(gb, rb) < 1e-5
+    del z
+
+
 def test_gap():
     ops = _ops()
     B, G, Cc = 5, 147, 512

@@ -38,7 +38,7 @@ def cos(a, b):
     return F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
 
 
-@pytest.mark.parametrize("fusion", ["concat", "sum", "gated"])
+@pytest.mark.parametrize("fusion", ["concat", "sum", "gated", "film"])
 def test_step_matches_oracle_and_golden_tiny(fusion):
     from oracle import dgl_oracle as O
     from oracle.synth import make_batch
