@@ -43,9 +43,20 @@ __global__ void gemm_tn_reduce_kernel(const float* __restrict__ partial, int spl
 }
 
 // Zt[f = i*D + j][col]: col < B: a_i v_j (multimodal, detached) | B..2B: a_i a_j | 2B..3B: v_i v_j | rest 0.
-// at / vt are the features transposed to [D][B] so that the batch index is contiguous.
-__global__ void __launch_bounds__(256) film_outer_kernel(const float* __restrict__ a, const float* __restrict__ v,
-                                                         bf16* __restrict__ Zt, int B, int D, int ZB, int variants) {
+// Step 1 transposes the features to [D][ZB-padded batch] so that step 2 reads them along the batch index.
+__global__ void film_transpose_feat_kernel(const float* __restrict__ a, const float* __restrict__ v,
+                                           float* __restrict__ at, float* __restrict__ vt, int B, int D, int Bp) {
+  const int64_t total = (int64_t)D * Bp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = int(idx / Bp), b = int(idx - (int64_t)i * Bp);
+    at[idx] = b < B ? a[(int64_t)b * D + i] : 0.f;
+    vt[idx] = b < B ? v[(int64_t)b * D + i] : 0.f;
+  }
+}
+__global__ void __launch_bounds__(256) film_outer_kernel(const float* __restrict__ at, const float* __restrict__ vt,
+                                                         bf16* __restrict__ Zt, int B, int D, int ZB, int Bp,
+                                                         int variants) {
   const int groups = ZB / 8;
   const int64_t total = (int64_t)D * D * groups;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -53,17 +64,17 @@ __global__ void __launch_bounds__(256) film_outer_kernel(const float* __restrict
     const int g = int(idx % groups);
     const int64_t f = idx / groups;
     const int i = int(f / D), j = int(f - (int64_t)i * D);
+    const float* ai = at + (int64_t)i * Bp;
+    const float* aj = at + (int64_t)j * Bp;
+    const float* vi = vt + (int64_t)i * Bp;
+    const float* vj = vt + (int64_t)j * Bp;
     float o[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int col = g * 8 + c;
       const int var = col / B, b = col - var * B;
       float val = 0.f;
-      if (var < variants) {
-        const float ai = a[(int64_t)b * D + i], aj = a[(int64_t)b * D + j];
-        const float vi = v[(int64_t)b * D + i], vj = v[(int64_t)b * D + j];
-        val = var == 0 ? ai * vj : (var == 1 ? ai * aj : vi * vj);
-      }
+      if (var < variants) val = var == 0 ? ai[b] * vj[b] : (var == 1 ? ai[b] * aj[b] : vi[b] * vj[b]);
       o[c] = val;
     }
     *reinterpret_cast<uint4*>(Zt + f * ZB + g * 8) = pack8(o);
@@ -91,18 +102,76 @@ __global__ void cast_pad_kernel(const float* __restrict__ src0, int r0, const fl
 // G [D*D][ldg] bf16 (column = batch row): dx[b][i] = sum_j G[i*D+j][c0+b] * y[b][j],
 //                                        dy[b][j] = sum_i G[i*D+j][c0+b] * x[b][i]
 // sum_mode 1: dx <- dx + dy (x and y are the same tensor: a (x) a), dy not written.
-// One block per output index t (i for dx, j for dy), threads over the batch (coalesced rows of G).
-__global__ void __launch_bounds__(256) film_contract_kernel(const bf16* __restrict__ G, int ldg, int c0,
-                                                            const float* __restrict__ x, const float* __restrict__ y,
-                                                            float* __restrict__ dx, float* __restrict__ dy, int B, int D,
-                                                            int sum_mode) {
+// One block per output index t (i for dx, j for dy).  Vector path (B, c0, ldg multiples of 8): a thread owns 8
+// batch columns (one 16-byte load per G row) and one of KS interleaved k slices; slices are combined in a
+// fixed order through shared memory.  xt / yt are the features transposed to [D][Bp].
+constexpr int kContractThreads = 256;
+__global__ void __launch_bounds__(kContractThreads) film_contract_kernel(
+    const bf16* __restrict__ G, int ldg, int c0, const float* __restrict__ xt, const float* __restrict__ yt,
+    float* __restrict__ dx, float* __restrict__ dy, int B, int D, int Bp, int sum_mode) {
+  __shared__ float red[2][kContractThreads][8];
+  const int t = blockIdx.x;
+  const int bgroups = B / 8;                       // vector path only
+  const int KS = kContractThreads / bgroups;       // k slices
+  const int bq = threadIdx.x % bgroups, ks = threadIdx.x / bgroups;
+  float sx[8], sy[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) sx[c] = sy[c] = 0.f;
+  if (ks < KS) {
+    for (int k = ks; k < D; k += KS) {
+      float g1[8], g2[8];
+      unpack8(ld_stream16(G + ((int64_t)t * D + k) * ldg + c0 + bq * 8), g1);
+      unpack8(ld_stream16(G + ((int64_t)k * D + t) * ldg + c0 + bq * 8), g2);
+      const float4 y0 = *reinterpret_cast<const float4*>(yt + (int64_t)k * Bp + bq * 8);
+      const float4 y1 = *reinterpret_cast<const float4*>(yt + (int64_t)k * Bp + bq * 8 + 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(xt + (int64_t)k * Bp + bq * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(xt + (int64_t)k * Bp + bq * 8 + 4);
+      const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        sx[c] = fmaf(g1[c], yv[c], sx[c]);
+        sy[c] = fmaf(g2[c], xv[c], sy[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    red[0][threadIdx.x][c] = sx[c];
+    red[1][threadIdx.x][c] = sy[c];
+  }
+  __syncthreads();
+  if (ks == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float ax = 0.f, ay = 0.f;
+      for (int s2 = 0; s2 < KS; ++s2) {
+        ax += red[0][s2 * bgroups + bq][c];
+        ay += red[1][s2 * bgroups + bq][c];
+      }
+      const int b = bq * 8 + c;
+      if (sum_mode) {
+        dx[(int64_t)b * D + t] = ax + ay;
+      } else {
+        dx[(int64_t)b * D + t] = ax;
+        dy[(int64_t)b * D + t] = ay;
+      }
+    }
+  }
+}
+// scalar path for batches that are not a multiple of 8
+__global__ void __launch_bounds__(256) film_contract_scalar_kernel(const bf16* __restrict__ G, int ldg, int c0,
+                                                                   const float* __restrict__ xt,
+                                                                   const float* __restrict__ yt, float* __restrict__ dx,
+                                                                   float* __restrict__ dy, int B, int D, int Bp,
+                                                                   int sum_mode) {
   const int t = blockIdx.x;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     float sx = 0.f, sy = 0.f;
     const bf16* gcol = G + c0 + b;
     for (int k = 0; k < D; ++k) {
-      sx = fmaf(__bfloat162float(gcol[((int64_t)t * D + k) * ldg]), y[(int64_t)b * D + k], sx);
-      sy = fmaf(__bfloat162float(gcol[((int64_t)k * D + t) * ldg]), x[(int64_t)b * D + k], sy);
+      sx = fmaf(__bfloat162float(gcol[((int64_t)t * D + k) * ldg]), yt[(int64_t)k * Bp + b], sx);
+      sy = fmaf(__bfloat162float(gcol[((int64_t)k * D + t) * ldg]), xt[(int64_t)k * Bp + b], sy);
     }
     if (sum_mode) {
       dx[(int64_t)b * D + t] = sx + sy;
@@ -179,14 +248,31 @@ extern "C" int gdl_gemm_tn_f32(const void* At, const void* Bt, const float* bias
   return GDL_OK;
 }
 
+static int film_bp(int B) { return (B + 7) / 8 * 8; }
+
+extern "C" int64_t gdl_film_scratch_floats(int B, int D) { return 2 * (int64_t)D * film_bp(B); }
+
+static int film_transpose(const float* a, const float* v, float* scratch, int B, int D, cudaStream_t s) {
+  const int Bp = film_bp(B);
+  const int64_t total = (int64_t)D * Bp;
+  film_transpose_feat_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(a, v, scratch, scratch + total, B, D, Bp);
+  GDL_CHECK_LAUNCH("film_transpose_feat_kernel");
+  return GDL_OK;
+}
+
 extern "C" int gdl_film_outer(const float* a, const float* v, void* Zt, int B, int D, int ZB, int variants,
-                              gdl_stream_t s) {
-  GDL_REQUIRE(a && v && Zt && B > 0 && D > 0 && ZB % 8 == 0 && variants >= 1 && variants <= 3 && variants * B <= ZB,
+                              float* scratch, gdl_stream_t s) {
+  GDL_REQUIRE(a && v && Zt && scratch && B > 0 && D > 0 && ZB % 8 == 0 && variants >= 1 && variants <= 3 &&
+                  variants * B <= ZB,
               "gdl_film_outer: bad arguments");
+  int rc = film_transpose(a, v, scratch, B, D, (cudaStream_t)s);
+  if (rc != GDL_OK) return rc;
+  const int Bp = film_bp(B);
   const int64_t total = (int64_t)D * D * (ZB / 8);
   int64_t blocks = ceil_div64(total, 256);
   if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
-  film_outer_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(a, v, (bf16*)Zt, B, D, ZB, variants);
+  film_outer_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(scratch, scratch + (int64_t)D * Bp, (bf16*)Zt, B, D, ZB,
+                                                                  Bp, variants);
   GDL_CHECK_LAUNCH("film_outer_kernel");
   return GDL_OK;
 }
@@ -205,9 +291,19 @@ extern "C" int gdl_cast_pad_bf16(const float* src0, int r0, const float* src1, i
 }
 
 extern "C" int gdl_film_contract(const void* G, int ldg, int c0, const float* x, const float* y, float* dx, float* dy,
-                                 int B, int D, int sum_mode, gdl_stream_t s) {
-  GDL_REQUIRE(G && x && y && dx && (sum_mode || dy) && B > 0 && D > 0, "gdl_film_contract: bad arguments");
-  film_contract_kernel<<<D, 256, 0, (cudaStream_t)s>>>((const bf16*)G, ldg, c0, x, y, dx, dy, B, D, sum_mode);
+                                 int B, int D, int sum_mode, float* scratch, gdl_stream_t s) {
+  GDL_REQUIRE(G && x && y && dx && scratch && (sum_mode || dy) && B > 0 && D > 0, "gdl_film_contract: bad arguments");
+  int rc = film_transpose(x, y, scratch, B, D, (cudaStream_t)s);
+  if (rc != GDL_OK) return rc;
+  const int Bp = film_bp(B);
+  const float* xt = scratch;
+  const float* yt = scratch + (int64_t)D * Bp;
+  if (B % 8 == 0 && c0 % 8 == 0 && ldg % 8 == 0 && B / 8 <= kContractThreads)
+    film_contract_kernel<<<D, kContractThreads, 0, (cudaStream_t)s>>>((const bf16*)G, ldg, c0, xt, yt, dx, dy, B, D, Bp,
+                                                                     sum_mode);
+  else
+    film_contract_scalar_kernel<<<D, 256, 0, (cudaStream_t)s>>>((const bf16*)G, ldg, c0, xt, yt, dx, dy, B, D, Bp,
+                                                                sum_mode);
   GDL_CHECK_LAUNCH("film_contract_kernel");
   return GDL_OK;
 }

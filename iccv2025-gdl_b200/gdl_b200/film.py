@@ -41,6 +41,7 @@ class FilmBuffers:
         self.dHs = torch.empty(self.NG, D, **bf)
         self.dW1t = torch.empty(F2, D, **bf)
         self.G = torch.empty(F2, self.NG, **bf)
+        self.scratch = torch.empty(ops.film_scratch_floats(B, D), device=dev)
 
     def refresh(self, W1):
         """bf16 feature-major shadow of fc.weight (after every optimizer step)."""
@@ -65,7 +66,7 @@ class FilmHead:
         """st: the DGLStep (features, labels, logits, losses, da/dv live there)."""
         fm, b, B, n = self.fm, self.buf, self.B, self.n
         W1, b1, W2, b2 = fm.fc.weight, fm.fc.bias, fm.fc_out.weight, fm.fc_out.bias
-        ops.film_outer(st.a_feat, st.v_feat, b.Zt, B, D, b.ZB, 3)
+        ops.film_outer(st.a_feat, st.v_feat, b.Zt, B, D, b.ZB, 3, b.scratch)
         ops.gemm_tn_f32(b.Zt, b.W1t, b1.data, b.H, b.ZB, D, F2, b.ws)          # rows: [z | a(x)a | v(x)v]
         for i in range(3):                                                       # logits: out, out_a, out_v
             ops.linear_fwd(b.H[i * B:(i + 1) * B], W2.data, b2.data, st.logits[i], B, D, n)
@@ -82,8 +83,8 @@ class FilmHead:
         ops.transpose_bf16_to_f32(b.dW1t, W1.grad, D, F2)
         ops.cast_pad_bf16(self.dH[1], B, self.dH[2], B, D, D, False, b.dHs, b.NG, D)
         ops.gemm_nt_bf16(b.W1t, D, b.dHs, b.G, F2, b.NG, D)
-        ops.film_contract(b.G, b.NG, 0, st.a_feat, st.a_feat, st.da, None, B, D, True)
-        ops.film_contract(b.G, b.NG, B, st.v_feat, st.v_feat, st.dv, None, B, D, True)
+        ops.film_contract(b.G, b.NG, 0, st.a_feat, st.a_feat, st.da, None, B, D, True, b.scratch)
+        ops.film_contract(b.G, b.NG, B, st.v_feat, st.v_feat, st.dv, None, B, D, True, b.scratch)
 
 
 class FilmFn(torch.autograd.Function):
@@ -95,7 +96,7 @@ class FilmFn(torch.autograd.Function):
         B = x.shape[0]
         buf = FilmBuffers(B, 1, x.device)
         buf.refresh(W.data)
-        ops.film_outer(x, y, buf.Zt, B, D, buf.ZB, 1)
+        ops.film_outer(x, y, buf.Zt, B, D, buf.ZB, 1, buf.scratch)
         ops.gemm_tn_f32(buf.Zt, buf.W1t, b.data if b is not None else None, buf.H, buf.ZB, D, F2, buf.ws)
         ctx.save_for_backward(x, y, W, b)
         ctx.buf = buf
@@ -118,5 +119,5 @@ class FilmFn(torch.autograd.Function):
             ops.cast_pad_bf16(dh, B, None, 0, D, D, False, buf.dHs, buf.NG, D)
             ops.gemm_nt_bf16(buf.W1t, D, buf.dHs, buf.G, F2, buf.NG, D)
             dx, dy = torch.empty_like(x), torch.empty_like(y)
-            ops.film_contract(buf.G, buf.NG, 0, x, y, dx, dy, B, D, False)
+            ops.film_contract(buf.G, buf.NG, 0, x, y, dx, dy, B, D, False, buf.scratch)
         return dx, dy, dW, db

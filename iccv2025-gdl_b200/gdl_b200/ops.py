@@ -298,9 +298,14 @@ def gemm_tn_f32(At, Bt, bias, Cm, M, N, K, ws):
                                       ws.numel() * ws.element_size(), _stream()), "gdl_gemm_tn_f32")
 
 
-@_op("film_outer", 1, lambda a, v, Zt, B, D, ZB, variants: ("bytes", 2.0 * D * D * ZB))
-def film_outer(a, v, Zt, B, D, ZB, variants):
-    check(_lib.load().gdl_film_outer(_ptr(a), _ptr(v), _ptr(Zt), B, D, ZB, variants, _stream()), "gdl_film_outer")
+def film_scratch_floats(B, D):
+    return int(_lib.load().gdl_film_scratch_floats(B, D))
+
+
+@_op("film_outer", 2, lambda a, v, Zt, B, D, ZB, variants, scratch: ("bytes", 2.0 * D * D * ZB))
+def film_outer(a, v, Zt, B, D, ZB, variants, scratch):
+    check(_lib.load().gdl_film_outer(_ptr(a), _ptr(v), _ptr(Zt), B, D, ZB, variants, _ptr(scratch), _stream()),
+          "gdl_film_outer")
 
 
 @_op("cast_pad", 1)
@@ -309,10 +314,10 @@ def cast_pad_bf16(src0, r0, src1, r1, cols, ld, transpose, dst, drows, dcols):
                                         drows, dcols, _stream()), "gdl_cast_pad_bf16")
 
 
-@_op("film_contract", 1, lambda G, ldg, c0, x, y, dx, dy, B, D, sum_mode: ("bytes", 4.0 * D * D * B))
-def film_contract(G, ldg, c0, x, y, dx, dy, B, D, sum_mode):
+@_op("film_contract", 2, lambda G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch: ("bytes", 4.0 * D * D * B))
+def film_contract(G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch):
     check(_lib.load().gdl_film_contract(_ptr(G), ldg, c0, _ptr(x), _ptr(y), _ptr(dx), _ptr(dy), B, D,
-                                        int(sum_mode), _stream()), "gdl_film_contract")
+                                        int(sum_mode), _ptr(scratch), _stream()), "gdl_film_contract")
 
 
 @_op("transpose", 1, lambda src, dst, R, Cn: ("bytes", 6.0 * R * Cn))

@@ -201,7 +201,9 @@ int gdl_gemm_tn_f32(const void* At, const void* Bt, const float* bias, float* C,
                     void* workspace, int64_t workspace_bytes, gdl_stream_t s);
 /* Zt bf16 [D*D][ZB]: column b of variant 0 = a_b (x) v_b, variant 1 = a_b (x) a_b, variant 2 = v_b (x) v_b
  * (columns var*B + b; the rest zero).  a, v f32 [B][D]. */
-int gdl_film_outer(const float* a, const float* v, void* Zt, int B, int D, int ZB, int variants, gdl_stream_t s);
+int64_t gdl_film_scratch_floats(int B, int D); /* scratch of gdl_film_outer / gdl_film_contract */
+int gdl_film_outer(const float* a, const float* v, void* Zt, int B, int D, int ZB, int variants, float* scratch,
+                   gdl_stream_t s);
 /* dst bf16 [drows][dcols], zero padded, from f32 rows [src0 (r0 rows); src1 (r1 rows)] of `cols` columns
  * (row stride ld); transpose != 0 writes dst[c][r]. */
 int gdl_cast_pad_bf16(const float* src0, int r0, const float* src1, int r1, int cols, int ld, int transpose,
@@ -209,7 +211,7 @@ int gdl_cast_pad_bf16(const float* src0, int r0, const float* src1, int r1, int 
 /* G bf16 [D*D][ldg], batch row b in column c0+b: dx[b][i] = sum_j G[i*D+j]*y[b][j], dy[b][j] = sum_i G[i*D+j]*x[b][i];
  * sum_mode != 0: dx <- dx + dy (x == y), dy untouched. */
 int gdl_film_contract(const void* G, int ldg, int c0, const float* x, const float* y, float* dx, float* dy,
-                      int B, int D, int sum_mode, gdl_stream_t s);
+                      int B, int D, int sum_mode, float* scratch, gdl_stream_t s);
 /* fp32 [R][Cn] <-> bf16 [Cn][R] (the feature-major shadow of fc.weight and its gradient). */
 int gdl_transpose_f32_to_bf16(const float* src, void* dst, int R, int64_t Cn, gdl_stream_t s);
 int gdl_transpose_bf16_to_f32(const void* src, float* dst, int R, int64_t Cn, gdl_stream_t s);
