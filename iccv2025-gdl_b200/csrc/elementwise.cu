@@ -81,7 +81,25 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const bf16* __rest
   float acc[2][8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[0][c] = acc[1][c] = 0.f;
-  for (int64_t pix = (int64_t)blockIdx.x * lanes + lane; pix < P; pix += (int64_t)gridDim.x * lanes) {
+  // four pixels in flight per thread (memory-level parallelism); the per-thread order stays fixed
+  const int64_t stride = (int64_t)gridDim.x * lanes;
+  int64_t pix = (int64_t)blockIdx.x * lanes + lane;
+  for (; pix + 3 * stride < P; pix += 4 * stride) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = ld_stream16(x + (pix + k * stride) * C + cg * 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(u[k], f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        acc[0][c] += f[c];
+        acc[1][c] = fmaf(f[c], f[c], acc[1][c]);
+      }
+    }
+  }
+  for (; pix < P; pix += stride) {
     float f[8];
     unpack8(ld_stream16(x + pix * C + cg * 8), f);
 #pragma unroll
@@ -196,14 +214,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
   float acc[2][8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[0][c] = acc[1][c] = 0.f;
-  for (int64_t pix = (int64_t)blockIdx.x * lanes + lane; pix < P; pix += (int64_t)gridDim.x * lanes) {
-    const int64_t off = pix * C + cg * 8;
+  const int64_t stride = (int64_t)gridDim.x * lanes;
+  int64_t pix = (int64_t)blockIdx.x * lanes + lane;
+  auto body = [&](int64_t off, const uint4& ug, const uint4& ux, const uint4& uy) {
     float g[8], xv[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + off), g);  // dz may alias dy: no .nc path
-    unpack8(ld_stream16(x + off), xv);
+    unpack8(ug, g);
+    unpack8(ux, xv);
     if (relu) {
       float yv[8];
-      unpack8(ld_stream16(y + off), yv);
+      unpack8(uy, yv);
 #pragma unroll
       for (int c = 0; c < 8; ++c) g[c] = yv[c] > 0.f ? g[c] : 0.f;
       *reinterpret_cast<uint4*>(dz + off) = pack8(g);
@@ -213,6 +232,19 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
       acc[0][c] += g[c];
       acc[1][c] = fmaf(g[c], (xv[c] - mu[c]) * is[c], acc[1][c]);
     }
+  };
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (; pix + stride < P; pix += 2 * stride) {  // two pixels in flight; dz may alias dy: no .nc path for dy
+    const int64_t o0 = pix * C + cg * 8, o1 = (pix + stride) * C + cg * 8;
+    const uint4 g0 = *reinterpret_cast<const uint4*>(dy + o0), x0 = ld_stream16(x + o0);
+    const uint4 g1 = *reinterpret_cast<const uint4*>(dy + o1), x1 = ld_stream16(x + o1);
+    const uint4 y0 = relu ? ld_stream16(y + o0) : zero4, y1 = relu ? ld_stream16(y + o1) : zero4;
+    body(o0, g0, x0, y0);
+    body(o1, g1, x1, y1);
+  }
+  for (; pix < P; pix += stride) {
+    const int64_t off = pix * C + cg * 8;
+    body(off, *reinterpret_cast<const uint4*>(dy + off), ld_stream16(x + off), relu ? ld_stream16(y + off) : zero4);
   }
   block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
 }
@@ -253,17 +285,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   }
   __syncthreads();
   const int groups = C / 8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto body = [&](int64_t i, const uint4& ug, const uint4& ux) {
     const int cg = int(i % groups);
     float g[8], xv[8];
-    unpack8(ld_stream16(dz + i * 8), g);
-    unpack8(ld_stream16(x + i * 8), xv);
+    unpack8(ug, g);
+    unpack8(ux, xv);
 #pragma unroll
     for (int c = 0; c < 8; ++c)
       g[c] = fmaf(s_a[cg * 8 + c], g[c], fmaf(s_b[cg * 8 + c], xv[c], s_c[cg * 8 + c]));
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(g);
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {
+    const uint4 g0 = ld_stream16(dz + i * 8), x0 = ld_stream16(x + i * 8);
+    const uint4 g1 = ld_stream16(dz + (i + stride) * 8), x1 = ld_stream16(x + (i + stride) * 8);
+    body(i, g0, x0);
+    body(i + stride, g1, x1);
   }
+  for (; i < nvec; i += stride) body(i, ld_stream16(dz + i * 8), ld_stream16(x + i * 8));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -383,17 +423,29 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
   float acc[2][8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[0][c] = acc[1][c] = 0.f;
-  for (int64_t pix = (int64_t)blockIdx.x * lanes + lane; pix < P; pix += (int64_t)gridDim.x * lanes) {
-    const int64_t off = pix * C + cg * 8;
+  const int64_t stride = (int64_t)gridDim.x * lanes;
+  int64_t pix = (int64_t)blockIdx.x * lanes + lane;
+  auto body = [&](const uint4& ug, const uint4& ux) {
     float g[8], xv[8];
-    unpack8(ld_stream16(dy + off), g);
-    unpack8(ld_stream16(x + off), xv);
+    unpack8(ug, g);
+    unpack8(ux, xv);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float gz = fmaf(xv[c], sc[c], sh[c]) > 0.f ? g[c] : 0.f;
       acc[0][c] += gz;
       acc[1][c] = fmaf(gz, (xv[c] - mu[c]) * is[c], acc[1][c]);
     }
+  };
+  for (; pix + stride < P; pix += 2 * stride) {  // two pixels (four 16-byte loads) in flight per thread
+    const int64_t o0 = pix * C + cg * 8, o1 = (pix + stride) * C + cg * 8;
+    const uint4 g0 = ld_stream16(dy + o0), x0 = ld_stream16(x + o0);
+    const uint4 g1 = ld_stream16(dy + o1), x1 = ld_stream16(x + o1);
+    body(g0, x0);
+    body(g1, x1);
+  }
+  for (; pix < P; pix += stride) {
+    const int64_t off = pix * C + cg * 8;
+    body(ld_stream16(dy + off), ld_stream16(x + off));
   }
   block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
 }
@@ -415,12 +467,12 @@ __global__ void __launch_bounds__(256) bn_bwd_nores_apply_kernel(
   }
   __syncthreads();
   const int groups = C / 8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto body = [&](int64_t i, const uint4& ug, const uint4& ux) {
     const int cg = int(i % groups);
     float g[8], xv[8];
-    unpack8(ld_stream16(dy + i * 8), g);
-    unpack8(ld_stream16(x + i * 8), xv);
+    unpack8(ug, g);
+    unpack8(ux, xv);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int ch = cg * 8 + c;
@@ -428,7 +480,15 @@ __global__ void __launch_bounds__(256) bn_bwd_nores_apply_kernel(
       g[c] = fmaf(s_a[ch], gz, fmaf(s_b[ch], xv[c], s_c[ch]));
     }
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(g);
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {
+    const uint4 g0 = ld_stream16(dy + i * 8), x0 = ld_stream16(x + i * 8);
+    const uint4 g1 = ld_stream16(dy + (i + stride) * 8), x1 = ld_stream16(x + (i + stride) * 8);
+    body(i, g0, x0);
+    body(i + stride, g1, x1);
   }
+  for (; i < nvec; i += stride) body(i, ld_stream16(dy + i * 8), ld_stream16(x + i * 8));
 }
 
 // ------------------------------------------------------------------------------------------

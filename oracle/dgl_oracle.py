@@ -161,12 +161,36 @@ class _RoundF(torch.autograd.Function):
         return g
 
 
+class _Force(torch.autograd.Function):
+    """Teacher forcing: the forward value is REPLACED by a recorded tensor (the activation the CUDA path
+    stored in bf16); the gradient passes straight through, rounded to bf16 like the CUDA path stores it.
+    With every rounding point forced, ReLU masks / max-pool arg-maxes / BN statistics of the oracle are
+    exactly those of the CUDA forward, so what remains is a test of the backward kernels alone."""
+
+    @staticmethod
+    def forward(ctx, x, forced):
+        assert forced.shape == x.shape, (forced.shape, x.shape)
+        return forced.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32), None
+
+
+FORCED = []  # activations consumed in call order by _qa when quantize == "forced" (tests/ only)
+
+
 def _qa(x, quantize):
-    return _RoundFB.apply(x) if quantize == "bf16" else x
+    if quantize == "bf16":
+        return _RoundFB.apply(x)
+    if quantize == "forced":
+        t = FORCED.pop(0)
+        return _RoundFB.apply(x) if t is None else _Force.apply(x, t)
+    return x
 
 
 def _qw(w, quantize):
-    return _RoundF.apply(w) if quantize == "bf16" else w
+    return _RoundF.apply(w) if quantize in ("bf16", "forced") else w
 
 
 # ----------------------------------------------------------------------------------------------
