@@ -63,11 +63,26 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler, wr
             totals[2] += r[2]
         del pending[:]
 
-    for step_i, (spec, image, label) in enumerate(dataloader):
-        st = _get_step(args, model, optimizer, spec, image)
+    # one batch of look-ahead: the H2D copy of batch k+1 (copy stream) overlaps the kernels of step k
+    it = iter(dataloader)
+    nxt = next(it, None)
+    st = None
+    if nxt is not None:
+        st = _get_step(args, model, optimizer, nxt[0], nxt[1])
+        st.prefetch(*nxt)
+    step_i = -1
+    while nxt is not None:
+        step_i += 1
+        spec, image, label = nxt
         if hist is None:
             hist = torch.zeros(LOG_EVERY, 8, device=st.device)
-        stats = st.step(spec, image, label, lr=optimizer.param_groups[0]['lr'])
+        stats = st.step(lr=optimizer.param_groups[0]['lr'])
+        nxt = next(it, None)
+        if nxt is not None:
+            st2 = _get_step(args, model, optimizer, nxt[0], nxt[1])
+            if st2 is not st:  # geometry changed (last partial batch without drop_last): new engine
+                st = st2
+            st.prefetch(*nxt)
         hist[len(pending)].copy_(stats)
         pending.append(step_i)
         nsteps += 1
