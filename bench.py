@@ -135,9 +135,10 @@ def run_reference(a):
 
 
 def workload_config(a, batch_per_gpu, n):
-    return {"workload": "%s-shape DGL step, ResNet-18 audio+visual, %sFusion_DGL, batch %d per GPU x %d GPU, "
+    head = {"concat": "ConcatFusion_DGL", "sum": "SumFusion_DGL", "film": "FiLM_DGL", "gated": "GatedFusion_DGL"}
+    return {"workload": "%s-shape DGL step, ResNet-18 audio+visual, %s, batch %d per GPU x %d GPU, "
                         "synthetic" % ("CREMA-D" if a.dataset == "CREMAD" else a.dataset,
-                                       a.fusion.capitalize(), batch_per_gpu, n),
+                                       head.get(a.fusion, a.fusion), batch_per_gpu, n),
             "global_batch": batch_per_gpu * n, "parallelism": "dp%d" % n,
             "l2": "per-step inputs (%.0f MB) and activations (GBs) exceed the 126 MB L2; no flush needed"
                   % (batch_per_gpu * (257 * 188 + 3 * 3 * 224 * 224) * 4 / 1e6)}
@@ -164,7 +165,8 @@ def run_gpu(a):
     dev = torch.device("cuda", local)
     pg = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         pg = dist.group.WORLD
     n_cls = {"CREMAD": 6, "KineticSound": 34, "VGGSound": 309}[a.dataset]
     Fq, Tt, T, H, W = SHAPES[a.dataset]
@@ -253,8 +255,11 @@ def run_gpu(a):
             "final_losses": {"Lf": stats[0], "La": stats[1], "Lv": stats[2]},
             "wall_ms_per_step": wall_ms / a.steps}
 
-    if rank == 0 and not a.no_roofline:
-        line["roofline"], line["kernel_breakdown"] = roofline_pass(step, torch, ops, B)
+    if not a.no_roofline:
+        # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports it
+        roof, breakdown = roofline_pass(step, torch, ops, B)
+        if rank == 0:
+            line["roofline"], line["kernel_breakdown"] = roof, breakdown
     if world > 1:
         dist.barrier()
     if rank == 0:
