@@ -96,12 +96,19 @@ def main(argv=None):
         raise ValueError('Incorrect optimizer: {}'.format(args.optimizer))
     scheduler = optim.lr_scheduler.MultiStepLR(optimizer, eval(args.lr_decay_step), args.lr_decay_ratio)
 
-    if args.audio_path != 'synthetic':
-        raise NotImplementedError("this environment ships no datasets: pass --audio_path synthetic, or plug the "
-                                  "reference's dataset classes (same (spec, images, label) contract) in here")
+    if args.audio_path not in ('synthetic', 'synthetic_exact'):
+        raise NotImplementedError("this environment ships no datasets: pass --audio_path synthetic (random tensors) "
+                                  "or synthetic_exact (the reference's per-item random-draw order on seeded images), "
+                                  "or plug the reference's dataset classes (same (spec, images, label) contract) in")
     n = args.synthetic_len or None
-    train_dataset = SyntheticAV(args, 'train', n)
-    test_dataset = SyntheticAV(args, 'test', n and max(n // 8, args.batch_size))
+    if args.audio_path == 'synthetic_exact':
+        from gdl_b200.synthetic import SyntheticCramed, SyntheticKS
+        cls = SyntheticCramed if args.dataset == 'CREMAD' else SyntheticKS
+        train_dataset = cls(args, 'train', n or 6698)
+        test_dataset = cls(args, 'test', (n and max(n // 8, args.batch_size)) or 744)
+    else:
+        train_dataset = SyntheticAV(args, 'train', n)
+        test_dataset = SyntheticAV(args, 'test', n and max(n // 8, args.batch_size))
     per_rank = args.batch_size // world
     sampler = torch.utils.data.distributed.DistributedSampler(train_dataset, shuffle=True) if world > 1 else None
     train_loader = DataLoader(train_dataset, batch_size=per_rank, shuffle=sampler is None, sampler=sampler,

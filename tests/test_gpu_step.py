@@ -213,6 +213,50 @@ def test_kinetics_shape_head_width():
     assert step.logits.shape == (3, 4, 34)
 
 
+def test_prefetch_pipeline_equals_synchronous_inputs():
+    """prefetch()/step() (H2D on the copy stream into the alternate staging set) must be bit-identical to
+    step(spec, image, label), in eager and CUDA-graph mode."""
+    from oracle.synth import make_batch
+    outs = []
+    batches = [make_batch(4, 6, "tiny", seed=1 + s) for s in range(4)]
+    for mode in ("sync", "prefetch", "prefetch_graph"):
+        model, step = build("concat", "CREMAD", 4, "tiny", use_graph=(mode == "prefetch_graph"))
+        if mode == "sync":
+            for b in batches:
+                step.step(*[t.cuda() for t in b])
+        else:
+            pinned = [[t.pin_memory() for t in b] for b in batches]
+            step.prefetch(*pinned[0])
+            for i in range(len(pinned)):
+                step.step()
+                if i + 1 < len(pinned):
+                    step.prefetch(*pinned[i + 1])
+                step.read_stats()
+        torch.cuda.synchronize()
+        outs.append((step.stats.clone(), step.arena.param.clone()))
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1])
+
+
+def test_vggsound_head_width_309():
+    """VGGSound: 309 classes (reference basic_model.py:20), the widest fused concat head."""
+    from oracle import dgl_oracle as O
+    from oracle.synth import SHAPES, make_batch
+    SHAPES.setdefault("vgg_tiny", SHAPES["tiny"])
+    model, step = build("concat", "VGGSound", 4, "tiny", lr=0.002)
+    batch = make_batch(4, 309, "tiny", seed=1)
+    step.step(*[t.cuda() for t in batch])
+    got = step.read_stats()
+    sd = O.init_state("concat", "VGGSound", 0)
+    ref = O.dgl_step(sd, {}, *batch, fusion="concat", lr=0.002)
+    for g, r in zip(got[:3], ref["losses"]):
+        assert abs(g - r) <= 2e-2 * abs(r), (got[:3], ref["losses"])
+    assert step.logits.shape == (3, 4, 309)
+    names = dict(model.named_parameters())
+    for k in ("fusion_module.fc_out.weight", "fusion_module.fc_out.bias"):
+        assert cos(names[k].grad.detach().float().cpu(), ref["grads"][k]) > 0.995, k
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
