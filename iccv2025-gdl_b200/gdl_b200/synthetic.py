@@ -13,7 +13,7 @@ everything that consumes random numbers is kept exactly as the reference does it
 
 so that, given the same seeds, the crop offsets / flips / audio offsets are bit-identical to the reference's
 (tests/test_cpu_sampling.py compares against the reference classes with their file I/O mocked, and against
-golden digests where /root/reference is not available).  Sampler and worker seeding are torch's own
+golden digests where the reference tree is not available).  Sampler and worker seeding are torch's own
 DataLoader, used unchanged by main_dgl.py.
 
 `SyntheticAV` is the light-weight variant (pre-normalised random tensors, no PIL work) used for throughput runs.
