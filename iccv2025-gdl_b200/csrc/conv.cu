@@ -543,7 +543,8 @@ int try_conv3x3_halo(int N, int H, int W, int Cs, int Cd, const void* src, const
 // conv_flat.cu
 int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t sH, int64_t sN, const void* src,
                   const void* wt, int64_t wt_rows, int64_t wt_k, void* dst, int Hd, int Wd, int Cd,
-                  const void* add_src, int add_mode, cudaStream_t s);
+                  const void* add_src, int add_mode, cudaStream_t s, float* stats = nullptr,
+                  int* stats_rows = nullptr);
 
 // Which TMA kernel serves a 3x3/s1 convolution.  Measured at the bench geometry (tools/conv_bench.py) the
 // flat-window kernel beats the 16x8-tile halo kernel on every layer (1.1x at 56x56 ... 2.1x at 7x7), so it
@@ -649,15 +650,16 @@ extern "C" int gdl_conv_pack_weights(const gdl_conv_desc* d, int ci_real, const 
   return GDL_OK;
 }
 
-extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
-                            gdl_stream_t s) {
+static int conv_fwd_impl(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y, float* stats,
+                         int* stats_rows, gdl_stream_t s) {
   GDL_REQUIRE(desc_ok(d), "gdl_conv_fwd: bad descriptor");
   GDL_REQUIRE(x && w_packed && y, "gdl_conv_fwd: null pointer");
+  if (stats_rows) *stats_rows = 0;
   if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1 && d->Ci % 64 == 0) {
     if (prefer_flat_s1(d->Hi, d->Wi)) {
       int rc = try_conv_flat(0, d->N, d->Hi, d->Wi, d->Ci, d->Ci, (int64_t)d->Wi * d->Ci,
                              (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y, d->Ho, d->Wo,
-                             d->Co, nullptr, 0, (cudaStream_t)s);
+                             d->Co, nullptr, 0, (cudaStream_t)s, stats, stats_rows);
       if (rc != 0) return rc < 0 ? rc : GDL_OK;
     }
     int rc = try_conv3x3_halo(d->N, d->Hi, d->Wi, d->Ci, d->Co, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y,
@@ -668,14 +670,14 @@ extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w
     // stride 2: the four parity planes of x are stride-1 sources on the output grid
     int rc = try_conv_flat(4, d->N, d->Ho, d->Wo, d->Ci, d->Ci, (int64_t)d->Wi * d->Ci,
                            (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y, d->Ho, d->Wo,
-                           d->Co, nullptr, 0, (cudaStream_t)s);
+                           d->Co, nullptr, 0, (cudaStream_t)s, stats, stats_rows);
     if (rc != 0) return rc < 0 ? rc : GDL_OK;
   }
   if (d->R == 1 && d->S == 1 && d->pad == 0 && d->Ci % 64 == 0 && d->Ci <= 128 && flat_policy() != 0) {
     // 1x1 (stride 1 or 2): a single tap over the strided view x[:, ::stride, ::stride, :]
     int rc = try_conv_flat(3, d->N, d->Ho, d->Wo, d->Ci, (int64_t)d->stride * d->Ci,
                            (int64_t)d->stride * d->Wi * d->Ci, (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co,
-                           (int64_t)d->Ci, y, d->Ho, d->Wo, d->Co, nullptr, 0, (cudaStream_t)s);
+                           (int64_t)d->Ci, y, d->Ho, d->Wo, d->Co, nullptr, 0, (cudaStream_t)s, stats, stats_rows);
     if (rc != 0) return rc < 0 ? rc : GDL_OK;
   }
   ConvParams p{};
@@ -694,6 +696,17 @@ extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w
   p.K = packed_k(d);
   p.KB = p.K / 64;
   return run_igemm(p, (cudaStream_t)s);
+}
+
+extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
+                            gdl_stream_t s) {
+  return conv_fwd_impl(d, x, w_packed, y, nullptr, nullptr, s);
+}
+
+extern "C" int gdl_conv_fwd_stats(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
+                                  float* bn_partial, int* bn_partial_rows, gdl_stream_t s) {
+  GDL_REQUIRE(bn_partial && bn_partial_rows, "gdl_conv_fwd_stats: null pointer");
+  return conv_fwd_impl(d, x, w_packed, y, bn_partial, bn_partial_rows, s);
 }
 
 extern "C" int gdl_conv_dgrad(const gdl_conv_desc* d, const void* dy, const void* w_packed_T,

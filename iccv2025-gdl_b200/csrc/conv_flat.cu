@@ -41,6 +41,7 @@ struct FlatParams {
   CUtensorMap tm_w;  // {K, rows} packed weights, box {64, BN}
   bf16* dst;
   const bf16* add_src;
+  float* stats;  // optional [gridDim.x * 4 epilogue warps][2][Cd]: per-warp sum / sum of squares of the bf16 outputs
   int add_mode;  // 0 none; 1 add_src has dst's shape; 2 add_src lives on the source grid (parity class (0,0) only)
   int N, Hs, Ws, Cs;
   int Hd, Wd, Cd;
@@ -64,7 +65,7 @@ __device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
   return (a - q * b < 0) ? q - 1 : q;
 }
 
-template <int BN, int MT, int WST>
+template <int BN, int MT, int WST, bool STATS>
 __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid_constant__ FlatParams p) {
   constexpr int W_BYTES = BN * 128;
   constexpr int TM = MT * 128;
@@ -215,6 +216,30 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
     // on the accumulator, one tile ahead, so their DRAM latency hides behind the MMAs instead of stalling the
     // TMEM drain (measured: 0.45 -> 0.25 ms on the 56x56 C64 dgrads).
     constexpr int NV = BN / 8;  // 16-byte vectors per output row
+    // Optional BatchNorm statistics of the output (reference backbone.py:45,48 train-mode BN): per 32-column
+    // chunk the 32 rows of a warp are reduced with a transposing shuffle butterfly (31 shuffles per statistic)
+    // so that lane l ends up with the column sum of channel c0+l; the per-warp sums accumulate in registers
+    // over the CTA's tiles and are flushed to the warp's private slot when the channel tile changes.
+    constexpr int NCH = BN / 32;
+    const int lane = tid & 31;
+    float st_sum[NCH], st_sq[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) st_sum[c] = st_sq[c] = 0.f;
+    float* st_slot = (STATS && p.stats) ? p.stats + (size_t)(blockIdx.x * 4 + warp) * 2 * p.Cd : nullptr;
+    if (st_slot != nullptr)
+      for (int c = lane; c < 2 * p.Cd; c += 32) st_slot[c] = 0.f;
+    int st_nt = -1;
+    auto st_flush = [&]() {
+      if (st_slot == nullptr || st_nt < 0) return;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = st_nt * BN + c * 32 + lane;
+        st_slot[ch] += st_sum[c];
+        st_slot[p.Cd + ch] += st_sq[c];
+        st_sum[c] = st_sq[c] = 0.f;
+      }
+    };
     int it = 0;
     for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++it) {
       const int cls = item / per_class;
@@ -223,6 +248,10 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int q0 = (rem - nt * p.mtiles) * TM;
       const int n0 = nt * BN;
       const int acc = it & 1;
+      if (STATS && nt != st_nt) {
+        st_flush();
+        st_nt = nt;
+      }
       bf16* outp[MT];
       const bf16* addp[MT];
       bool validj[MT];
@@ -284,6 +313,29 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
               st_global32(outp[j] + c0 + g * 8, o[0], o[1]);
             }
           }
+          if (STATS && st_slot != nullptr) {
+            // statistics of what BatchNorm will read: the bf16-rounded outputs (zero for pad rows)
+            float xs[32], xq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = validj[j] ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[i]))) : 0.f;
+              xs[i] = v;
+              xq[i] = v * v;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float ss = upper ? xs[i] : xs[i + off], ks = upper ? xs[i + off] : xs[i];
+                const float sq = upper ? xq[i] : xq[i + off], kq = upper ? xq[i + off] : xq[i];
+                xs[i] = ks + __shfl_xor_sync(0xffffffffu, ss, off);
+                xq[i] = kq + __shfl_xor_sync(0xffffffffu, sq, off);
+              }
+            }
+            st_sum[c0 / 32] += xs[0];
+            st_sq[c0 / 32] += xq[0];
+          }
         }
         if (p.add_mode != 0 && j + 1 < MT) {
 #pragma unroll
@@ -293,6 +345,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (STATS) st_flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -317,18 +370,26 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   p.items_total = p.nclass * p.ntiles * p.mtiles;
   int total = ws * p.win_stage_bytes + fixed + 1024;
   if (total < 116 * 1024) total = 116 * 1024;  // one CTA per SM: the kernel relies on TMEM base 0
-  static int attr_set = 0;
-  if (attr_set < total) {
-    cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_flat)");
-    attr_set = 227 * 1024;
+    attr_set = true;
   }
   int grid = p.items_total < kNumSMs ? p.items_total : kNumSMs;
-  conv_flat_kernel<BN, MT, WST><<<grid, kFlatThreads, total, s>>>(p);
+  if (p.stats != nullptr)
+    conv_flat_kernel<BN, MT, WST, true><<<grid, kFlatThreads, total, s>>>(p);
+  else
+    conv_flat_kernel<BN, MT, WST, false><<<grid, kFlatThreads, total, s>>>(p);
   GDL_CHECK_LAUNCH("conv_flat_kernel");
   return 1;
 }
+
+int g_fused_stats_min_k = 1 << 30;
 
 static int env_int3(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -342,7 +403,7 @@ static int env_int3(const char* name, int dflt) {
 // wt is [Cd rows][K] bf16 with k = tap*Cs + c.  Returns 1 when launched, 0 when not eligible, <0 on error.
 int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t sH, int64_t sN, const void* src,
                   const void* wt, int64_t wt_rows, int64_t wt_k, void* dst, int Hd, int Wd, int Cd,
-                  const void* add_src, int add_mode, cudaStream_t s) {
+                  const void* add_src, int add_mode, cudaStream_t s, float* stats, int* stats_rows) {
   static const int mt_force = env_int3("GDL_FLAT_MT", 0);
   if (Cs % 64 != 0 || Cd % 64 != 0) return 0;
   const int P = Ws + 1;
@@ -355,6 +416,12 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   p.dst = (bf16*)dst;
   p.add_src = (const bf16*)add_src;
   p.add_mode = add_mode;
+  // The statistics butterfly costs ~1.3k instructions per 128x128 tile in the epilogue warps: it hides behind the
+  // MMAs only when the reduction is long (measured: +2-8 % kernel time for K >= 1152, +30 % at K = 576, 2.4x for
+  // 1x1); against the separate statistics kernel it came out even on the whole step, so it is off by default
+  // (gdl_set_fused_stats_min_k(K) enables it for convolutions with K >= that value; tests/ cover both paths).
+  if (stats != nullptr && wt_k < g_fused_stats_min_k) stats = nullptr;
+  p.stats = stats;
   p.N = N; p.Hs = Hs; p.Ws = Ws; p.Cs = Cs;
   p.Hd = Hd; p.Wd = Wd; p.Cd = Cd;
   p.P = P; p.IS = (int)IS;
@@ -459,7 +526,18 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
     if (mt == 2) rc = launch_flat<64, 2, 6>(p, Q, s);
     if (rc == 0) rc = launch_flat<64, 1, 6>(p, Q, s);
   }
+  if (rc > 0 && stats_rows != nullptr && stats != nullptr) {
+    // one partial row per epilogue warp of every CTA (launch_flat's grid)
+    const int grid = p.items_total < kNumSMs ? p.items_total : kNumSMs;
+    *stats_rows = grid * 4;
+  }
   return rc;
 }
 
 }  // namespace gdl
+
+extern "C" int gdl_set_fused_stats_min_k(int k) {
+  int old = gdl::g_fused_stats_min_k;
+  gdl::g_fused_stats_min_k = k < 0 ? (1 << 30) : k;
+  return old;
+}

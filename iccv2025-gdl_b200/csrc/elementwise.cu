@@ -778,6 +778,18 @@ extern "C" int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, con
   return GDL_OK;
 }
 
+extern "C" int gdl_bn_stats_finalize(const float* partial, int rows, int64_t P, int C, const float* gamma,
+                                     const float* beta, float eps, float momentum, float* running_mean,
+                                     float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                                     gdl_stream_t s) {
+  GDL_REQUIRE(chan_ok(C) && P > 0 && rows > 0, "gdl_bn_stats_finalize: bad shape");
+  GDL_REQUIRE(partial && gamma && beta && mean && invstd && scale && shift, "gdl_bn_stats_finalize: null pointer");
+  bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(
+      partial, rows, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
+  GDL_CHECK_LAUNCH("bn_stats_finalize_kernel");
+  return GDL_OK;
+}
+
 extern "C" int gdl_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
                                   const float* running_var, float eps, float* scale, float* shift, int C,
                                   gdl_stream_t s) {

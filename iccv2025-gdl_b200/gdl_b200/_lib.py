@@ -48,6 +48,9 @@ SIGNATURES = {
     "gdl_layout_ncthw_to_nhwc8": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "gdl_bn_partial_floats": (_l, [_l, _i]),
     "gdl_bn_stats": (_i, [_p, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "gdl_set_fused_stats_min_k": (_i, [_i]),
+    "gdl_conv_fwd_stats": (_i, [_p, _p, _p, _p, _p, _p, _p]),
+    "gdl_bn_stats_finalize": (_i, [_p, _i, _l, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "gdl_bn_eval_affine": (_i, [_p, _p, _p, _p, _f, _p, _p, _i, _p]),
     "gdl_bn_apply": (_i, [_p, _p, _p, _l, _i, _p, _p, _i, _p]),
     "gdl_bn_bwd": (_i, [_p, _p, _p, _p, _p, _l, _i, _p, _p, _p, _p, _p, _p, _i, _p]),

@@ -68,13 +68,20 @@ class _ConvBN:
         ops.conv_pack_weights(self.d, self.ci_real, self.conv.weight.data, self.wp, self.wT)
 
     def forward(self, eng, inp, res=None, training=True):
-        ops.conv_fwd(self.d, inp, self.wp, self.x, self.ci_real)
         bn = self.bn
         if training:
-            ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
-                         bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
-                         self.scale, self.shift)
+            # batch statistics come out of the conv epilogue where the kernel supports it (no extra pass over x)
+            rows = ops.conv_fwd_stats(self.d, inp, self.wp, self.x, eng.bn_partial, self.ci_real)
+            if rows:
+                ops.bn_stats_finalize(eng.bn_partial, rows, self.P, self.C, bn.weight.data, bn.bias.data, bn.eps,
+                                      bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                                      self.scale, self.shift)
+            else:
+                ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
+                             bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                             self.scale, self.shift)
         else:
+            ops.conv_fwd(self.d, inp, self.wp, self.x, self.ci_real)
             ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
                                self.scale, self.shift, self.C)
         ops.bn_apply(self.x, res, self.y, self.P, self.C, self.scale, self.shift, self.relu)

@@ -105,6 +105,29 @@ def conv_fwd(d, x, w_packed, y, ci_real=None):
           "gdl_conv_fwd")
 
 
+@_op("conv_fwd", 1, lambda d, x, w, y, partial, ci_real=None: ("flops", conv_flops(d, ci_real), _dstr(d)))
+def conv_fwd_stats(d, x, w_packed, y, bn_partial, ci_real=None):
+    """conv forward with the BatchNorm partial sums of y accumulated in the epilogue; returns the number of
+    partial rows written (0: this shape has no fused statistics, run bn_stats on y)."""
+    rows = C.c_int(0)
+    check(_lib.load().gdl_conv_fwd_stats(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(y), _ptr(bn_partial),
+                                         C.byref(rows), _stream()), "gdl_conv_fwd_stats")
+    return rows.value
+
+
+def set_fused_stats_min_k(k):
+    """Enable the conv-epilogue BN statistics for convolutions with R*S*Ci >= k (k < 0: library default = off)."""
+    return int(_lib.load().gdl_set_fused_stats_min_k(int(k)))
+
+
+@_op("bn_stats", 1)
+def bn_stats_finalize(partial, rows, P, Cc, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd,
+                      scale, shift):
+    check(_lib.load().gdl_bn_stats_finalize(_ptr(partial), rows, P, Cc, _ptr(gamma), _ptr(beta), eps, momentum,
+                                            _ptr(running_mean), _ptr(running_var), _ptr(mean), _ptr(invstd),
+                                            _ptr(scale), _ptr(shift), _stream()), "gdl_bn_stats_finalize")
+
+
 @_op("conv_dgrad", 1, lambda d, *a, **k: ("flops", conv_flops(d), _dstr(d)))
 def conv_dgrad(d, dy, w_packed_T, dx, add_src=None, add_mode=0):
     check(_lib.load().gdl_conv_dgrad(C.byref(d), _ptr(dy), _ptr(w_packed_T), _ptr(dx),

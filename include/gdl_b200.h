@@ -63,6 +63,15 @@ int gdl_conv_pack_weights(const gdl_conv_desc* d, int ci_real, const float* w_oi
 /* y[N,Ho,Wo,Co] = conv(x[N,Hi,Wi,Ci], w).  Implicit GEMM, tcgen05 + TMEM accumulators. */
 int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
                  gdl_stream_t s);
+/* Same, and the BatchNorm statistics of y (reference backbone.py:45,48: train-mode BN follows every conv) are
+ * accumulated in the epilogue: bn_partial receives *bn_partial_rows rows of [2][Co] floats (per-warp sum and sum
+ * of squares of the bf16-rounded outputs) for gdl_bn_stats_finalize.  *bn_partial_rows == 0 means the shape took
+ * a path without the fused statistics (call gdl_bn_stats on y instead).  bn_partial: gdl_bn_partial_floats(). */
+int gdl_conv_fwd_stats(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
+                       float* bn_partial, int* bn_partial_rows, gdl_stream_t s);
+/* Fused statistics are used for convolutions with R*S*Ci >= k (default: never — on the bench geometry the
+ * epilogue cost equals what the separate kernel costs); k < 0 restores the default.  Returns the old value. */
+int gdl_set_fused_stats_min_k(int k);
 /* dx[N,Hi,Wi,Ci] = conv_transpose(dy, w) (+ add_src).  add_mode: 0 none, 1 add_src has the
  * shape of dx (residual gradient), 2 add_src is [N,ceil(Hi/2),ceil(Wi/2),Ci] and is added at
  * even (h,w) only (gradient of a 1x1 stride-2 downsample branch). */
@@ -102,6 +111,11 @@ int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, const float* g
                  const float* beta, float eps, float momentum, float* running_mean,
                  float* running_var, float* mean, float* invstd, float* scale, float* shift,
                  gdl_stream_t s);
+/* Second half of gdl_bn_stats for partial sums produced elsewhere (gdl_conv_fwd_stats): rows x [2][C]. */
+int gdl_bn_stats_finalize(const float* partial, int rows, int64_t P, int C, const float* gamma,
+                          const float* beta, float eps, float momentum, float* running_mean,
+                          float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                          gdl_stream_t s);
 /* Eval mode (reference model.eval() in valid(), main_dgl.py:186): scale/shift from the running stats. */
 int gdl_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, int C,

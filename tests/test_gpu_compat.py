@@ -97,9 +97,12 @@ def test_eval_forward_and_valid():
     spec, image, label = make_batch(4, 6, "tiny", seed=9)
     with torch.no_grad():
         out, oa, ov = model(spec.cuda().unsqueeze(1).float(), image.cuda().float())
-        ro, ra, rv = O.model_forward(sd, spec, image, "concat", training=False)
+        # eval-mode forward of the oracle on the SAME weights and running statistics (the drift of the two
+        # training trajectories is checked above; here only the eval kernels are under test)
+        sd_same = {k: v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu() for k, v in msd.items()}
+        ro, ra, rv = O.model_forward(sd_same, spec, image, "concat", training=False)
     for g, r in zip((out, oa, ov), (ro, ra, rv)):
-        assert (g.cpu() - r).abs().max().item() < 0.15 * (r.abs().max().item() + 1.0)
+        assert (g.cpu() - r).abs().max().item() < 0.05 * (r.abs().max().item() + 1.0)
     acc = valid(args, _Wrap(model), torch.device("cuda"), [(spec, image, label)])
     assert len(acc) == 3 and all(0.0 <= a <= 1.0 for a in acc)
     assert model.args.drop == 1  # the reference flips this flag back (main_dgl.py:221)

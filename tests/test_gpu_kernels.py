@@ -69,6 +69,44 @@ def test_conv_fwd(case):
     assert rel_err(nchw(y), ref) < 6e-3, rel_err(nchw(y), ref)
 
 
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_fused_bn_statistics(case):
+    """gdl_conv_fwd_stats: the partial sums from the conv epilogue give the same BN statistics as a
+    separate pass over the stored bf16 output."""
+    ops = _ops()
+    N, H, W, Ci, Co, R, stride, pad = case
+    xb, wb = _mk(*case)
+    d = ops.conv_desc(N, H, W, Ci, Co, R, R, stride, pad)
+    wp = torch.empty(Co, ops.conv_packed_k(d), device="cuda", dtype=torch.bfloat16)
+    ops.conv_pack_weights(d, Ci, wb, wp, None)
+    y = torch.empty(N, d.Ho, d.Wo, Co, device="cuda", dtype=torch.bfloat16)
+    P = N * d.Ho * d.Wo
+    partial = torch.full((ops.bn_partial_floats(P, Co),), float("nan"), device="cuda")
+    old = ops.set_fused_stats_min_k(0)
+    try:
+        rows = ops.conv_fwd_stats(d, nhwc(xb), wp, y, partial)
+    finally:
+        ops.set_fused_stats_min_k(old)
+    ref = F.conv2d(xb, wb, stride=stride, padding=pad)
+    assert rel_err(nchw(y), ref) < 6e-3
+    if rows == 0:
+        pytest.skip("shape served by a kernel without fused statistics")
+    gamma, beta = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    outs = []
+    for fused in (True, False):
+        rm, rv = torch.zeros(Co, device="cuda"), torch.ones(Co, device="cuda")
+        mean, invstd, scale, shift = (torch.empty(Co, device="cuda") for _ in range(4))
+        if fused:
+            ops.bn_stats_finalize(partial, rows, P, Co, gamma, beta, 1e-5, 0.1, rm, rv, mean, invstd, scale, shift)
+        else:
+            p2 = torch.empty_like(partial)
+            ops.bn_stats(y, P, Co, p2, gamma, beta, 1e-5, 0.1, rm, rv, mean, invstd, scale, shift)
+        outs.append((mean, invstd, scale, shift, rm, rv))
+    torch.cuda.synchronize()
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (a - b).abs().max()
+
+
 @pytest.mark.parametrize("ci_real,H,W", [(3, 37, 29), (1, 41, 30), (3, 224, 224)])
 def test_conv_fwd_stem(ci_real, H, W):
     ops = _ops()
