@@ -442,6 +442,33 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
   if (wT != nullptr && valid) wT[(size_t)ci * (R * S * Co) + (size_t)tap * Co + co] = b;
 }
 
+// Multi-tensor variant: one launch refreshes the bf16 shadows of a whole encoder (reference
+// main_dgl.py:154 optimizer.step() is followed by nothing — the shadows are this library's own state).
+__global__ void pack_weights_multi_kernel(const gdl_pack_entry* __restrict__ tab, int n, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;  // last entry with start <= idx
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tab[mid].start <= idx) lo = mid; else hi = mid - 1;
+    }
+    const gdl_pack_entry e = tab[lo];
+    const int64_t li = idx - e.start;
+    const int co = int(li / e.Kp), k = int(li - (int64_t)co * e.Kp);
+    const int tap = k / e.Ci, ci = k - tap * e.Ci;
+    float v = 0.f;
+    const bool valid = tap < e.R * e.S && ci < e.ci_real;
+    if (valid) {
+      const int r = tap / e.S, s2 = tap - r * e.S;
+      v = e.w[(((size_t)co * e.ci_real + ci) * e.R + r) * e.S + s2];
+    }
+    const bf16 b = __float2bfloat16_rn(v);
+    reinterpret_cast<bf16*>(e.wp)[li] = b;
+    if (e.wT != nullptr && valid)
+      reinterpret_cast<bf16*>(e.wT)[(size_t)ci * (e.R * e.S * e.Co) + (size_t)tap * e.Co + co] = b;
+  }
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                     int splits, int Kp, int Cd, int Ci, int ci_real, int R, int S) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (k, co), co fastest
@@ -696,6 +723,15 @@ static int conv_fwd_impl(const gdl_conv_desc* d, const void* x, const void* w_pa
   p.K = packed_k(d);
   p.KB = p.K / 64;
   return run_igemm(p, (cudaStream_t)s);
+}
+
+extern "C" int gdl_conv_pack_weights_multi(const gdl_pack_entry* table_dev, int n, int64_t total, gdl_stream_t s) {
+  GDL_REQUIRE(table_dev && n > 0 && total > 0, "gdl_conv_pack_weights_multi: bad arguments");
+  int64_t blocks = ceil_div64(total, 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  pack_weights_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(table_dev, n, total);
+  GDL_CHECK_LAUNCH("pack_weights_multi_kernel");
+  return GDL_OK;
 }
 
 extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,

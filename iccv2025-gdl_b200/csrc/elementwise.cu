@@ -436,12 +436,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
       acc[1][c] = fmaf(gz, (xv[c] - mu[c]) * is[c], acc[1][c]);
     }
   };
-  for (; pix + stride < P; pix += 2 * stride) {  // two pixels (four 16-byte loads) in flight per thread
-    const int64_t o0 = pix * C + cg * 8, o1 = (pix + stride) * C + cg * 8;
-    const uint4 g0 = ld_stream16(dy + o0), x0 = ld_stream16(x + o0);
-    const uint4 g1 = ld_stream16(dy + o1), x1 = ld_stream16(x + o1);
-    body(g0, x0);
-    body(g1, x1);
+  for (; pix + 3 * stride < P; pix += 4 * stride) {  // four pixels (eight 16-byte loads) in flight per thread
+    uint4 g[4], xx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t o = (pix + k * stride) * C + cg * 8;
+      g[k] = ld_stream16(dy + o);
+      xx[k] = ld_stream16(x + o);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) body(g[k], xx[k]);
   }
   for (; pix < P; pix += stride) {
     const int64_t off = pix * C + cg * 8;
@@ -482,11 +486,15 @@ __global__ void __launch_bounds__(256) bn_bwd_nores_apply_kernel(
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(g);
   };
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + stride < nvec; i += 2 * stride) {
-    const uint4 g0 = ld_stream16(dy + i * 8), x0 = ld_stream16(x + i * 8);
-    const uint4 g1 = ld_stream16(dy + (i + stride) * 8), x1 = ld_stream16(x + (i + stride) * 8);
-    body(i, g0, x0);
-    body(i + stride, g1, x1);
+  for (; i + 3 * stride < nvec; i += 4 * stride) {  // four vectors (eight loads) in flight per thread
+    uint4 g[4], xx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      g[k] = ld_stream16(dy + (i + k * stride) * 8);
+      xx[k] = ld_stream16(x + (i + k * stride) * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) body(i + k * stride, g[k], xx[k]);
   }
   for (; i < nvec; i += stride) body(i, ld_stream16(dy + i * 8), ld_stream16(x + i * 8));
 }

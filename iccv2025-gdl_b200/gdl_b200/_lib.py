@@ -16,6 +16,11 @@ class GdlError(RuntimeError):
     pass
 
 
+class PackEntry(C.Structure):  # mirrors gdl_pack_entry
+    _fields_ = [("w", C.c_void_p), ("wp", C.c_void_p), ("wT", C.c_void_p), ("Co", C.c_int32), ("Ci", C.c_int32),
+                ("ci_real", C.c_int32), ("R", C.c_int32), ("S", C.c_int32), ("Kp", C.c_int32), ("start", C.c_int64)]
+
+
 class ConvDesc(C.Structure):
     """Mirror of gdl_conv_desc."""
     _fields_ = [(n, C.c_int32) for n in
@@ -48,6 +53,7 @@ SIGNATURES = {
     "gdl_layout_ncthw_to_nhwc8": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "gdl_bn_partial_floats": (_l, [_l, _i]),
     "gdl_bn_stats": (_i, [_p, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "gdl_conv_pack_weights_multi": (_i, [_p, _i, _l, _p]),
     "gdl_set_fused_stats_min_k": (_i, [_i]),
     "gdl_conv_fwd_stats": (_i, [_p, _p, _p, _p, _p, _p, _p]),
     "gdl_bn_stats_finalize": (_i, [_p, _i, _l, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),

@@ -171,9 +171,16 @@ class EncoderEngine:
 
     # ------------------------------------------------------------------ weights
     def repack(self):
-        """Refresh the bf16 shadows from the fp32 masters (after every optimizer step)."""
-        for u in self.units:
-            u.repack()
+        """Refresh the bf16 shadows from the fp32 masters (after every optimizer step): one multi-tensor
+        launch for the 19 block convolutions + the stem's own packer."""
+        convs = [u for u in self.units if u is not self.stem]
+        key = tuple(u.conv.weight.data_ptr() for u in convs)
+        if getattr(self, "_pack_key", None) != key:  # the parameters moved (e.g. into the step's arena)
+            entries = [(u.conv.weight.data, u.wp, u.wT, u.C, u.d.Ci, u.ci_real, u.d.R, u.d.S, u.Kp) for u in convs]
+            self._pack_table = ops.make_pack_table(entries, self.device)
+            self._pack_key = key
+        self.stem.repack()
+        ops.conv_pack_weights_multi(*self._pack_table)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x16, training=True):

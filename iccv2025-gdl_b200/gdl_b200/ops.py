@@ -99,6 +99,24 @@ def conv_pack_weights(d, ci_real, w_oihw, w_packed, w_packed_T=None):
                                             _ptr(w_packed_T), _stream()), "gdl_conv_pack_weights")
 
 
+def make_pack_table(entries, device):
+    """entries: [(w_oihw, w_packed, w_packed_T or None, Co, Ci, ci_real, R, S, Kp)] -> (device table, n, total).
+    The table holds raw device addresses: rebuild it if any tensor is re-allocated."""
+    arr = (_lib.PackEntry * len(entries))()
+    start = 0
+    for e, (w, wp, wT, Co, Ci, ci_real, R, S, Kp) in zip(arr, entries):
+        e.w, e.wp, e.wT = w.data_ptr(), wp.data_ptr(), (wT.data_ptr() if wT is not None else None)
+        e.Co, e.Ci, e.ci_real, e.R, e.S, e.Kp, e.start = Co, Ci, ci_real, R, S, Kp, start
+        start += Co * Kp
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device), len(entries), start
+
+
+@_op("pack_weights", 1)
+def conv_pack_weights_multi(table, n, total):
+    check(_lib.load().gdl_conv_pack_weights_multi(_ptr(table), n, total, _stream()), "gdl_conv_pack_weights_multi")
+
+
 @_op("conv_fwd", 1, lambda d, x, w, y, ci_real=None: ("flops", conv_flops(d, ci_real), _dstr(d)))
 def conv_fwd(d, x, w_packed, y, ci_real=None):
     check(_lib.load().gdl_conv_fwd(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(y), _stream()),

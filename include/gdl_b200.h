@@ -60,6 +60,16 @@ int64_t gdl_conv_wgrad_workspace_bytes(const gdl_conv_desc* d);
  * bf16 transposed [Ci][R*S*Co] (k=(r,s,co)) for dgrad (wT may be NULL). */
 int gdl_conv_pack_weights(const gdl_conv_desc* d, int ci_real, const float* w_oihw,
                           void* w_packed, void* w_packed_T, gdl_stream_t s);
+/* The same for many convolutions in ONE launch: table_dev is a DEVICE array of n entries sorted by `start`
+ * (running sum of Co*Kp); total = sum of Co*Kp. */
+typedef struct {
+  const float* w; /* fp32 OIHW master */
+  void* wp;       /* bf16 [Co][Kp] */
+  void* wT;       /* bf16 [Ci][R*S*Co] or NULL */
+  int32_t Co, Ci, ci_real, R, S, Kp;
+  int64_t start;
+} gdl_pack_entry;
+int gdl_conv_pack_weights_multi(const gdl_pack_entry* table_dev, int n, int64_t total, gdl_stream_t s);
 /* y[N,Ho,Wo,Co] = conv(x[N,Hi,Wi,Ci], w).  Implicit GEMM, tcgen05 + TMEM accumulators. */
 int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
                  gdl_stream_t s);

@@ -107,6 +107,25 @@ def test_conv_fwd_fused_bn_statistics(case):
         assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (a - b).abs().max()
 
 
+def test_pack_weights_multi_equals_single():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(31)
+    entries, singles = [], []
+    for (Co, Ci, R) in ((64, 64, 3), (128, 64, 3), (128, 64, 1), (256, 256, 3), (512, 256, 1)):
+        d = ops.conv_desc(2, 8, 8, Ci, Co, R, R, 1, R // 2)
+        Kp = ops.conv_packed_k(d)
+        w = torch.randn(Co, Ci, R, R, device="cuda", generator=g)
+        wp1, wT1 = torch.zeros(Co, Kp, device="cuda", dtype=torch.bfloat16), torch.zeros(Ci, R * R * Co, device="cuda", dtype=torch.bfloat16)
+        ops.conv_pack_weights(d, Ci, w, wp1, wT1)
+        wp2, wT2 = torch.zeros_like(wp1), torch.zeros_like(wT1)
+        entries.append((w, wp2, wT2, Co, Ci, Ci, R, R, Kp))
+        singles.append((wp1, wT1, wp2, wT2))
+    ops.conv_pack_weights_multi(*ops.make_pack_table(entries, torch.device("cuda")))
+    torch.cuda.synchronize()
+    for wp1, wT1, wp2, wT2 in singles:
+        assert torch.equal(wp1, wp2) and torch.equal(wT1, wT2)
+
+
 @pytest.mark.parametrize("ci_real,H,W", [(3, 37, 29), (1, 41, 30), (3, 224, 224)])
 def test_conv_fwd_stem(ci_real, H, W):
     ops = _ops()
