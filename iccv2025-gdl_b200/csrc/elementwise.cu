@@ -510,7 +510,8 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 
 __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(
     const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-    bf16* __restrict__ y, uint8_t* __restrict__ amax, int N, int H, int W, int C, int Ho, int Wo) {
+    bf16* __restrict__ y, uint8_t* __restrict__ amax, bf16* __restrict__ xmax, int N, int H, int W, int C, int Ho,
+    int Wo) {
   __shared__ float s_scale[512], s_shift[512];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     s_scale[c] = scale[c];
@@ -527,13 +528,14 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(
     int64_t t = pix / Wo;
     int ho = int(t % Ho);
     int n = int(t / Ho);
-    float sc[8], sh[8], best[8];
+    float sc[8], sh[8], best[8], bx[8];
     int bi[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       sc[c] = s_scale[cg * 8 + c];
       sh[c] = s_shift[cg * 8 + c];
       best[c] = -INFINITY;
+      bx[c] = 0.f;
       bi[c] = 0;
     }
 #pragma unroll
@@ -552,12 +554,16 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(
           const float v = bf16_round(fmaxf(fmaf(f[c], sc[c], sh[c]), 0.f));
           if (v > best[c]) {  // strict: the first maximum in scan order wins (ATen rule)
             best[c] = v;
+            bx[c] = f[c];
             bi[c] = r * 3 + s;
           }
         }
       }
     }
     *reinterpret_cast<uint4*>(y + pix * C + cg * 8) = pack8(best);
+    // the conv output AT the arg-max (exact: f came from bf16): lets the backward form the BN sums on the
+    // pooled grid (4x fewer elements) instead of a pass over the whole stem output
+    if (xmax != nullptr) *reinterpret_cast<uint4*>(xmax + pix * C + cg * 8) = pack8(bx);
     uint2 packed;
     packed.x = uint32_t(bi[0]) | (uint32_t(bi[1]) << 8) | (uint32_t(bi[2]) << 16) | (uint32_t(bi[3]) << 24);
     packed.y = uint32_t(bi[4]) | (uint32_t(bi[5]) << 8) | (uint32_t(bi[6]) << 16) | (uint32_t(bi[7]) << 24);
@@ -861,28 +867,39 @@ extern "C" int gdl_bn_bwd_nores(const void* dy, const void* x, void* dx, int64_t
 }
 
 extern "C" int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const float* shift, void* y,
-                                       uint8_t* argmax, int N, int H, int W, int C, int Ho, int Wo,
+                                       uint8_t* argmax, void* xmax, int N, int H, int W, int C, int Ho, int Wo,
                                        gdl_stream_t s) {
   GDL_REQUIRE(x && scale && shift && y && argmax, "gdl_bn_relu_maxpool_fwd: null pointer");
   GDL_REQUIRE(chan_ok(C) && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_bn_relu_maxpool_fwd: bad shape");
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
   bn_relu_maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(
-      (const bf16*)x, scale, shift, (bf16*)y, argmax, N, H, W, C, Ho, Wo);
+      (const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H, W, C, Ho, Wo);
   GDL_CHECK_LAUNCH("bn_relu_maxpool_fwd_kernel");
   return GDL_OK;
 }
 
-extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax, const void* x, void* dx, int N,
-                                       int H, int W, int C, int Ho, int Wo, const float* gamma, const float* mean,
+extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax, const void* xmax, const void* x,
+                                       void* dx, int N, int H, int W, int C, int Ho, int Wo, const float* gamma,
+                                       const float* mean,
                                        const float* invstd, const float* scale, const float* shift, float* partial,
                                        float* dgamma, float* dbeta, gdl_stream_t s) {
   GDL_REQUIRE(gpool && argmax && x && dx && gamma && mean && invstd && scale && shift && partial && dgamma && dbeta,
               "gdl_bn_relu_maxpool_bwd: null pointer");
   GDL_REQUIRE(chan_ok(C) && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_bn_relu_maxpool_bwd: bad shape");
   const int64_t P = (int64_t)N * H * W;
-  int nblk = bn_blocks((int64_t)N * Ho * Wo * 4, C);
-  bn_relu_maxpool_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
-      (const bf16*)gpool, argmax, (const bf16*)x, N, H, W, C, Ho, Wo, mean, invstd, scale, shift, partial);
+  int nblk;
+  if (xmax != nullptr) {
+    // sums of dz and dz*xhat over the POOLED grid: each window contributes its gradient at its arg-max pixel,
+    // whose conv output the forward saved — the no-residual BN reduce kernel on (gpool, xmax)
+    const int64_t Pp = (int64_t)N * Ho * Wo;
+    nblk = bn_blocks(Pp, C);
+    bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)gpool, (const bf16*)xmax, Pp, C,
+                                                                        mean, invstd, scale, shift, partial);
+  } else {
+    nblk = bn_blocks((int64_t)N * Ho * Wo * 4, C);
+    bn_relu_maxpool_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
+        (const bf16*)gpool, argmax, (const bf16*)x, N, H, W, C, Ho, Wo, mean, invstd, scale, shift, partial);
+  }
   GDL_CHECK_LAUNCH("bn_relu_maxpool_bwd_reduce_kernel");
   bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");

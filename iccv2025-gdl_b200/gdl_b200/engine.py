@@ -123,8 +123,8 @@ class _StemBN(_ConvBN):
             ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
                                self.scale, self.shift, self.C)
         # BN-apply + ReLU + MaxPool(3,2,1) in one pass (reference backbone.py:104-106)
-        ops.bn_relu_maxpool_fwd(self.x, self.scale, self.shift, eng.pool_y, eng.pool_idx, self.N, self.Ho, self.Wo,
-                                64, eng.Hp, eng.Wp)
+        ops.bn_relu_maxpool_fwd(self.x, self.scale, self.shift, eng.pool_y, eng.pool_idx,
+                                eng.pool_xmax if training else None, self.N, self.Ho, self.Wo, 64, eng.Hp, eng.Wp)
         return eng.pool_y
 
 
@@ -146,6 +146,7 @@ class EncoderEngine:
         self.Hp, self.Wp = (H1 - 1) // 2 + 1, (W1 - 1) // 2 + 1
         self.pool_y = torch.empty(N, self.Hp, self.Wp, 64, device=device, dtype=torch.bfloat16)
         self.pool_idx = torch.empty(N, self.Hp, self.Wp, 64, device=device, dtype=torch.uint8)
+        self.pool_xmax = torch.empty(N, self.Hp, self.Wp, 64, device=device, dtype=torch.bfloat16)  # conv out at arg-max
         h, w, cin = self.Hp, self.Wp, 64
         for li in range(1, 5):
             layer = getattr(net, "layer%d" % li)
@@ -273,8 +274,8 @@ class EncoderEngine:
                 ops.conv_dgrad(u1.d, b["d_c1"], u1.wT, b["g_u"], g_out, 1)
         s = self.stem
         # max-pool scatter + ReLU mask + BN backward in one pair of passes over the stem conv output
-        ops.bn_relu_maxpool_bwd(self.g_pool, self.pool_idx, s.x, self.d_c0, self.N, s.d.Ho, s.d.Wo, 64, self.Hp,
-                                self.Wp, s.bn.weight.data, s.mean, s.invstd, s.scale, s.shift, self.bn_partial,
+        ops.bn_relu_maxpool_bwd(self.g_pool, self.pool_idx, self.pool_xmax, s.x, self.d_c0, self.N, s.d.Ho, s.d.Wo,
+                                64, self.Hp, self.Wp, s.bn.weight.data, s.mean, s.invstd, s.scale, s.shift, self.bn_partial,
                                 self._grad(s.bn.weight), self._grad(s.bn.bias))
         ops.stem_wgrad(x16, self.d_c0, self._grad(s.conv.weight), s.ci_real, self.N, self.H, self.W, self.wgrad_ws)
 

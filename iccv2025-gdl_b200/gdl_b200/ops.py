@@ -243,16 +243,17 @@ def bn_bwd_nores(dy, x, dx, P, Cc, gamma, mean, invstd, scale, shift, partial, d
                                        _stream()), "gdl_bn_bwd_nores")
 
 
-@_op("stem_tail_fwd", 1, lambda x, sc, sh, y, am, N, H, W, Cc, Ho, Wo: ("bytes", N * Cc * (2.0 * H * W + 3.0 * Ho * Wo)))
-def bn_relu_maxpool_fwd(x, scale, shift, y, argmax, N, H, W, Cc, Ho, Wo):
-    check(_lib.load().gdl_bn_relu_maxpool_fwd(_ptr(x), _ptr(scale), _ptr(shift), _ptr(y), _ptr(argmax), N, H, W, Cc,
-                                              Ho, Wo, _stream()), "gdl_bn_relu_maxpool_fwd")
+@_op("stem_tail_fwd", 1, lambda x, sc, sh, y, am, xm, N, H, W, Cc, Ho, Wo: ("bytes", N * Cc * (2.0 * H * W + (5.0 if xm is not None else 3.0) * Ho * Wo)))
+def bn_relu_maxpool_fwd(x, scale, shift, y, argmax, xmax, N, H, W, Cc, Ho, Wo):
+    check(_lib.load().gdl_bn_relu_maxpool_fwd(_ptr(x), _ptr(scale), _ptr(shift), _ptr(y), _ptr(argmax), _ptr(xmax),
+                                              N, H, W, Cc, Ho, Wo, _stream()), "gdl_bn_relu_maxpool_fwd")
 
 
-@_op("stem_tail_bwd", 3, lambda g, am, x, dx, N, H, W, Cc, Ho, Wo, *a: ("bytes", N * Cc * (6.0 * H * W + 6.0 * Ho * Wo)))
-def bn_relu_maxpool_bwd(gpool, argmax, x, dx, N, H, W, Cc, Ho, Wo, gamma, mean, invstd, scale, shift, partial,
+@_op("stem_tail_bwd", 3, lambda g, am, xm, x, dx, N, H, W, Cc, Ho, Wo, *a: ("bytes", N * Cc * ((4.0 if xm is not None else 6.0) * H * W + (7.0 if xm is not None else 6.0) * Ho * Wo)))
+def bn_relu_maxpool_bwd(gpool, argmax, xmax, x, dx, N, H, W, Cc, Ho, Wo, gamma, mean, invstd, scale, shift, partial,
                         dgamma, dbeta):
-    check(_lib.load().gdl_bn_relu_maxpool_bwd(_ptr(gpool), _ptr(argmax), _ptr(x), _ptr(dx), N, H, W, Cc, Ho, Wo,
+    check(_lib.load().gdl_bn_relu_maxpool_bwd(_ptr(gpool), _ptr(argmax), _ptr(xmax), _ptr(x), _ptr(dx), N, H, W, Cc,
+                                              Ho, Wo,
                                               _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
                                               _ptr(partial), _ptr(dgamma), _ptr(dbeta), _stream()),
           "gdl_bn_relu_maxpool_bwd")

@@ -152,12 +152,13 @@ int gdl_bn_bwd_nores(const void* dy, const void* x, void* dx, int64_t P, int C, 
  * Forward reads the stem conv output x [N,H,W,C] and writes the pooled map y [N,Ho,Wo,C] + 1-byte arg-max;
  * the activation relu(bn(x)) — the largest tensor of the step — is never materialised.  Backward gathers the
  * pooled gradient through the arg-max, recomputes the ReLU mask from x and does the BN backward
- * (dgamma/dbeta fp32 overwritten, dx bf16).  Results are bit-identical to gdl_bn_apply + gdl_maxpool_fwd
- * and gdl_maxpool_bwd + gdl_bn_bwd. */
+ * (dgamma/dbeta fp32 overwritten, dx bf16).  The forward is bit-identical to gdl_bn_apply + gdl_maxpool_fwd.
+ * xmax (optional, bf16 [N,Ho,Wo,C]): the conv output at each window's arg-max, saved by the forward; with it the
+ * backward forms the BN sums on the pooled grid (4x fewer elements) instead of a pass over x. */
 int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const float* shift, void* y,
-                            uint8_t* argmax, int N, int H, int W, int C, int Ho, int Wo, gdl_stream_t s);
-int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax, const void* x, void* dx, int N,
-                            int H, int W, int C, int Ho, int Wo, const float* gamma, const float* mean,
+                            uint8_t* argmax, void* xmax, int N, int H, int W, int C, int Ho, int Wo, gdl_stream_t s);
+int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax, const void* xmax, const void* x, void* dx,
+                            int N, int H, int W, int C, int Ho, int Wo, const float* gamma, const float* mean,
                             const float* invstd, const float* scale, const float* shift, float* partial,
                             float* dgamma, float* dbeta, gdl_stream_t s);
 
