@@ -285,8 +285,10 @@ def roofline_pass(step, torch, ops, B):
     torch.cuda.synchronize()
     ops.TIMING = []
     saved = step.stream_a, step.stream_v, step.use_graph
+    saved_ws = step.enc_a.wgrad_stream, step.enc_v.wgrad_stream
     cur = torch.cuda.current_stream()
     step.stream_a = step.stream_v = cur
+    step.enc_a.wgrad_stream = step.enc_v.wgrad_stream = None  # everything serialised on one stream
     step.use_graph = False
     try:
         step.step()
@@ -295,6 +297,7 @@ def roofline_pass(step, torch, ops, B):
     finally:
         ops.TIMING = None
         step.stream_a, step.stream_v, step.use_graph = saved
+        step.enc_a.wgrad_stream, step.enc_v.wgrad_stream = saved_ws
     agg = {}
     dump = []
     for name, e0, e1, work in recs:

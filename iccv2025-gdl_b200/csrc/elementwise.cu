@@ -33,11 +33,26 @@ __global__ void layout_kernel(const float* __restrict__ src, bf16* __restrict__ 
 constexpr int kBnThreads = 256;
 constexpr int kBnMaxBlocks = 4 * kNumSMs;
 
-static int bn_blocks(int64_t P, int C) {
+// Grid-stride kernels are launched with exactly one wave of co-resident CTAs (occupancy x 148 SMs): a fixed
+// 4 x 148 grid left a 33 % partial second wave whenever register use allowed only 3 CTAs per SM.
+template <typename K>
+static int resident_blocks(K kernel, int threads) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * kNumSMs;
+}
+#define GDL_RESIDENT(kernel, threads)                           \
+  ([]() {                                                       \
+    static const int v = resident_blocks(kernel, threads);      \
+    return v;                                                   \
+  }())
+
+static int bn_blocks_cap(int64_t P, int C, int cap) {
   int lanes = kBnThreads / (C / 8);
   int64_t want = ceil_div64(P, (int64_t)lanes * 8);
   if (want < 1) want = 1;
-  return int(want < kBnMaxBlocks ? want : kBnMaxBlocks);
+  if (cap > kBnMaxBlocks) cap = kBnMaxBlocks;
+  return int(want < cap ? want : cap);
 }
 
 // Reduce the 8-channel accumulators of all pixel lanes of a block; thread layout is
@@ -748,9 +763,8 @@ __global__ void gap_bwd_kernel(const float* __restrict__ dout, bf16* __restrict_
   }
 }
 
-static unsigned ew_grid(int64_t work_items, int threads) {
+static unsigned ew_grid(int64_t work_items, int threads, int cap = kNumSMs * 16) {
   int64_t blocks = ceil_div64(work_items, threads);
-  int64_t cap = (int64_t)kNumSMs * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
@@ -783,7 +797,7 @@ extern "C" int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, con
                             float* shift, gdl_stream_t s) {
   GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_stats: bad shape");
   GDL_REQUIRE(x && partial && gamma && beta && mean && invstd && scale && shift, "gdl_bn_stats: null pointer");
-  int nblk = bn_blocks(P, C);
+  int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_stats_kernel, kBnThreads));
   bn_stats_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)x, P, C, partial);
   GDL_CHECK_LAUNCH("bn_stats_kernel");
   bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(
@@ -819,7 +833,7 @@ extern "C" int gdl_bn_apply(const void* x, const void* res, void* y, int64_t P, 
   GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_apply: bad shape");
   GDL_REQUIRE(x && y && scale && shift, "gdl_bn_apply: null pointer");
   int64_t nvec = P * C / 8;
-  bn_apply_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)x, (const bf16*)res,
+  bn_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>((const bf16*)x, (const bf16*)res,
                                                                   (bf16*)y, nvec, C, scale, shift, relu);
   GDL_CHECK_LAUNCH("bn_apply_kernel");
   return GDL_OK;
@@ -832,7 +846,7 @@ extern "C" int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz
   GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_bwd: bad shape");
   GDL_REQUIRE(dy && x && dx && gamma && mean && invstd && partial && dgamma && dbeta, "gdl_bn_bwd: null pointer");
   GDL_REQUIRE(!relu || (y && dz), "gdl_bn_bwd: relu needs y and dz");
-  int nblk = bn_blocks(P, C);
+  int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_bwd_reduce_kernel, kBnThreads));
   bn_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
       (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, mean, invstd, partial, relu);
   GDL_CHECK_LAUNCH("bn_bwd_reduce_kernel");
@@ -840,7 +854,7 @@ extern "C" int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t nvec = P * C / 8;
   const bf16* dzp = relu ? (const bf16*)dz : (const bf16*)dy;
-  bn_bwd_apply_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>(
+  bn_bwd_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
       dzp, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return GDL_OK;
@@ -852,14 +866,14 @@ extern "C" int gdl_bn_bwd_nores(const void* dy, const void* x, void* dx, int64_t
   GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_bwd_nores: bad shape");
   GDL_REQUIRE(dy && x && dx && gamma && mean && invstd && scale && shift && partial && dgamma && dbeta,
               "gdl_bn_bwd_nores: null pointer");
-  int nblk = bn_blocks(P, C);
+  int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_bwd_nores_reduce_kernel, kBnThreads));
   bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)dy, (const bf16*)x, P, C, mean,
                                                                       invstd, scale, shift, partial);
   GDL_CHECK_LAUNCH("bn_bwd_nores_reduce_kernel");
   bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t nvec = P * C / 8;
-  bn_bwd_nores_apply_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)s>>>(
+  bn_bwd_nores_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_nores_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
       (const bf16*)dy, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, scale, shift, dgamma,
       dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_nores_apply_kernel");
@@ -872,7 +886,7 @@ extern "C" int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const 
   GDL_REQUIRE(x && scale && shift && y && argmax, "gdl_bn_relu_maxpool_fwd: null pointer");
   GDL_REQUIRE(chan_ok(C) && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_bn_relu_maxpool_fwd: bad shape");
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  bn_relu_maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(
+  bn_relu_maxpool_fwd_kernel<<<ew_grid(total, 256, GDL_RESIDENT(bn_relu_maxpool_fwd_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
       (const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H, W, C, Ho, Wo);
   GDL_CHECK_LAUNCH("bn_relu_maxpool_fwd_kernel");
   return GDL_OK;
@@ -892,11 +906,11 @@ extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax,
     // sums of dz and dz*xhat over the POOLED grid: each window contributes its gradient at its arg-max pixel,
     // whose conv output the forward saved — the no-residual BN reduce kernel on (gpool, xmax)
     const int64_t Pp = (int64_t)N * Ho * Wo;
-    nblk = bn_blocks(Pp, C);
+    nblk = bn_blocks_cap(Pp, C, GDL_RESIDENT(bn_bwd_nores_reduce_kernel, kBnThreads));
     bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)gpool, (const bf16*)xmax, Pp, C,
                                                                         mean, invstd, scale, shift, partial);
   } else {
-    nblk = bn_blocks((int64_t)N * Ho * Wo * 4, C);
+    nblk = bn_blocks_cap((int64_t)N * Ho * Wo * 4, C, GDL_RESIDENT(bn_relu_maxpool_bwd_reduce_kernel, kBnThreads));
     bn_relu_maxpool_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
         (const bf16*)gpool, argmax, (const bf16*)x, N, H, W, C, Ho, Wo, mean, invstd, scale, shift, partial);
   }
@@ -904,7 +918,8 @@ extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax,
   bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  bn_relu_maxpool_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(
+  bn_relu_maxpool_bwd_apply_kernel<<<ew_grid(total, 256, GDL_RESIDENT(bn_relu_maxpool_bwd_apply_kernel, 256)), 256, 0,
+                                     (cudaStream_t)s>>>(
       (const bf16*)gpool, argmax, (const bf16*)x, (bf16*)dx, N, H, W, C, Ho, Wo, 1.f / (float)P, gamma, mean, invstd,
       scale, shift, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_relu_maxpool_bwd_apply_kernel");

@@ -14,9 +14,16 @@ Data layout in HBM:
                   mean / invstd / fused scale+shift saved for backward
   gradients       activations bf16 NHWC; parameters fp32 written straight into p.grad storage
 """
+import os
+
 import torch
 
 from . import ops
+
+
+# Measured on B=256: no gain (24.05 vs 23.88 ms) — the two encoder streams already keep the GPU busy and the
+# tensor-bound wgrads contend with the BN kernels for L2/HBM; kept as an option, off by default.
+USE_WGRAD_STREAM = os.environ.get("GDL_WGRAD_STREAM", "0") != "0"
 
 
 class _Pool:
@@ -162,6 +169,8 @@ class EncoderEngine:
         self.Hf, self.Wf, self.Cf = h, w, cin
         self.wgrad_ws = torch.empty(max(self.max_wgrad_ws, 16) // 4, device=device, dtype=torch.float32)
         self.bn_partial = torch.empty(self.max_bn_partial, device=device, dtype=torch.float32)
+        self.wgrad_stream = torch.cuda.Stream(device) if USE_WGRAD_STREAM else None
+        self._readers = {}
         self._plan_backward()
         self.repack()
 
@@ -249,23 +258,53 @@ class EncoderEngine:
         ops.bn_bwd(dy, u.y, u.x, dz, dx, u.P, u.C, bn.weight.data, u.mean, u.invstd, self.bn_partial,
                    self._grad(bn.weight), self._grad(bn.bias), relu)
 
+    # ------------------------------------------------------------------ weight-gradient side stream
+    # A weight gradient only needs the BN-backward output d_c and a saved forward activation, and nothing in
+    # the backward chain needs ITS result: all wgrads run on a side stream, concurrently with the dgrad -> BN
+    # chain, so the tensor-bound wgrad kernels overlap the HBM-bound BN kernels.  d_c buffers are reused by
+    # later blocks: before the chain overwrites one, it waits for the wgrad that still reads it.
+    def _wgrad(self, fn, d_c):
+        ws = self.wgrad_stream
+        if ws is None:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        ws.wait_stream(main)              # d_c is complete
+        with torch.cuda.stream(ws):
+            fn()
+            ev = torch.cuda.Event()
+            ev.record(ws)
+        self._readers[d_c.data_ptr()] = ev
+
+    def _before_write(self, buf):
+        ev = self._readers.pop(buf.data_ptr(), None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
     def backward(self, x16):
         """Consumes self.g_feat (grad wrt the layer4 map, bf16) and writes every parameter
         gradient of the encoder into p.grad (overwrite).  x16 is the stem input of the forward."""
+        self._readers = {}
         for (u1, u2, ud), b, in_t in zip(reversed(self.blocks), self.bwd_plan, reversed(self._block_inputs())):
             g_out = b["g_out"]
             # out = relu(bn2(c2) + identity): dz = g_out * (out > 0), in place
+            self._before_write(b["d_c2"])
             self._bn_bwd(u2, g_out, g_out, b["d_c2"], True)
-            ops.conv_wgrad(u2.d, u2.ci_real, u1.y, b["d_c2"], self._grad(u2.conv.weight), self.wgrad_ws)
+            self._wgrad(lambda: ops.conv_wgrad(u2.d, u2.ci_real, u1.y, b["d_c2"], self._grad(u2.conv.weight),
+                                               self.wgrad_ws), b["d_c2"])
             ops.conv_dgrad(u2.d, b["d_c2"], u2.wT, b["g_y1"])
             # bn1 + relu has no residual input: mask recomputed from x, no y read / dz write
+            self._before_write(b["d_c1"])
             ops.bn_bwd_nores(b["g_y1"], u1.x, b["d_c1"], u1.P, u1.C, u1.bn.weight.data, u1.mean, u1.invstd,
                              u1.scale, u1.shift, self.bn_partial, self._grad(u1.bn.weight), self._grad(u1.bn.bias))
-            ops.conv_wgrad(u1.d, u1.ci_real, in_t, b["d_c1"], self._grad(u1.conv.weight), self.wgrad_ws)
+            self._wgrad(lambda: ops.conv_wgrad(u1.d, u1.ci_real, in_t, b["d_c1"], self._grad(u1.conv.weight),
+                                               self.wgrad_ws), b["d_c1"])
             if ud is not None:
                 # identity = bn_d(conv1x1_s2(u)), no relu: its output gradient is dz (= g_out now)
+                self._before_write(b["d_cd"])
                 self._bn_bwd(ud, g_out, None, b["d_cd"], False)
-                ops.conv_wgrad(ud.d, ud.ci_real, in_t, b["d_cd"], self._grad(ud.conv.weight), self.wgrad_ws)
+                self._wgrad(lambda: ops.conv_wgrad(ud.d, ud.ci_real, in_t, b["d_cd"], self._grad(ud.conv.weight),
+                                                   self.wgrad_ws), b["d_cd"])
                 # 1x1 stride-2 dgrad on the compact grid, then folded into conv1's dgrad epilogue
                 dc = ops.conv_desc(self.N, ud.d.Ho, ud.d.Wo, ud.d.Ci, ud.d.Co, 1, 1, 1, 0)
                 ops.conv_dgrad(dc, b["d_cd"], ud.wT, b["g_ds"])
@@ -274,10 +313,15 @@ class EncoderEngine:
                 ops.conv_dgrad(u1.d, b["d_c1"], u1.wT, b["g_u"], g_out, 1)
         s = self.stem
         # max-pool scatter + ReLU mask + BN backward in one pair of passes over the stem conv output
+        self._before_write(self.d_c0)
         ops.bn_relu_maxpool_bwd(self.g_pool, self.pool_idx, self.pool_xmax, s.x, self.d_c0, self.N, s.d.Ho, s.d.Wo,
                                 64, self.Hp, self.Wp, s.bn.weight.data, s.mean, s.invstd, s.scale, s.shift, self.bn_partial,
                                 self._grad(s.bn.weight), self._grad(s.bn.bias))
-        ops.stem_wgrad(x16, self.d_c0, self._grad(s.conv.weight), s.ci_real, self.N, self.H, self.W, self.wgrad_ws)
+        self._wgrad(lambda: ops.stem_wgrad(x16, self.d_c0, self._grad(s.conv.weight), s.ci_real, self.N, self.H,
+                                           self.W, self.wgrad_ws), self.d_c0)
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)  # join: every gradient is complete
+        self._readers = {}
 
     def _block_inputs(self):
         ins = [self.pool_y]
