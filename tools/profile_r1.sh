@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 1 --warmup 3 --no-graph --no-roofline --no-cpu --batch ${PROF_BATCH:-256}"
 # 4 warm-up + 1 timed + e2e eager steps; skip the first 3 steps' worth of launches, keep > one full step
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 1100 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_bench.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1300 -c 1000 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_bench.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on"
 $NCU -k regex:conv_flat_kernel -s 40 -c 8 -f -o gpurun_out/prof_flat $BENCH > gpurun_out/prof_flat.log 2>&1
 $NCU -k regex:conv_wgrad_flat -s 20 -c 6 -f -o gpurun_out/prof_wflat $BENCH > gpurun_out/prof_wflat.log 2>&1
