@@ -86,4 +86,7 @@ __device__ __forceinline__ void st_global32(void* p, const uint4& lo, const uint
 
 static const int kNumSMs = 148;
 
+// gdl_set_sweep() hint (elementwise.cu): non-zero = walk pixel ranges in descending order
+extern thread_local int g_sweep_rev;
+
 }  // namespace gdl

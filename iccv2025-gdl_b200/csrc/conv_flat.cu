@@ -57,6 +57,7 @@ struct FlatParams {
   int gtap0[4][5];  // group g of class c owns taps [gtap0[c][g], gtap0[c][g+1])
   int smin, smax;
   int mtiles, ntiles, items_total;
+  int rev;  // gdl_set_sweep hint: walk the pixel tiles of every (class, channel tile) in descending order
   int win_stage_bytes, win_stages;
 };
 
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
       const int nt = rem / p.mtiles;
-      const int q0 = (rem - nt * p.mtiles) * TM;
+      const int mt_i = rem - nt * p.mtiles;
+      const int q0 = (p.rev ? p.mtiles - 1 - mt_i : mt_i) * TM;
       const int n0 = nt * BN;
       const int rho_a = floor_div(q0 + p.smin, p.P);
       const int rho_b = floor_div(q0 + TM + p.smax - 1, p.P);
@@ -172,7 +174,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
       const int nt = rem / p.mtiles;
-      const int q0 = (rem - nt * p.mtiles) * TM;
+      const int mt_i = rem - nt * p.mtiles;
+      const int q0 = (p.rev ? p.mtiles - 1 - mt_i : mt_i) * TM;
       const int rho_a = floor_div(q0 + p.smin, p.P);
       const int o = q0 + p.smin - rho_a * p.P;  // first window row inside the stage
       const int acc = it & 1;
@@ -245,7 +248,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
       const int nt = rem / p.mtiles;
-      const int q0 = (rem - nt * p.mtiles) * TM;
+      const int mt_i = rem - nt * p.mtiles;
+      const int q0 = (p.rev ? p.mtiles - 1 - mt_i : mt_i) * TM;
       const int n0 = nt * BN;
       const int acc = it & 1;
       if (STATS && nt != st_nt) {
@@ -416,6 +420,7 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   p.dst = (bf16*)dst;
   p.add_src = (const bf16*)add_src;
   p.add_mode = add_mode;
+  p.rev = g_sweep_rev;
   // The statistics butterfly costs ~1.3k instructions per 128x128 tile in the epilogue warps: it hides behind the
   // MMAs only when the reduction is long (measured: +2-8 % kernel time for K >= 1152, +30 % at K = 576, 2.4x for
   // 1x1); against the separate statistics kernel it came out even on the whole step, so it is off by default

@@ -20,6 +20,7 @@
 //   reduced in a fixed order (deterministic).
 //   MODE 0 (Ci == 64): an M tile is TWO taps x 64 ci (second block = same window, LBO rows further).
 //   MODE 1 (Ci >= 128): an M tile is one tap x 128 ci (two slab windows, LBO = slab stride).
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "tma.cuh"
@@ -43,7 +44,8 @@ struct WfJobType {
 struct WfParams {
   CUtensorMap tm_x[4];  // box {64, P, xrows, NI}
   CUtensorMap tm_dy;    // box {64, P, dyrows, NI}
-  float* partial;       // [splits][Kp][Co]
+  float* partial;       // [splits][Kp][Co], or [splits][Co][Kp] when transposed
+  int transposed;       // 1: partials stored co-major, so a warp's 32 rows (consecutive ci) store 128 contiguous bytes
   int Ci, Co, Kp;
   int ntypes;
   WfJobType jt[4];
@@ -201,16 +203,26 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
         ci = ci0 + row;
       }
       const bool valid = tap >= 0 && t1 > t0;
-      float* out = p.partial + ((size_t)blockIdx.x * p.Kp + (size_t)(tap < 0 ? 0 : tap) * p.Ci + ci) * p.Co + co0;
+      const size_t krow = (size_t)(tap < 0 ? 0 : tap) * p.Ci + ci;
+      // transposed: lane l of a warp owns row ci0+l, so for one output column the warp writes 32 consecutive
+      // floats (one 128-byte line per store instruction); row-major partials put every lane on its own line
+      // (32 lines per store instruction, i.e. 32x the LSU wavefronts for the same bytes).
+      float* out = p.transposed ? p.partial + ((size_t)blockIdx.x * p.Co + co0) * p.Kp + krow
+                                : p.partial + ((size_t)blockIdx.x * p.Kp + krow) * p.Co + co0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(trow + u * BN + c0, r);
         tmem_ld_wait();
         if (valid) {
+          if (p.transposed) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(out + c0 + g * 4) = make_uint4(r[g * 4], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]);
+            for (int i = 0; i < 32; ++i) out[(size_t)(c0 + i) * p.Kp] = __uint_as_float(r[i]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(out + c0 + g * 4) = make_uint4(r[g * 4], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]);
+          }
         }
       }
     }
@@ -353,7 +365,15 @@ static bool plan_wgrad_flat(int N, int Ho, int Wo, int Ci, int Co, int R, int st
   if (best >= 1e30) return false;
   if (w.xwin_bytes >= (1 << 18) || w.dywin_bytes >= (1 << 18)) return false;  // LBO field
   w.gy = w.ci_tiles * w.co_tiles * w.ntypes;
-  int splits = (2 * kNumSMs) / w.gy;
+  // One CTA per SM (the stage ring takes ~200 KB) and all 512 TMEM columns: CTAs of a second wave cannot
+  // overlap the first wave's epilogue, they only add a prologue, an epilogue and a set of partials each.
+  // GDL_WGRAD_WAVES (default 1) sets how many CTAs per SM the split-K factor is sized for.
+  static const int waves = []() {
+    const char* e = getenv("GDL_WGRAD_WAVES");
+    const int v = e ? atoi(e) : 1;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+  }();
+  int splits = (waves * kNumSMs) / w.gy;
   if (splits < 1) splits = 1;
   if (splits > w.tiles_total) splits = w.tiles_total;
   w.tiles_per_split = (w.tiles_total + splits - 1) / splits;
@@ -385,8 +405,9 @@ int64_t wgrad_flat_workspace_bytes(int N, int Ho, int Wo, int Ci, int Co, int R,
 
 // x is the conv INPUT [N,Hi,Wi,Ci]; dy the output gradient [N,Ho,Wo,Co].  Returns the number of splits
 // written (>0) when handled, 0 when not eligible, <0 on error.
+// transposed != 0: partials are written [split][Co][Kp] (coalesced epilogue stores), else [split][Kp][Co].
 int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R, int stride, const void* x,
-                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s) {
+                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed) {
   WfPlan w;
   if (!plan_wgrad_flat(N, Ho, Wo, Ci, Co, R, stride, w)) return 0;
   if (workspace_bytes < (int64_t)w.splits * w.taps * Ci * Co * (int64_t)sizeof(float)) return 0;
@@ -415,6 +436,7 @@ int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R,
   if (!td) return GDL_ECUDA;
   p.tm_dy = *td;
   p.partial = partial;
+  p.transposed = transposed != 0;
   p.Ci = Ci; p.Co = Co; p.Kp = w.taps * Ci;
   p.ntypes = w.ntypes;
   for (int i = 0; i < 4; ++i) p.jt[i] = w.jt[i];

@@ -33,6 +33,14 @@ __global__ void layout_kernel(const float* __restrict__ src, bf16* __restrict__ 
 constexpr int kBnThreads = 256;
 constexpr int kBnMaxBlocks = 4 * kNumSMs;
 
+// Sweep direction hint (gdl_set_sweep, include/gdl_b200.h): the grid-stride kernels below walk their pixel /
+// vector range in ascending order, or descending when the hint is set.  A pass that runs opposite to the pass
+// that last touched a tensor starts on the part of it that is still in the 126 MB L2 (the producer's tail)
+// instead of on the part that was evicted first.  Two-pass operations (reduce + apply) run their second pass
+// opposite to the first.  Element-wise results do not depend on it; reductions keep a fixed order per setting.
+thread_local int g_sweep_rev = 0;
+__device__ __forceinline__ int64_t sweep_idx(int64_t i, int64_t n, int rev) { return rev ? n - 1 - i : i; }
+
 // Grid-stride kernels are launched with exactly one wave of co-resident CTAs (occupancy x 148 SMs): a fixed
 // 4 x 148 grid left a 33 % partial second wave whenever register use allowed only 3 CTAs per SM.
 template <typename K>
@@ -88,7 +96,7 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NACC][8], int 
 }
 
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const bf16* __restrict__ x, int64_t P,
-                                                              int C, float* __restrict__ partial) {
+                                                              int C, float* __restrict__ partial, int rev) {
   const int groups = C / 8;
   const int lanes = kBnThreads / groups;
   const int cg = threadIdx.x % groups;
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const bf16* __rest
   for (; pix + 3 * stride < P; pix += 4 * stride) {
     uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = ld_stream16(x + (pix + k * stride) * C + cg * 8);
+    for (int k = 0; k < 4; ++k) u[k] = ld_stream16(x + sweep_idx(pix + k * stride, P, rev) * C + cg * 8);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float f[8];
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const bf16* __rest
   }
   for (; pix < P; pix += stride) {
     float f[8];
-    unpack8(ld_stream16(x + pix * C + cg * 8), f);
+    unpack8(ld_stream16(x + sweep_idx(pix, P, rev) * C + cg * 8), f);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       acc[0][c] += f[c];
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
                                                        const bf16* __restrict__ res,
                                                        bf16* __restrict__ y, int64_t nvec, int C,
                                                        const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, int relu) {
+                                                       const float* __restrict__ shift, int relu, int rev) {
   __shared__ float s_scale[512], s_shift[512];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     s_scale[c] = scale[c];
@@ -191,8 +199,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
   }
   __syncthreads();
   const int groups = C / 8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec;
+       i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = sweep_idx(i0, nvec, rev);
     const int cg = int(i % groups);
     float f[8];
     unpack8(ld_stream16(x + i * 8), f);
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 // backward pass 1: dz = dy * (y > 0); partial sums of dz and dz * xhat
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     const bf16* dy, const bf16* __restrict__ y, const bf16* __restrict__ x, bf16* dz, int64_t P, int C, const float* __restrict__ mean,
-    const float* __restrict__ invstd, float* __restrict__ partial, int relu) {
+    const float* __restrict__ invstd, float* __restrict__ partial, int relu, int rev) {
   const int groups = C / 8;
   const int lanes = kBnThreads / groups;
   const int cg = threadIdx.x % groups;
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
   };
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   for (; pix + stride < P; pix += 2 * stride) {  // two pixels in flight; dz may alias dy: no .nc path for dy
-    const int64_t o0 = pix * C + cg * 8, o1 = (pix + stride) * C + cg * 8;
+    const int64_t o0 = sweep_idx(pix, P, rev) * C + cg * 8, o1 = sweep_idx(pix + stride, P, rev) * C + cg * 8;
     const uint4 g0 = *reinterpret_cast<const uint4*>(dy + o0), x0 = ld_stream16(x + o0);
     const uint4 g1 = *reinterpret_cast<const uint4*>(dy + o1), x1 = ld_stream16(x + o1);
     const uint4 y0 = relu ? ld_stream16(y + o0) : zero4, y1 = relu ? ld_stream16(y + o1) : zero4;
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     body(o1, g1, x1, y1);
   }
   for (; pix < P; pix += stride) {
-    const int64_t off = pix * C + cg * 8;
+    const int64_t off = sweep_idx(pix, P, rev) * C + cg * 8;
     body(off, *reinterpret_cast<const uint4*>(dy + off), ld_stream16(x + off), relu ? ld_stream16(y + off) : zero4);
   }
   block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const bf16* __restrict__ dz, const bf16* __restrict__ x, bf16* __restrict__ dx, int64_t nvec,
     int C, float invP, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ dgamma,
-    const float* __restrict__ dbeta) {
+    const float* __restrict__ dbeta, int rev) {
   // dx = a*dz + b*x + c  with  a = gamma*invstd,  b = -a*invstd*dgamma/P,
   //                            c = -a*dbeta/P - b*mean
   __shared__ float s_a[512], s_b[512], s_c[512];
@@ -313,12 +322,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   };
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + stride < nvec; i += 2 * stride) {
-    const uint4 g0 = ld_stream16(dz + i * 8), x0 = ld_stream16(x + i * 8);
-    const uint4 g1 = ld_stream16(dz + (i + stride) * 8), x1 = ld_stream16(x + (i + stride) * 8);
-    body(i, g0, x0);
-    body(i + stride, g1, x1);
+    const int64_t j0 = sweep_idx(i, nvec, rev), j1 = sweep_idx(i + stride, nvec, rev);
+    const uint4 g0 = ld_stream16(dz + j0 * 8), x0 = ld_stream16(x + j0 * 8);
+    const uint4 g1 = ld_stream16(dz + j1 * 8), x1 = ld_stream16(x + j1 * 8);
+    body(j0, g0, x0);
+    body(j1, g1, x1);
   }
-  for (; i < nvec; i += stride) body(i, ld_stream16(dz + i * 8), ld_stream16(x + i * 8));
+  for (; i < nvec; i += stride) {
+    const int64_t j = sweep_idx(i, nvec, rev);
+    body(j, ld_stream16(dz + j * 8), ld_stream16(x + j * 8));
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -422,7 +435,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, int64_t P, int C, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
-    float* __restrict__ partial) {
+    float* __restrict__ partial, int rev) {
   const int groups = C / 8;
   const int lanes = kBnThreads / groups;
   const int cg = threadIdx.x % groups;
@@ -455,7 +468,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
     uint4 g[4], xx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int64_t o = (pix + k * stride) * C + cg * 8;
+      const int64_t o = sweep_idx(pix + k * stride, P, rev) * C + cg * 8;
       g[k] = ld_stream16(dy + o);
       xx[k] = ld_stream16(x + o);
     }
@@ -463,7 +476,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
     for (int k = 0; k < 4; ++k) body(g[k], xx[k]);
   }
   for (; pix < P; pix += stride) {
-    const int64_t off = pix * C + cg * 8;
+    const int64_t off = sweep_idx(pix, P, rev) * C + cg * 8;
     body(ld_stream16(dy + off), ld_stream16(x + off));
   }
   block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
@@ -473,7 +486,7 @@ __global__ void __launch_bounds__(256) bn_bwd_nores_apply_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, int64_t nvec, int C,
     float invP, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
-    const float* __restrict__ dgamma, const float* __restrict__ dbeta) {
+    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int rev) {
   __shared__ float s_a[512], s_b[512], s_c[512], s_sc[512], s_sh[512];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = gamma[c] * invstd[c];
@@ -505,13 +518,17 @@ __global__ void __launch_bounds__(256) bn_bwd_nores_apply_kernel(
     uint4 g[4], xx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      g[k] = ld_stream16(dy + (i + k * stride) * 8);
-      xx[k] = ld_stream16(x + (i + k * stride) * 8);
+      const int64_t j = sweep_idx(i + k * stride, nvec, rev);
+      g[k] = ld_stream16(dy + j * 8);
+      xx[k] = ld_stream16(x + j * 8);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) body(i + k * stride, g[k], xx[k]);
+    for (int k = 0; k < 4; ++k) body(sweep_idx(i + k * stride, nvec, rev), g[k], xx[k]);
   }
-  for (; i < nvec; i += stride) body(i, ld_stream16(dy + i * 8), ld_stream16(x + i * 8));
+  for (; i < nvec; i += stride) {
+    const int64_t j = sweep_idx(i, nvec, rev);
+    body(j, ld_stream16(dy + j * 8), ld_stream16(x + j * 8));
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -798,7 +815,7 @@ extern "C" int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, con
   GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_stats: bad shape");
   GDL_REQUIRE(x && partial && gamma && beta && mean && invstd && scale && shift, "gdl_bn_stats: null pointer");
   int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_stats_kernel, kBnThreads));
-  bn_stats_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)x, P, C, partial);
+  bn_stats_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)x, P, C, partial, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_stats_kernel");
   bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(
       partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
@@ -834,7 +851,7 @@ extern "C" int gdl_bn_apply(const void* x, const void* res, void* y, int64_t P, 
   GDL_REQUIRE(x && y && scale && shift, "gdl_bn_apply: null pointer");
   int64_t nvec = P * C / 8;
   bn_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>((const bf16*)x, (const bf16*)res,
-                                                                  (bf16*)y, nvec, C, scale, shift, relu);
+                                                                  (bf16*)y, nvec, C, scale, shift, relu, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_apply_kernel");
   return GDL_OK;
 }
@@ -848,14 +865,14 @@ extern "C" int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz
   GDL_REQUIRE(!relu || (y && dz), "gdl_bn_bwd: relu needs y and dz");
   int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_bwd_reduce_kernel, kBnThreads));
   bn_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
-      (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, mean, invstd, partial, relu);
+      (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, mean, invstd, partial, relu, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_reduce_kernel");
   bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t nvec = P * C / 8;
   const bf16* dzp = relu ? (const bf16*)dz : (const bf16*)dy;
   bn_bwd_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
-      dzp, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, dgamma, dbeta);
+      dzp, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, dgamma, dbeta, !g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return GDL_OK;
 }
@@ -868,14 +885,14 @@ extern "C" int gdl_bn_bwd_nores(const void* dy, const void* x, void* dx, int64_t
               "gdl_bn_bwd_nores: null pointer");
   int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_bwd_nores_reduce_kernel, kBnThreads));
   bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)dy, (const bf16*)x, P, C, mean,
-                                                                      invstd, scale, shift, partial);
+                                                                      invstd, scale, shift, partial, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_nores_reduce_kernel");
   bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t nvec = P * C / 8;
   bn_bwd_nores_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_nores_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
       (const bf16*)dy, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, scale, shift, dgamma,
-      dbeta);
+      dbeta, !g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_nores_apply_kernel");
   return GDL_OK;
 }
@@ -908,7 +925,7 @@ extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax,
     const int64_t Pp = (int64_t)N * Ho * Wo;
     nblk = bn_blocks_cap(Pp, C, GDL_RESIDENT(bn_bwd_nores_reduce_kernel, kBnThreads));
     bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)gpool, (const bf16*)xmax, Pp, C,
-                                                                        mean, invstd, scale, shift, partial);
+                                                                        mean, invstd, scale, shift, partial, g_sweep_rev);
   } else {
     nblk = bn_blocks_cap((int64_t)N * Ho * Wo * 4, C, GDL_RESIDENT(bn_relu_maxpool_bwd_reduce_kernel, kBnThreads));
     bn_relu_maxpool_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
@@ -962,4 +979,10 @@ extern "C" int gdl_gap_bwd(const float* dout, void* dx, int B, int G, int C, gdl
   gap_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(dout, (bf16*)dx, B, G, C);
   GDL_CHECK_LAUNCH("gap_bwd_kernel");
   return GDL_OK;
+}
+
+extern "C" int gdl_set_sweep(int reverse) {
+  const int old = gdl::g_sweep_rev;
+  gdl::g_sweep_rev = reverse != 0;
+  return old;
 }

@@ -25,6 +25,14 @@ from . import ops
 # tensor-bound wgrads contend with the BN kernels for L2/HBM; kept as an option, off by default.
 USE_WGRAD_STREAM = os.environ.get("GDL_WGRAD_STREAM", "0") != "0"
 
+# Sweep directions (ops.sweep / gdl_set_sweep): every pass over a tensor larger than L2 leaves its LAST-touched
+# part in the 126 MB L2, so the next pass over the same tensor should start there, i.e. run the other way.
+#   0  every kernel ascending (the behaviour before this option)
+#   1  BatchNorm passes alternate: statistics descending after the (ascending) conv, apply ascending; backward
+#      reduce descending after the (ascending) dgrad, apply ascending
+#   2  the convolutions alternate as well (conv1 of a block descending, conv2 ascending, BN passes in between)
+SWEEP = int(os.environ.get("GDL_SWEEP", "1"))
+
 
 class _Pool:
     """Static buffer planner: buffers are requested/released while the plan is built; a released
@@ -58,6 +66,7 @@ class _ConvBN:
         self.conv, self.bn = conv, bn
         self.ci_real = ci_real
         self.relu = relu
+        self.cdir = 0  # sweep direction of this unit's convolution (set by the engine for SWEEP == 2)
         self.d = ops.conv_desc(N, Hi, Wi, ci_store, Co, R, S, conv.stride[0], conv.padding[0])
         self.P = N * self.d.Ho * self.d.Wo
         self.C = Co
@@ -76,9 +85,12 @@ class _ConvBN:
 
     def forward(self, eng, inp, res=None, training=True):
         bn = self.bn
+        c = self.cdir
         if training:
             # batch statistics come out of the conv epilogue where the kernel supports it (no extra pass over x)
+            ops.sweep(c)
             rows = ops.conv_fwd_stats(self.d, inp, self.wp, self.x, eng.bn_partial, self.ci_real)
+            ops.sweep((not c) if SWEEP else 0)
             if rows:
                 ops.bn_stats_finalize(eng.bn_partial, rows, self.P, self.C, bn.weight.data, bn.bias.data, bn.eps,
                                       bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
@@ -88,9 +100,12 @@ class _ConvBN:
                              bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
                              self.scale, self.shift)
         else:
+            ops.sweep(c)
             ops.conv_fwd(self.d, inp, self.wp, self.x, self.ci_real)
             ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
                                self.scale, self.shift, self.C)
+            c = (not c) if SWEEP else 0  # no statistics pass in between: apply runs opposite to the conv
+        ops.sweep(c)
         ops.bn_apply(self.x, res, self.y, self.P, self.C, self.scale, self.shift, self.relu)
         return self.y
 
@@ -123,6 +138,7 @@ class _StemBN(_ConvBN):
         ops.stem_fwd(x16, self.wp, self.x, self.N, self.H, self.W, self.ci_real)
         bn = self.bn
         if training:
+            ops.sweep(1 if SWEEP else 0)
             ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
                          bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
                          self.scale, self.shift)
@@ -164,6 +180,10 @@ class EncoderEngine:
                 ud = None
                 if blk.downsample is not None:
                     ud = self._unit(pre + "downsample", blk.downsample[0], blk.downsample[1], N, h, w, cin, False)
+                if SWEEP >= 2:  # the block input was written ascending (max-pool / previous bn2 apply)
+                    u1.cdir = 1
+                    if ud is not None:
+                        ud.cdir = 1
                 self.blocks.append((u1, u2, ud))
                 h, w, cin = u1.d.Ho, u1.d.Wo, u1.C
         self.Hf, self.Wf, self.Cf = h, w, cin
@@ -205,6 +225,7 @@ class EncoderEngine:
                 ident = ud.forward(self, u, training=training)
             # bn2 + residual + relu (reference backbone.py:62-66)
             u = u2.forward(self, y1, res=ident, training=training)
+        ops.sweep(0)
         return u
 
     # ------------------------------------------------------------------ backward
@@ -281,18 +302,39 @@ class EncoderEngine:
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
 
-    def backward(self, x16):
+    N_LATE_BLOCKS = 4  # layer4 + layer3: 94 % of the encoder's parameters, the first gradients to be complete
+
+    def late_parameters(self):
+        """Parameters whose gradients are complete after backward(part=0) (layer3 + layer4)."""
+        out = []
+        for (u1, u2, ud) in self.blocks[len(self.blocks) - self.N_LATE_BLOCKS:]:
+            for u in (u1, u2, ud):
+                if u is not None:
+                    out += [u.conv.weight, u.bn.weight, u.bn.bias]
+        return out
+
+    def backward(self, x16, part=None):
         """Consumes self.g_feat (grad wrt the layer4 map, bf16) and writes every parameter
-        gradient of the encoder into p.grad (overwrite).  x16 is the stem input of the forward."""
+        gradient of the encoder into p.grad (overwrite).  x16 is the stem input of the forward.
+        part=None runs the whole backward; part=0 only layer4 + layer3 (after which the gradients of
+        late_parameters() are final and their all-reduce can start), part=1 the rest (layer2, layer1, stem)."""
         self._readers = {}
-        for (u1, u2, ud), b, in_t in zip(reversed(self.blocks), self.bwd_plan, reversed(self._block_inputs())):
+        chain = list(zip(reversed(self.blocks), self.bwd_plan, reversed(self._block_inputs())))
+        if part == 0:
+            chain = chain[:self.N_LATE_BLOCKS]
+        elif part == 1:
+            chain = chain[self.N_LATE_BLOCKS:]
+        for (u1, u2, ud), b, in_t in chain:
             g_out = b["g_out"]
             # out = relu(bn2(c2) + identity): dz = g_out * (out > 0), in place
             self._before_write(b["d_c2"])
+            ops.sweep(1 if SWEEP else 0)      # g_out was written ascending: reduce descending, apply ascending
             self._bn_bwd(u2, g_out, g_out, b["d_c2"], True)
             self._wgrad(lambda: ops.conv_wgrad(u2.d, u2.ci_real, u1.y, b["d_c2"], self._grad(u2.conv.weight),
                                                self.wgrad_ws), b["d_c2"])
+            ops.sweep(1 if SWEEP >= 2 else 0)
             ops.conv_dgrad(u2.d, b["d_c2"], u2.wT, b["g_y1"])
+            ops.sweep(1 if SWEEP == 1 else 0)  # SWEEP 2: g_y1 was written descending -> reduce ascending
             # bn1 + relu has no residual input: mask recomputed from x, no y read / dz write
             self._before_write(b["d_c1"])
             ops.bn_bwd_nores(b["g_y1"], u1.x, b["d_c1"], u1.P, u1.C, u1.bn.weight.data, u1.mean, u1.invstd,
@@ -302,7 +344,9 @@ class EncoderEngine:
             if ud is not None:
                 # identity = bn_d(conv1x1_s2(u)), no relu: its output gradient is dz (= g_out now)
                 self._before_write(b["d_cd"])
+                ops.sweep(1 if SWEEP else 0)
                 self._bn_bwd(ud, g_out, None, b["d_cd"], False)
+                ops.sweep(0)
                 self._wgrad(lambda: ops.conv_wgrad(ud.d, ud.ci_real, in_t, b["d_cd"], self._grad(ud.conv.weight),
                                                    self.wgrad_ws), b["d_cd"])
                 # 1x1 stride-2 dgrad on the compact grid, then folded into conv1's dgrad epilogue
@@ -310,8 +354,16 @@ class EncoderEngine:
                 ops.conv_dgrad(dc, b["d_cd"], ud.wT, b["g_ds"])
                 ops.conv_dgrad(u1.d, b["d_c1"], u1.wT, b["g_u"], b["g_ds"], 2)
             else:
+                ops.sweep(0)
                 ops.conv_dgrad(u1.d, b["d_c1"], u1.wT, b["g_u"], g_out, 1)
+        if part == 0:
+            ops.sweep(0)
+            if self.wgrad_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+            self._readers = {}
+            return
         s = self.stem
+        ops.sweep(1 if SWEEP else 0)  # g_pool was written ascending by the last dgrad
         # max-pool scatter + ReLU mask + BN backward in one pair of passes over the stem conv output
         self._before_write(self.d_c0)
         ops.bn_relu_maxpool_bwd(self.g_pool, self.pool_idx, self.pool_xmax, s.x, self.d_c0, self.N, s.d.Ho, s.d.Wo,
@@ -319,6 +371,7 @@ class EncoderEngine:
                                 self._grad(s.bn.weight), self._grad(s.bn.bias))
         self._wgrad(lambda: ops.stem_wgrad(x16, self.d_c0, self._grad(s.conv.weight), s.ci_real, self.N, self.H,
                                            self.W, self.wgrad_ws), self.d_c0)
+        ops.sweep(0)
         if self.wgrad_stream is not None:
             torch.cuda.current_stream().wait_stream(self.wgrad_stream)  # join: every gradient is complete
         self._readers = {}

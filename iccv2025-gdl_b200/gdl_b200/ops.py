@@ -4,6 +4,7 @@ every computation below runs in libgdl_b200.so.  No fallbacks.
 """
 import ctypes as C
 import functools
+import threading
 
 import torch
 
@@ -131,6 +132,20 @@ def conv_fwd_stats(d, x, w_packed, y, bn_partial, ci_real=None):
     check(_lib.load().gdl_conv_fwd_stats(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(y), _ptr(bn_partial),
                                          C.byref(rows), _stream()), "gdl_conv_fwd_stats")
     return rows.value
+
+
+_sweep_state = {}  # thread id -> last value handed to the (thread-local) C hint
+
+
+def sweep(reverse):
+    """Direction hint for the following conv / BN launches of this thread (gdl_set_sweep): reverse=1 walks the
+    pixel range in descending order, so a pass that follows a forward-order producer starts on the part of the
+    tensor that is still in L2.  Cached: the C call is made only when the setting changes."""
+    reverse = 1 if reverse else 0
+    tid = threading.get_ident()
+    if _sweep_state.get(tid, 0) != reverse:
+        _lib.load().gdl_set_sweep(reverse)
+        _sweep_state[tid] = reverse
 
 
 def set_fused_stats_min_k(k):

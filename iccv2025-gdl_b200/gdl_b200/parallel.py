@@ -23,3 +23,26 @@ def allreduce_sum_(flat, group=None):
 
 def flatten_grads(grads, names):
     return torch.cat([grads[k].reshape(-1) for k in names])
+
+
+def gradient_buckets(grad, cut_a, end_a, cut_v):
+    """Views of the flat gradient arena (order: head | audio_net | visual_net | 3 losses) for the two-bucket
+    all-reduce: `late` = layer3 + layer4 of both encoders (their gradients are final first, 94 % of the
+    bytes) plus the loss tail, `early` = head + stem / layer1 / layer2.  cut_a / cut_v: arena offsets where
+    layer3 of the audio / visual encoder starts; end_a: where the audio group ends."""
+    assert 0 < cut_a < end_a < cut_v < grad.numel()
+    return dict(late=[grad[cut_a:end_a], grad[cut_v:]], early=[grad[:cut_a], grad[end_a:cut_v]])
+
+
+def allreduce_async(tensors, group=None):
+    """Start SUM all-reduces that run on the backend's own stream beside whatever the caller enqueues next;
+    returns the work handles (wait() makes the current stream — not the host — wait on NCCL)."""
+    return [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in tensors]
+
+
+def allreduce_finish(works, tensors, group=None):
+    """Join the asynchronous bucket, then all-reduce the remaining (small) tensors on the critical path."""
+    for w in works:
+        w.wait()
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)

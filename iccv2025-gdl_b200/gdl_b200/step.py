@@ -15,14 +15,21 @@ Parameters that never receive a gradient in the reference (ConcatFusion_DGL.fc_a
 GatedFusion_DGL.fc_x / fc_y — SURVEY.md §8a quirks 1-2) are left untouched: no weight decay,
 no momentum, exactly like torch.optim.SGD skipping `grad is None`.
 """
+import os
+
 import torch
 
-from . import ops
+from . import ops, parallel
 from .autograd import to_nhwc8  # noqa: F401  (re-export for callers)
 from .basic_model import AVClassifier_DGL
 from .fusion_modules import ConcatFusion_DGL, FiLM_DGL, GatedFusion_DGL, SumFusion_DGL
 
 _SEG_ALIGN = 64  # floats; keeps every tensor 256-byte aligned inside the arenas
+
+# Data parallel: all-reduce the gradients in two buckets, the first (layer3 + layer4 of both encoders, 94 % of
+# the bytes) on NCCL's stream WHILE layer2 / layer1 / stem are still being back-propagated (SURVEY.md §8e,
+# reference main_dgl.py:244 nn.DataParallel's reduce-add).  0 = one all-reduce after the whole backward.
+AR_OVERLAP = os.environ.get("GDL_AR_OVERLAP", "1") != "0"
 
 
 def _pad(n):
@@ -75,11 +82,22 @@ class ParamArena:
             self.param[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.param[o:o + n].view(p.shape)
             p.grad = self.grad[o:o + n].view(p.shape)
+        self.offset_of = {id(p): o for p, o in zip(self.params, self.offsets)}
         self.nseg = len(seg_end)
         self.seg_end = torch.tensor(seg_end, device=device, dtype=torch.int64)
         self.seg_group = torch.tensor(seg_group, device=device, dtype=torch.int32)
         self.seg_inv = torch.tensor(seg_inv, device=device, dtype=torch.float32)
         self.scratch = torch.empty(ops.optim_scratch_floats(off, self.nseg), device=device)
+
+    def late_split(self, gid, late_params):
+        """Offset where the `late_params` of group gid start, checked to be exactly the tail of the group
+        (module registration order: conv1, bn1, layer1 .. layer4)."""
+        start, end = self.group_ranges[gid]
+        cut = min(self.offset_of[id(p)] for p in late_params)
+        tail = {id(p) for p, o in zip(self.params, self.offsets) if cut <= o < end}
+        if tail != {id(p) for p in late_params} or not start < cut < end:
+            raise RuntimeError("late parameters are not a contiguous tail of their arena group")
+        return cut
 
 
 class DGLStep:
@@ -134,9 +152,18 @@ class DGLStep:
         self.stream_a, self.stream_v = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.steps_done = 0
         self._graph = None
+        self._graph_b = None
         self._graph_update = None
         self._graph_lr = None
         self.launches_per_step = None
+        # gradient buckets (views of the gradient arena; arena order: head | audio | visual)
+        self.overlap = AR_OVERLAP and world_size > 1
+        self._buckets = None
+        if self.overlap:
+            ar = self.arena
+            cut_a = ar.late_split(0, self.enc_a.late_parameters())
+            cut_v = ar.late_split(1, self.enc_v.late_parameters())
+            self._buckets = parallel.gradient_buckets(ar.grad, cut_a, ar.group_ranges[0][1], cut_v)
 
     # ------------------------------------------------------------------ heads
     def _init_head(self):
@@ -216,35 +243,45 @@ class DGLStep:
         self._stage_free[self._cur].record(main)
 
     def _enqueue(self, lr, first):
-        self._enqueue_compute()
-        if self.world_size > 1:
-            self._allreduce()
+        if self.overlap:
+            self._enqueue_compute(part=0)
+            works = self._allreduce_late()
+            self._enqueue_compute(part=1)
+            self._allreduce_finish(works)
+        else:
+            self._enqueue_compute()
+            if self.world_size > 1:
+                self._allreduce()
         self._enqueue_update(lr, first)
 
-    def _enqueue_compute(self):
-        """Forward + head + backward on the current stream (+ the two encoder streams)."""
+    def _enqueue_compute(self, part=None):
+        """Forward + head + backward on the current stream (+ the two encoder streams).
+        part=0: forward, head and the backward of layer4 + layer3; part=1: the rest of the backward."""
         B, T = self.B, self.T
         main = torch.cuda.current_stream()
         sa, sv = self.stream_a, self.stream_v
+        if part != 1:
+            sa.wait_stream(main)
+            sv.wait_stream(main)
+            with torch.cuda.stream(sa):
+                fa = self.enc_a.forward(self.a8)
+                ops.gap_fwd(fa, self.a_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
+            with torch.cuda.stream(sv):
+                fv = self.enc_v.forward(self.v8)
+                ops.gap_fwd(fv, self.v_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
+            main.wait_stream(sa)
+            main.wait_stream(sv)
+            self._head()
         sa.wait_stream(main)
         sv.wait_stream(main)
         with torch.cuda.stream(sa):
-            fa = self.enc_a.forward(self.a8)
-            ops.gap_fwd(fa, self.a_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
+            if part != 1:
+                ops.gap_bwd(self.da, self.enc_a.g_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
+            self.enc_a.backward(self.a8, part)
         with torch.cuda.stream(sv):
-            fv = self.enc_v.forward(self.v8)
-            ops.gap_fwd(fv, self.v_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
-        main.wait_stream(sa)
-        main.wait_stream(sv)
-        self._head()
-        sa.wait_stream(main)
-        sv.wait_stream(main)
-        with torch.cuda.stream(sa):
-            ops.gap_bwd(self.da, self.enc_a.g_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
-            self.enc_a.backward(self.a8)
-        with torch.cuda.stream(sv):
-            ops.gap_bwd(self.dv, self.enc_v.g_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
-            self.enc_v.backward(self.v8)
+            if part != 1:
+                ops.gap_bwd(self.dv, self.enc_v.g_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
+            self.enc_v.backward(self.v8, part)
         main.wait_stream(sa)
         main.wait_stream(sv)
 
@@ -253,6 +290,16 @@ class DGLStep:
         # full-batch mean (DataParallel gathers logits, main_dgl.py:102-104); BN stays per replica.
         # The 3 losses ride in the tail of the gradient arena (one collective per step).
         torch.distributed.all_reduce(self.arena.grad, group=self.pg)
+
+    def _allreduce_late(self):
+        """Bucket 1 (layer3 + layer4 of both encoders + the losses): issued asynchronously — NCCL's stream waits
+        for what the current stream has enqueued so far (the backward of those layers) and then runs beside
+        the kernels enqueued next (the backward of layer2 / layer1 / stem)."""
+        return parallel.allreduce_async(self._buckets["late"], self.pg)
+
+    def _allreduce_finish(self, works):
+        """Join bucket 1, then bucket 2 (head + the early layers, 6 % of the bytes) on the critical path."""
+        parallel.allreduce_finish(works, self._buckets["early"], self.pg)
 
     def _enqueue_update(self, lr, first):
         """Clip statistics + diagnostics + SGD + bf16 shadow refresh (after the all-reduce)."""
@@ -310,17 +357,29 @@ class DGLStep:
                         self._enqueue(self.lr, False)
                     self._graph_update = None
                 else:
-                    # NCCL stays outside the captured region: graph(compute) -> all-reduce -> graph(update)
+                    # NCCL stays outside the captured regions: graph(compute) -> all-reduce -> graph(update), or with
+                    # the overlapped buckets graph(fwd + late bwd) -> [NCCL bucket 1 || graph(early bwd)] ->
+                    # NCCL bucket 2 -> graph(update)
                     self._graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self._graph):
-                        self._enqueue_compute()
+                        self._enqueue_compute(part=0 if self.overlap else None)
+                    self._graph_b = None
+                    if self.overlap:
+                        self._graph_b = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(self._graph_b):
+                            self._enqueue_compute(part=1)
                     self._graph_update = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self._graph_update):
                         self._enqueue_update(self.lr, False)
                 self._graph_lr = self.lr
                 # capture does not execute: the replay below runs this step
             self._graph.replay()
-            if self._graph_update is not None:
+            if self._graph_b is not None:
+                works = self._allreduce_late()
+                self._graph_b.replay()
+                self._allreduce_finish(works)
+                self._graph_update.replay()
+            elif self._graph_update is not None:
                 self._allreduce()
                 self._graph_update.replay()
         self.steps_done += 1

@@ -82,6 +82,13 @@ int gdl_conv_fwd_stats(const gdl_conv_desc* d, const void* x, const void* w_pack
 /* Fused statistics are used for convolutions with R*S*Ci >= k (default: never — on the bench geometry the
  * epilogue cost equals what the separate kernel costs); k < 0 restores the default.  Returns the old value. */
 int gdl_set_fused_stats_min_k(int k);
+/* Scheduling hint for the calling thread (no reference counterpart: the reference's kernels are cuDNN's):
+ * reverse != 0 makes the following gdl_conv_fwd / gdl_conv_dgrad (flat kernels), gdl_bn_stats, gdl_bn_apply,
+ * gdl_bn_bwd and gdl_bn_bwd_nores launches walk their pixel range in DESCENDING order (two-pass operations run
+ * their second pass opposite to the first).  A pass that runs opposite to the pass that last touched a tensor
+ * starts on the part still resident in L2.  Element-wise results are unaffected; reductions keep one fixed
+ * summation order per setting (deterministic).  Returns the previous setting. */
+int gdl_set_sweep(int reverse);
 /* dx[N,Hi,Wi,Ci] = conv_transpose(dy, w) (+ add_src).  add_mode: 0 none, 1 add_src has the
  * shape of dx (residual gradient), 2 add_src is [N,ceil(Hi/2),ceil(Wi/2),Ci] and is added at
  * even (h,w) only (gradient of a 1x1 stride-2 downsample branch). */

@@ -70,3 +70,64 @@ def test_shard_range_covers_batch():
                 lo, hi = shard_range(r, world, B)
                 rows += list(range(lo, hi))
             assert rows == list(range(B))
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "iccv2025-gdl_b200"))
+    from gdl_b200.parallel import allreduce_async, allreduce_finish, gradient_buckets
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(5000 + 64, generator=g)
+    whole = flat.clone()
+    b = gradient_buckets(flat, 700, 2100, 3900)
+    works = allreduce_async(b["late"])          # bucket 1 in flight ...
+    flat[:700].mul_(1.0)                        # ... while the "early" gradients are still being produced
+    allreduce_finish(works, b["early"])
+    dist.all_reduce(whole)
+    if rank == 0:
+        torch.save({"bucketed": flat, "whole": whole}, os.path.join(out_dir, "buckets.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_bucket_allreduce_equals_one_allreduce(tmp_path):
+    """The overlapped two-bucket exchange covers the arena exactly once."""
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_bucket_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "buckets.pt"))
+    assert torch.equal(got["bucketed"], got["whole"])
+
+
+def test_late_bucket_is_a_contiguous_tail_of_each_encoder():
+    """ParamArena.late_split: layer3 + layer4 form the tail of each encoder's arena group, and the four
+    bucket views partition the gradient arena (incl. the loss tail) without overlap."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "iccv2025-gdl_b200"))
+    import gdl_b200
+    from gdl_b200.parallel import gradient_buckets
+    from gdl_b200.step import ParamArena
+    args = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modality="full")
+    gdl_b200.setup_seed(0)
+    model = gdl_b200.AVClassifier_DGL(args)
+    arena = ParamArena(model, torch.device("cpu"))
+    cuts = []
+    for gid, net in ((0, model.audio_net), (1, model.visual_net)):
+        late = [p for n, p in net.named_parameters() if n.startswith(("layer3.", "layer4."))]
+        cut = arena.late_split(gid, late)
+        start, end = arena.group_ranges[gid]
+        frac = (end - cut) / (end - start)
+        assert 0.9 < frac < 0.96, frac  # layer3 + layer4 hold ~94 % of a ResNet-18 encoder
+        cuts.append(cut)
+    b = gradient_buckets(arena.grad, cuts[0], arena.group_ranges[0][1], cuts[1])
+    arena.grad.zero_()
+    for t in b["late"] + b["early"]:
+        t.add_(1.0)
+    assert torch.equal(arena.grad, torch.ones_like(arena.grad))
+    # a set that is not a tail is rejected
+    try:
+        arena.late_split(0, [p for n, p in model.audio_net.named_parameters() if n.startswith("layer2.")])
+    except RuntimeError:
+        pass
+    else:
+        raise AssertionError("late_split accepted a non-tail parameter set")
