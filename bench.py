@@ -329,6 +329,16 @@ def roofline_pass(step, torch, ops, B):
             "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
             "peak_source": how, "share_of_step": round(ms / total, 4),
             "avg_launch_ms": ms / nl, "flops_per_launch": flops / nl}
+    # DRAM traffic per launch of the same kernels, from the committed ncu capture of this workload (ncu cannot run
+    # inside a timed bench): bytes, averaged over the launches like `achieved`; null for other workloads.
+    tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        crema = (step.F_, step.Tt, step.T) == (257, 188, 3)  # the capture is of the CREMA-D-shape workload
+        if crema and t.get("batch") == B and abs(t.get("launches_per_step", 0) - nl) <= 2:
+            roof["traffic"] = t["dram_bytes_per_launch"]
+            roof["traffic_unit"] = "bytes of DRAM read+write per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            roof["traffic_source"] = "profiles/r1_conv_traffic.json: " + t["source"]
     return roof, breakdown
 
 

@@ -65,6 +65,23 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   return r;
 }
 
+// Same, but allocating in L1 (neighbouring threads re-read the line).  volatile: a batch of these stays a batch
+// (the compiler does not sink each load to its first use), which is what puts several requests in flight.
+__device__ __forceinline__ uint4 ld_keep16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint2 ld_keep8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 32-byte (256-bit) global accesses (sm_100: LDG/STG.256): one full sector per lane, half the memory
 // instructions of 16-byte vectors for thread-per-row access patterns.  p must be 32-byte aligned.
 struct U32B {

@@ -487,17 +487,23 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 // (64x64x9 = 36 k outputs, up to 148 splits) spread it over G thread groups: group g sums splits g, g+G, ...
 // four loads in flight, and thread group 0 combines the G partial sums in ascending g — a fixed order, so the
 // result is deterministic (reference utils.py:12 cudnn.deterministic).  Reads are coalesced over k = (tap, ci).
+struct TapSplits {
+  int n[9];  // splits that wrote tap t's partials (parity planes of a stride-2 conv get different counts)
+};
 template <int G>
 __global__ void __launch_bounds__(256) wgrad_reduce_t_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                                             int splits, int Kp, int Co, int Ci, int taps) {
+                                                             const TapSplits ts, int Kp, int Co, int Ci, int taps) {
   constexpr int OB = 256 / G;  // outputs per block
   __shared__ float red[G > 1 ? 256 : 1];
   const int o = threadIdx.x % OB, g = threadIdx.x / OB;
   const int64_t total = (int64_t)Co * Kp;
   const int64_t idx = (int64_t)blockIdx.x * OB + o;  // (co, k), k fastest
   float acc = 0.f;
+  const int co = int(idx / Kp), k = int(idx - (int64_t)co * Kp);
+  const int tap = k / Ci, ci = k - tap * Ci;
   if (idx < total) {
     const float* src = partial + idx;
+    const int splits = ts.n[tap];
     int sp = g;
     for (; sp + 3 * G < splits; sp += 4 * G) {
       const float a0 = src[(size_t)sp * total], a1 = src[(size_t)(sp + G) * total];
@@ -517,20 +523,18 @@ __global__ void __launch_bounds__(256) wgrad_reduce_t_kernel(const float* __rest
     for (int j = 1; j < G; ++j) acc += red[j * OB + o];
   }
   if (idx >= total) return;
-  const int co = int(idx / Kp), k = int(idx - (int64_t)co * Kp);
-  const int tap = k / Ci, ci = k - tap * Ci;
   dw[((size_t)co * Ci + ci) * taps + tap] = acc;
 }
 
-static int launch_wgrad_reduce_t(const float* partial, float* dw, int splits, int Kp, int Co, int Ci, int taps,
-                                 cudaStream_t s) {
+static int launch_wgrad_reduce_t(const float* partial, float* dw, int splits, const TapSplits& ts, int Kp, int Co,
+                                 int Ci, int taps, cudaStream_t s) {
   const int64_t total = (int64_t)Co * Kp;
   if (total < 400000 && splits >= 16) {
-    wgrad_reduce_t_kernel<8><<<(unsigned)ceil_div64(total, 32), 256, 0, s>>>(partial, dw, splits, Kp, Co, Ci, taps);
+    wgrad_reduce_t_kernel<8><<<(unsigned)ceil_div64(total, 32), 256, 0, s>>>(partial, dw, ts, Kp, Co, Ci, taps);
   } else if (total < 800000 && splits >= 8) {
-    wgrad_reduce_t_kernel<4><<<(unsigned)ceil_div64(total, 64), 256, 0, s>>>(partial, dw, splits, Kp, Co, Ci, taps);
+    wgrad_reduce_t_kernel<4><<<(unsigned)ceil_div64(total, 64), 256, 0, s>>>(partial, dw, ts, Kp, Co, Ci, taps);
   } else {
-    wgrad_reduce_t_kernel<1><<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(partial, dw, splits, Kp, Co, Ci, taps);
+    wgrad_reduce_t_kernel<1><<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(partial, dw, ts, Kp, Co, Ci, taps);
   }
   GDL_CHECK_LAUNCH("wgrad_reduce_t_kernel");
   return GDL_OK;
@@ -654,7 +658,8 @@ static bool prefer_flat_s1(int H, int W) {
 // conv_wgrad_flat.cu
 int64_t wgrad_flat_workspace_bytes(int N, int Ho, int Wo, int Ci, int Co, int R, int stride);
 int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R, int stride, const void* x,
-                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed);
+                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed,
+                   int* tap_splits);
 // GDL_WFLAT: 0 off, 1 where the halo wgrad kernel is not eligible or its 16x8 tiles are poorly filled, 2 always
 // (default: measured equal or faster than the halo kernel on every layer of the bench geometry).
 static int wflat_policy() {
@@ -862,12 +867,14 @@ extern "C" int gdl_conv_wgrad(const gdl_conv_desc* d, int ci_real, const void* x
       const char* e = getenv("GDL_WGRAD_T");
       return e ? atoi(e) : 1;
     }();
+    TapSplits ts;
+    for (int i = 0; i < 9; ++i) ts.n[i] = 0;
     int ns = try_wgrad_flat(d->N, d->Hi, d->Wi, d->Ho, d->Wo, d->Ci, d->Co, d->R, d->stride, x, dy, (float*)workspace,
-                            workspace_bytes, (cudaStream_t)s, tr);
+                            workspace_bytes, (cudaStream_t)s, tr, tr ? ts.n : nullptr);
     if (ns < 0) return ns;
     if (ns > 0) {
       int Kp = d->R * d->S * d->Ci;
-      if (tr) return launch_wgrad_reduce_t((const float*)workspace, dw_oihw, ns, Kp, d->Co, d->Ci, d->R * d->S,
+      if (tr) return launch_wgrad_reduce_t((const float*)workspace, dw_oihw, ns, ts, Kp, d->Co, d->Ci, d->R * d->S,
                                            (cudaStream_t)s);
       int64_t total = (int64_t)Kp * d->Co;
       wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)s>>>(

@@ -52,7 +52,8 @@ struct WfParams {
   int ci_tiles, co_tiles;
   int NI, RB, nbands;   // stage = NI whole images (nbands == 1, RB == Ho+1) or one RB-row band of one image
   int ksteps;           // ceil(stage pixels / 16)
-  int tiles_total, tiles_per_split;
+  int tiles_total;
+  int tps[4];           // tiles per split-K CTA of each job type (types with more taps get more, shorter, splits)
   int xwin_bytes, dywin_bytes, stage_bytes, stages;
   uint32_t tx_bytes;
   int smem_bytes;
@@ -71,10 +72,11 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   const int tid = threadIdx.x, warp = warp_uniform_idx();
   const int ST = p.stages;
-  const int t0 = blockIdx.x * p.tiles_per_split;
-  const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
   int y = blockIdx.y;
   const int type = y % p.ntypes;
+  const int t0 = min(blockIdx.x * p.tps[type], p.tiles_total);
+  const int t1 = min(t0 + p.tps[type], p.tiles_total);
+  if (t0 >= t1) return;  // this type has fewer splits than the grid is wide (whole CTA, before any setup)
   y /= p.ntypes;
   const int co0 = (y % p.co_tiles) * BN;
   const int ci0 = (y / p.co_tiles) * (NS * 64);
@@ -236,7 +238,8 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
 // host side
 // ------------------------------------------------------------------------------------------
 struct WfPlan {
-  int mode, BN, ntypes, ci_tiles, co_tiles, gy, splits, tiles_total, tiles_per_split;
+  int mode, BN, ntypes, ci_tiles, co_tiles, gy, splits, tiles_total;
+  int tps[4], nsplit[4];  // per job type: tiles per CTA, number of split-K CTAs (splits = max nsplit)
   int xwin_bytes, dywin_bytes, stage_bytes, stages, P, taps;
   int NI, RB, nbands, ksteps, xrows, dyrows, rspan;
   WfJobType jt[4];
@@ -373,11 +376,39 @@ static bool plan_wgrad_flat(int N, int Ho, int Wo, int Ci, int Co, int R, int st
     const int v = e ? atoi(e) : 1;
     return v < 1 ? 1 : (v > 4 ? 4 : v);
   }();
-  int splits = (waves * kNumSMs) / w.gy;
-  if (splits < 1) splits = 1;
-  if (splits > w.tiles_total) splits = w.tiles_total;
-  w.tiles_per_split = (w.tiles_total + splits - 1) / splits;
-  w.splits = (w.tiles_total + w.tiles_per_split - 1) / w.tiles_per_split;
+  // Split-K CTAs per job type, proportional to the type's MMA work per tile (its accumulator count): the
+  // parity planes of a stride-2 convolution carry 4 / 2 / 2 / 1 taps, and with equal splits the 1-tap CTAs
+  // would idle for 3/4 of the kernel.  GDL_WGRAD_BALANCE=0 restores equal splits.
+  static const int balance = []() {
+    const char* e = getenv("GDL_WGRAD_BALANCE");
+    return e ? atoi(e) : 1;
+  }();
+  const int groups = w.ci_tiles * w.co_tiles;
+  int cta_budget = (waves * kNumSMs) / groups;  // CTAs of one (ci, co) tile over all types
+  if (cta_budget < w.ntypes) cta_budget = w.ntypes;
+  int wsum = 0;
+  for (int k = 0; k < w.ntypes; ++k) wsum += w.jt[k].nunits;
+  int used = 0;
+  for (int k = 0; k < w.ntypes; ++k) {
+    int sk = balance ? cta_budget * w.jt[k].nunits / wsum : cta_budget / w.ntypes;
+    if (sk < 1) sk = 1;
+    w.nsplit[k] = sk;
+    used += sk;
+  }
+  while (balance && used < cta_budget) {  // hand the remainder to the type with the most work per CTA
+    int best_k = 0;
+    for (int k = 1; k < w.ntypes; ++k)
+      if ((int64_t)w.jt[k].nunits * w.nsplit[best_k] > (int64_t)w.jt[best_k].nunits * w.nsplit[k]) best_k = k;
+    ++w.nsplit[best_k];
+    ++used;
+  }
+  w.splits = 0;
+  for (int k = 0; k < w.ntypes; ++k) {
+    int sk = w.nsplit[k] > w.tiles_total ? w.tiles_total : w.nsplit[k];
+    w.tps[k] = (w.tiles_total + sk - 1) / sk;
+    w.nsplit[k] = (w.tiles_total + w.tps[k] - 1) / w.tps[k];
+    if (w.nsplit[k] > w.splits) w.splits = w.nsplit[k];
+  }
   return true;
 }
 
@@ -406,8 +437,11 @@ int64_t wgrad_flat_workspace_bytes(int N, int Ho, int Wo, int Ci, int Co, int R,
 // x is the conv INPUT [N,Hi,Wi,Ci]; dy the output gradient [N,Ho,Wo,Co].  Returns the number of splits
 // written (>0) when handled, 0 when not eligible, <0 on error.
 // transposed != 0: partials are written [split][Co][Kp] (coalesced epilogue stores), else [split][Kp][Co].
+// tap_splits (optional, R*R ints): how many splits wrote each tap's partials (taps of different parity planes
+// may have different split counts; the return value is the maximum).
 int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R, int stride, const void* x,
-                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed) {
+                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed,
+                   int* tap_splits) {
   WfPlan w;
   if (!plan_wgrad_flat(N, Ho, Wo, Ci, Co, R, stride, w)) return 0;
   if (workspace_bytes < (int64_t)w.splits * w.taps * Ci * Co * (int64_t)sizeof(float)) return 0;
@@ -442,7 +476,14 @@ int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R,
   for (int i = 0; i < 4; ++i) p.jt[i] = w.jt[i];
   p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles;
   p.NI = w.NI; p.RB = w.RB; p.nbands = w.nbands; p.ksteps = w.ksteps;
-  p.tiles_total = w.tiles_total; p.tiles_per_split = w.tiles_per_split;
+  p.tiles_total = w.tiles_total;
+  for (int k = 0; k < 4; ++k) p.tps[k] = w.tps[k];
+  if (tap_splits != nullptr)
+    for (int k = 0; k < w.ntypes; ++k)
+      for (int u = 0; u < w.jt[k].nunits; ++u) {
+        tap_splits[w.jt[k].u[u].tap0] = w.nsplit[k];
+        if (w.jt[k].u[u].tap1 >= 0) tap_splits[w.jt[k].u[u].tap1] = w.nsplit[k];
+      }
   p.xwin_bytes = w.xwin_bytes; p.dywin_bytes = w.dywin_bytes; p.stage_bytes = w.stage_bytes; p.stages = w.stages;
   const int NS = w.mode == 0 ? 1 : 2, NB = w.BN / 64;
   p.tx_bytes = (uint32_t)((NS * w.xrows + NB * w.dyrows) * w.NI * w.P * 128);

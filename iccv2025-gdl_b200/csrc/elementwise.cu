@@ -3,6 +3,7 @@
 // the BN passes, MaxPool 3x3/s2, global average pooling.  All activations NHWC bf16, 16-byte
 // vector accesses, fp32 math, deterministic fixed-order reductions (per-block partials reduced
 // by a finalize kernel; no float atomics — reference utils/utils.py:12 asks for determinism).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gdl {
@@ -603,6 +604,120 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(
   }
 }
 
+// Forward on 2x2 blocks of OUTPUT pixels (8 channels per thread): the four 3x3/s2 windows of a block cover a 5x5
+// input patch, so BN+ReLU+rounding is evaluated 25 times for 4 outputs instead of 36, two channels per
+// cvt.rn.relu.bf16x2, and the running (max, first arg-max) pair is ONE unsigned max per candidate: the rounded
+// activation is a non-negative bf16, so its fp32 bit pattern orders like the value and has 16 free low bits,
+// which hold 15 - tap — equal values keep the smallest tap, the "first maximum in scan order" rule of ATen's
+// max-pool.  (The per-output kernel above spends 8 instructions per candidate and was issue-bound: 64 % SM
+// issue utilisation at 24 % of DRAM bandwidth.)  The conv output at the arg-max is re-read (an L1 hit).
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float hi, float lo) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r & 0x7fff7fffu;  // -0 -> +0: the keys below compare as unsigned integers
+}
+
+__global__ void __launch_bounds__(256) bn_relu_maxpool_fwd2_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+    bf16* __restrict__ y, uint8_t* __restrict__ amax, bf16* __restrict__ xmax, int N, int H, int W, int C, int Ho,
+    int Wo) {
+  __shared__ float s_scale[512], s_shift[512];
+  __shared__ int s_tapoff[16];  // element offset of tap (r,s) from the window's top-left pixel
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_scale[c] = scale[c];
+    s_shift[c] = shift[c];
+  }
+  if (threadIdx.x < 9) s_tapoff[threadIdx.x] = ((threadIdx.x / 3) * W + threadIdx.x % 3) * C;
+  __syncthreads();
+  const int groups = C / 8;
+  const int HB = (Ho + 1) / 2, WB = (Wo + 1) / 2;
+  // 32-bit index arithmetic: the launcher checks that every element index of x fits in an int
+  const int total = N * HB * WB * groups;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cg = i % groups;
+    int t = i / groups;
+    const int wb = t % WB;
+    t /= WB;
+    const int hb = t % HB;
+    const int n = t / HB;
+    float sc[8], sh[8];
+    uint32_t key[2][2][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      sc[c] = s_scale[cg * 8 + c];
+      sh[c] = s_shift[cg * 8 + c];
+      key[0][0][c] = key[0][1][c] = key[1][0][c] = key[1][1][c] = 0u;
+    }
+    const int h0 = 4 * hb - 1, w0 = 4 * wb - 1;
+    const bf16* xn = x + (int64_t)n * H * W * C + cg * 8;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int h = h0 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const int w = w0 + s;
+        if (w < 0 || w >= W) continue;
+        const uint4 u = *reinterpret_cast<const uint4*>(xn + (h * W + w) * C);
+        const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float f0 = __uint_as_float(wd[j] << 16), f1 = __uint_as_float(wd[j] & 0xffff0000u);
+          const uint32_t pk = relu_pack_bf16x2(fmaf(f1, sc[2 * j + 1], sh[2 * j + 1]), fmaf(f0, sc[2 * j], sh[2 * j]));
+          const uint32_t k0 = pk << 16, k1 = pk & 0xffff0000u;
+#pragma unroll
+          for (int oy = 0; oy < 2; ++oy) {
+            if (r < 2 * oy || r > 2 * oy + 2) continue;
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox) {
+              if (s < 2 * ox || s > 2 * ox + 2) continue;
+              const uint32_t tag = 15u - uint32_t((r - 2 * oy) * 3 + (s - 2 * ox));
+              key[oy][ox][2 * j] = max(key[oy][ox][2 * j], k0 | tag);
+              key[oy][ox][2 * j + 1] = max(key[oy][ox][2 * j + 1], k1 | tag);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy) {
+      const int ho = 2 * hb + oy;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox) {
+        const int wo = 2 * wb + ox;
+        if (wo >= Wo) continue;
+        const int64_t off = (int64_t)((n * Ho + ho) * Wo + wo) * C + cg * 8;
+        uint4 yv;
+        uint32_t* yw = reinterpret_cast<uint32_t*>(&yv);
+        uint32_t tap[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) tap[c] = 15u - (key[oy][ox][c] & 15u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yw[j] = (key[oy][ox][2 * j] >> 16) | (key[oy][ox][2 * j + 1] & 0xffff0000u);
+        *reinterpret_cast<uint4*>(y + off) = yv;
+        uint2 packed;
+        packed.x = tap[0] | (tap[1] << 8) | (tap[2] << 16) | (tap[3] << 24);
+        packed.y = tap[4] | (tap[5] << 8) | (tap[6] << 16) | (tap[7] << 24);
+        *reinterpret_cast<uint2*>(amax + off) = packed;
+        if (xmax != nullptr) {
+          // conv output at the arg-max: re-read (L1 hit) through the tap-offset table
+          const unsigned short* xw = reinterpret_cast<const unsigned short*>(xn) + ((2 * ho - 1) * W + (2 * wo - 1)) * C;
+          uint32_t xb[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) xb[c] = xw[s_tapoff[tap[c]] + c];
+          uint4 xv;
+          xv.x = xb[0] | (xb[1] << 16);
+          xv.y = xb[2] | (xb[3] << 16);
+          xv.z = xb[4] | (xb[5] << 16);
+          xv.w = xb[6] | (xb[7] << 16);
+          *reinterpret_cast<uint4*>(xmax + off) = xv;
+        }
+      }
+    }
+  }
+}
+
 // Backward works on 2x2 blocks of stem pixels (rows 2i,2i+1 x cols 2j,2j+1; 8 channels per thread): the
 // block is covered by the four pooling windows (i,j), (i,j+1), (i+1,j), (i+1,j+1), and which tap of which
 // window each of the four pixels is follows from the parities alone, so one thread loads 4 windows for 4
@@ -611,41 +726,55 @@ struct PoolWin {
   float g[8];
   uint32_t a0, a1;  // 8 one-byte arg-max indices
 };
-__device__ __forceinline__ void load_win(const bf16* __restrict__ gpool, const uint8_t* __restrict__ amax,
-                                         int64_t off, bool ok, PoolWin& w) {
-  if (ok) {
-    unpack8(*reinterpret_cast<const uint4*>(gpool + off), w.g);
-    const uint2 am = *reinterpret_cast<const uint2*>(amax + off);
-    w.a0 = am.x;
-    w.a1 = am.y;
-  } else {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) w.g[c] = 0.f;
-    w.a0 = w.a1 = 0xffffffffu;  // matches no tap
-  }
-}
 __device__ __forceinline__ float win_pick(const PoolWin& w, int c, int tap) {
   const uint32_t word = c < 4 ? w.a0 : w.a1;
   return ((word >> ((c & 3) * 8)) & 0xffu) == (uint32_t)tap ? w.g[c] : 0.f;
 }
 // dy (gradient wrt relu output) of the four pixels of block (i,j): p[0]=(2i,2j) p[1]=(2i,2j+1) p[2]=(2i+1,2j) p[3]=(2i+1,2j+1).
 // Summation order per pixel = ascending (ho, wo), the order of the unfused max-pool backward.
-__device__ __forceinline__ void block_pool_grad(const bf16* __restrict__ gpool, const uint8_t* __restrict__ amax,
-                                                int n, int i, int j, int cg, int C, int Ho, int Wo,
-                                                float (&p)[4][8]) {
+// All loads of a block — four pooling windows (gradient + arg-max bytes) and the four stem pixels — are issued
+// UNCONDITIONALLY on clamped addresses before anything is consumed (a window / pixel outside the map is masked
+// afterwards): with a branch around each load the kernel had one request in flight per thread (2.6 TB/s).
+struct PoolBlock {
   PoolWin w00, w01, w10, w11;
+  uint4 xq[4];
+  bool okq[4];
+  int64_t offq[4];
+};
+__device__ __forceinline__ void set_win(PoolWin& w, const uint4& g, const uint2& am, bool ok) {
+  unpack8(g, w.g);
+  w.a0 = ok ? am.x : 0xffffffffu;  // 0xff matches no tap
+  w.a1 = ok ? am.y : 0xffffffffu;
+}
+__device__ __forceinline__ void load_block(const bf16* __restrict__ gpool, const uint8_t* __restrict__ amax,
+                                           const bf16* __restrict__ x, int n, int i, int j, int cg, int C, int H,
+                                           int W, int Ho, int Wo, PoolBlock& b) {
   const int64_t base = (((int64_t)n * Ho + i) * Wo + j) * C + cg * 8;
   const bool okj = j + 1 < Wo, oki = i + 1 < Ho;
-  load_win(gpool, amax, base, true, w00);
-  load_win(gpool, amax, base + C, okj, w01);
-  load_win(gpool, amax, base + (int64_t)Wo * C, oki, w10);
-  load_win(gpool, amax, base + (int64_t)Wo * C + C, oki && okj, w11);
+  const int64_t dj = okj ? C : 0, di = oki ? (int64_t)Wo * C : 0;
+  const uint4 g00 = ld_keep16(gpool + base), g01 = ld_keep16(gpool + base + dj);
+  const uint4 g10 = ld_keep16(gpool + base + di), g11 = ld_keep16(gpool + base + di + dj);
+  const uint2 a00 = ld_keep8(amax + base), a01 = ld_keep8(amax + base + dj);
+  const uint2 a10 = ld_keep8(amax + base + di), a11 = ld_keep8(amax + base + di + dj);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int h = 2 * i + (q >> 1), w = 2 * j + (q & 1);
+    b.okq[q] = h < H && w < W;
+    b.offq[q] = (((int64_t)n * H + min(h, H - 1)) * W + min(w, W - 1)) * C + cg * 8;
+    b.xq[q] = ld_stream16(x + b.offq[q]);
+  }
+  set_win(b.w00, g00, a00, true);
+  set_win(b.w01, g01, a01, okj);
+  set_win(b.w10, g10, a10, oki);
+  set_win(b.w11, g11, a11, oki && okj);
+}
+__device__ __forceinline__ void block_pool_grad(const PoolBlock& b, float (&p)[4][8]) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    p[0][c] = win_pick(w00, c, 4);
-    p[1][c] = win_pick(w00, c, 5) + win_pick(w01, c, 3);
-    p[2][c] = win_pick(w00, c, 7) + win_pick(w10, c, 1);
-    p[3][c] = ((win_pick(w00, c, 8) + win_pick(w01, c, 6)) + win_pick(w10, c, 2)) + win_pick(w11, c, 0);
+    p[0][c] = win_pick(b.w00, c, 4);
+    p[1][c] = win_pick(b.w00, c, 5) + win_pick(b.w01, c, 3);
+    p[2][c] = win_pick(b.w00, c, 7) + win_pick(b.w10, c, 1);
+    p[3][c] = ((win_pick(b.w00, c, 8) + win_pick(b.w01, c, 6)) + win_pick(b.w10, c, 2)) + win_pick(b.w11, c, 0);
   }
 }
 
@@ -673,18 +802,18 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_maxpool_bwd_reduce_kernel(
     const int j = int(b % Wo);
     const int64_t t = b / Wo;
     const int i = int(t % Ho), n = int(t / Ho);
+    PoolBlock blk;
+    load_block(gpool, amax, x, n, i, j, cg, C, H, W, Ho, Wo, blk);
     float p[4][8];
-    block_pool_grad(gpool, amax, n, i, j, cg, C, Ho, Wo, p);
+    block_pool_grad(blk, p);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int h = 2 * i + (q >> 1), w = 2 * j + (q & 1);
-      if (h >= H || w >= W) continue;
       float xv[8];
-      unpack8(ld_stream16(x + (((int64_t)n * H + h) * W + w) * C + cg * 8), xv);
+      unpack8(blk.xq[q], xv);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         // the pooled gradient was stored in bf16 by the unfused path; keep that rounding point
-        const float gz = fmaf(xv[c], sc[c], sh[c]) > 0.f ? bf16_round(p[q][c]) : 0.f;
+        const float gz = (blk.okq[q] && fmaf(xv[c], sc[c], sh[c]) > 0.f) ? bf16_round(p[q][c]) : 0.f;
         acc[0][c] += gz;
         acc[1][c] = fmaf(gz, (xv[c] - mu[c]) * is[c], acc[1][c]);
       }
@@ -714,27 +843,44 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_apply_kernel(
   const int64_t total = (int64_t)N * Ho * Wo * groups;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
+    {  // L2 prefetch of the four stem pixels of this thread's NEXT iteration (ptxas sinks three of the four
+       // x loads of load_block behind the stores; a full iteration of lead hides their DRAM latency)
+      const int64_t idx2 = idx + (int64_t)gridDim.x * blockDim.x;
+      if (idx2 < total) {
+        const int64_t b2 = idx2 / groups;
+        const int cg2 = int(idx2 - b2 * groups);
+        const int j2 = int(b2 % Wo);
+        const int64_t t2 = b2 / Wo;
+        const int i2 = int(t2 % Ho);
+        const bf16* xb = x + (((t2 / Ho) * H + min(2 * i2, H - 1)) * W + min(2 * j2, W - 1)) * C + cg2 * 8;
+        const int64_t dw = 2 * j2 + 1 < W ? C : 0, dh = 2 * i2 + 1 < H ? (int64_t)W * C : 0;
+        prefetch_l2(xb);
+        prefetch_l2(xb + dw);
+        prefetch_l2(xb + dh);
+        prefetch_l2(xb + dh + dw);
+      }
+    }
     const int cg = int(idx % groups);
     const int64_t b = idx / groups;
     const int j = int(b % Wo);
     const int64_t t = b / Wo;
     const int i = int(t % Ho), n = int(t / Ho);
+    PoolBlock blk;
+    load_block(gpool, amax, x, n, i, j, cg, C, H, W, Ho, Wo, blk);
     float p[4][8];
-    block_pool_grad(gpool, amax, n, i, j, cg, C, Ho, Wo, p);
+    block_pool_grad(blk, p);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int h = 2 * i + (q >> 1), w = 2 * j + (q & 1);
-      if (h >= H || w >= W) continue;
-      const int64_t off = (((int64_t)n * H + h) * W + w) * C + cg * 8;
+      const int64_t off = blk.offq[q];
       float xv[8], o[8];
-      unpack8(ld_stream16(x + off), xv);
+      unpack8(blk.xq[q], xv);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int ch = cg * 8 + c;
         const float gz = fmaf(xv[c], s_sc[ch], s_sh[ch]) > 0.f ? bf16_round(p[q][c]) : 0.f;
         o[c] = fmaf(s_a[ch], gz, fmaf(s_b[ch], xv[c], s_c[ch]));
       }
-      *reinterpret_cast<uint4*>(dx + off) = pack8(o);
+      if (blk.okq[q]) *reinterpret_cast<uint4*>(dx + off) = pack8(o);
     }
   }
 }
@@ -902,6 +1048,19 @@ extern "C" int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const 
                                        gdl_stream_t s) {
   GDL_REQUIRE(x && scale && shift && y && argmax, "gdl_bn_relu_maxpool_fwd: null pointer");
   GDL_REQUIRE(chan_ok(C) && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_bn_relu_maxpool_fwd: bad shape");
+  // GDL_STEM_TAIL: 2 (default) = one thread per 2x2 output block with packed max/arg-max keys, 1 = one thread per output
+  static const int variant = []() {
+    const char* e = getenv("GDL_STEM_TAIL");
+    return e ? atoi(e) : 2;
+  }();
+  if (variant >= 2 && (int64_t)N * H * W * C < ((int64_t)1 << 31)) {  // the v2 kernel indexes with 32-bit integers
+    int64_t total2 = (int64_t)N * ((Ho + 1) / 2) * ((Wo + 1) / 2) * (C / 8);
+    bn_relu_maxpool_fwd2_kernel<<<ew_grid(total2, 256, GDL_RESIDENT(bn_relu_maxpool_fwd2_kernel, 256)), 256, 0,
+                                  (cudaStream_t)s>>>((const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H,
+                                                     W, C, Ho, Wo);
+    GDL_CHECK_LAUNCH("bn_relu_maxpool_fwd2_kernel");
+    return GDL_OK;
+  }
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
   bn_relu_maxpool_fwd_kernel<<<ew_grid(total, 256, GDL_RESIDENT(bn_relu_maxpool_fwd_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
       (const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H, W, C, Ho, Wo);

@@ -22,7 +22,8 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
                   int* stats_rows = nullptr);
 int64_t wgrad_flat_workspace_bytes(int N, int Ho, int Wo, int Ci, int Co, int R, int stride);
 int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R, int stride, const void* x,
-                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed);
+                   const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed,
+                   int* tap_splits);
 
 constexpr int kGemmW = 128;  // the GEMM row index is folded into an (H, 128) "image"
 
@@ -236,7 +237,7 @@ extern "C" int gdl_gemm_tn_f32(const void* At, const void* Bt, const float* bias
   GDL_REQUIRE(K > 0 && K % kGemmW == 0 && N % 4 == 0, "gdl_gemm_tn_f32: need K % 128 == 0");
   const int H = int(K / kGemmW);
   int ns = try_wgrad_flat(1, H, kGemmW, H, kGemmW, M, N, 1, 1, At, Bt, (float*)workspace, workspace_bytes,
-                          (cudaStream_t)s, 0);
+                          (cudaStream_t)s, 0, nullptr);
   if (ns < 0) return ns;
   if (ns == 0) {
     set_last_error("gdl_gemm_tn_f32: shape not supported (M, N multiples of 128 or M == 64) or workspace too small");
