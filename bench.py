@@ -191,18 +191,21 @@ def run_gpu(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n_steps, e2e):
+    def host_prefetch():
+        step.prefetch(spec_h, image_h, label_h)
+
+    def timed(n_steps, e2e, prefetch=host_prefetch):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         if e2e:
-            step.prefetch(spec_h, image_h, label_h)          # batch 0: its copy is not overlapped
+            prefetch()                                       # batch 0: its copy is not overlapped
         for i in range(n_steps):
             if e2e:
                 step.step()                                  # consumes the prefetched batch i
                 if i + 1 < n_steps:
-                    step.prefetch(spec_h, image_h, label_h)  # H2D of batch i+1 overlaps step i (copy stream)
+                    prefetch()                               # H2D of batch i+1 overlaps step i (copy stream)
                 step.read_stats()          # D2H of the step's result (7 floats), syncs the step
             else:
                 step.step()
@@ -241,6 +244,36 @@ def run_gpu(a):
     ms_e2e, _ = timed(a.steps, e2e=True)
     stats = step.read_stats()
 
+    # Same end-to-end loop with the visual transform on the device: decoded uint8 frames
+    # resident in HBM, per step the host uploads the spectrograms, the labels and the crop boxes it drew
+    # (24 bytes per frame); gdl_crop_resize_normalize produces the fp32 frames on the copy stream.
+    dp = None
+    if (H, W) == (224, 224) and not a.no_device_pipeline:
+        from gdl_b200.datapipe import DeviceFrameStore, VisualPipeline, draw_frame_params
+        fh, fw = (360, 480) if a.dataset == "CREMAD" else (256, 340)  # frame sizes of the datasets' jpg dumps
+        n_store = 2 * B * T
+        gen = torch.Generator(device=dev).manual_seed(7 + rank)
+        store = DeviceFrameStore(torch.randint(0, 256, (n_store, fh, fw, 3), device=dev, dtype=torch.uint8,
+                                               generator=gen))
+        pipe = VisualPipeline(store, T, 224, max_frames=B * T)
+        torch.manual_seed(11 + rank)
+        rows = [draw_frame_params(f % n_store, fh, fw, "train") for f in range(B * T)]
+        params_h = torch.tensor(rows, dtype=torch.int32).pin_memory()
+
+        def device_prefetch():
+            step.prefetch(spec_h, params_h, label_h, pipeline=pipe)
+        for _ in range(2):
+            device_prefetch()
+            step.step()
+        ms_dp, _ = timed(a.steps, e2e=True, prefetch=device_prefetch)
+        dp = {"value": B * world * a.steps / (ms_dp / 1e3), "unit": UNIT,
+              "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in (spec_h, params_h, label_h)),
+              "d2h_bytes_per_step": 32, "ms_per_step": ms_dp / a.steps,
+              "frame_store": "%d uint8 frames %dx%d resident in HBM (%.0f MB)" % (n_store, fh, fw,
+                                                                                 n_store * fh * fw * 3 / 1e6),
+              "note": "crop boxes / flips drawn on the host in the reference's RNG order; crop + Pillow-exact "
+                      "bilinear resize + flip + normalise on the device (csrc/datapipe.cu)"}
+
     value = B * world * a.steps / (ms / 1e3)
     e2e_value = B * world * a.steps / (ms_e2e / 1e3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
@@ -254,6 +287,8 @@ def run_gpu(a):
             "clocks": clocks,
             "final_losses": {"Lf": stats[0], "La": stats[1], "Lv": stats[2]},
             "wall_ms_per_step": wall_ms / a.steps}
+    if dp is not None:
+        line["e2e_device_pipeline"] = dp
 
     if not a.no_roofline:
         # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports it
@@ -355,6 +390,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-device-pipeline", action="store_true", help="skip the e2e leg with the GPU visual transform")
     a = ap.parse_args()
     if a.impl == "reference":
         if a.steps > 3:

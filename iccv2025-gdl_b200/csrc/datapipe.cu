@@ -1,0 +1,190 @@
+// datapipe.cu — visual half of the reference's per-item transform on the GPU, driven by the crop boxes and
+// flip decisions that torchvision drew on the host (reference dataset/CramedDataset.py:76-89,96-101 and
+// dataset/KSDataset.py:160-173,183-190):
+//
+//   RandomResizedCrop(224) | Resize((224,224))  ->  RandomHorizontalFlip  ->  ToTensor  ->  Normalize
+//
+// The resize is Pillow's 8-bit two-pass bilinear resample (torchvision's PIL backend: img.crop + img.resize,
+// Pillow src/libImaging/Resample.c), restated bit for bit:
+//   crop_coeff_kernel      precompute_coeffs + normalize_coeffs_8bpc per frame and axis, in fp64 with explicit
+//                          round-to-nearest intrinsics (no FMA contraction: Pillow's x86-64 build has none)
+//   crop_resample_kernel   one CTA per (band of output rows, frame): horizontal pass of the input rows the band
+//                          needs into an 8-bit shared-memory tile (rounded and clipped like Pillow's temporary
+//                          image), vertical pass out of shared memory, flip, uint8/255, (t-mean)/std with IEEE
+//                          division, written as fp32 [B,3,T,S,S] — the tensor the reference's DataLoader delivers
+// Source frames are uint8 HWC in a device-resident store (a 180 GB B200 holds the decoded CREMA-D / Kinetics-
+// Sounds frame sets), so a training step uploads 24 bytes per frame instead of 602 KB.
+// HBM-bound byte work: one read of the crop region, one write of the fp32 batch.
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace gdl {
+
+constexpr int kCropKMax = 16;                 // coefficients per output sample: ceil(scale)*2+1 <= 16, scale <= 7.5
+constexpr int kCropRowInts = 2 + kCropKMax;   // xmin, count, coefficients
+constexpr int kCropBandRows = 8;
+constexpr int kCropThreads = 256;
+constexpr int kPrecisionBits = 32 - 8 - 2;    // Resample.c PRECISION_BITS for 8-bit channels
+
+struct CropParams {  // one frame: which stored frame, crop box (top, left, height, width), horizontal flip
+  int src, i, j, h, w, flip;
+};
+
+// table[frame][axis (0 = horizontal / width, 1 = vertical / height)][S][kCropRowInts]
+__global__ void crop_coeff_kernel(const CropParams* __restrict__ params, int* __restrict__ table, int S) {
+  const int f = blockIdx.x, axis = blockIdx.y;
+  const CropParams p = params[f];
+  const int in_size = axis == 0 ? p.w : p.h;
+  int* tab = table + ((size_t)(f * 2 + axis) * S) * kCropRowInts;
+  const double scale = __ddiv_rn((double)in_size, (double)S);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = filterscale;  // bilinear support 1.0 * filterscale
+  const double ss = __ddiv_rn(1.0, filterscale);
+  for (int xx = threadIdx.x; xx < S; xx += blockDim.x) {
+    const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+    int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    if (xmax > kCropKMax) xmax = kCropKMax;  // unreachable: the launcher bounds the scale
+    double k[kCropKMax];
+    double ww = 0.0;
+#pragma unroll
+    for (int x = 0; x < kCropKMax; ++x) {
+      double w = 0.0;
+      if (x < xmax) {
+        double a = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+        if (a < 0.0) a = -a;
+        w = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+        ww = __dadd_rn(ww, w);
+      }
+      k[x] = w;
+    }
+    int* row = tab + (size_t)xx * kCropRowInts;
+    row[0] = xmin;
+    row[1] = xmax;
+#pragma unroll
+    for (int x = 0; x < kCropKMax; ++x) {
+      int q = 0;
+      if (x < xmax) {
+        const double v = ww != 0.0 ? __ddiv_rn(k[x], ww) : k[x];
+        q = v < 0.0 ? (int)__dadd_rn(-0.5, __dmul_rn(v, (double)(1 << kPrecisionBits)))
+                    : (int)__dadd_rn(0.5, __dmul_rn(v, (double)(1 << kPrecisionBits)));
+      }
+      row[2 + x] = q;
+    }
+  }
+}
+
+__device__ __forceinline__ int clip8(int acc) {
+  const int v = acc >> kPrecisionBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// out[b][c][t][y][x], frame f = b*T + t.  Dynamic shared memory: max_rows * 3 * S bytes (planar 8-bit tile).
+__global__ void __launch_bounds__(kCropThreads) crop_resample_kernel(
+    const uint8_t* __restrict__ store, const CropParams* __restrict__ params, const int* __restrict__ table,
+    float* __restrict__ out, int Hs, int Ws, int T, int S, int max_rows, float m0, float m1, float m2, float s0,
+    float s1, float s2) {
+  extern __shared__ uint8_t tile[];  // [rows][3][S]
+  const int f = blockIdx.y;
+  const int y0 = blockIdx.x * kCropBandRows;
+  const int y1 = min(y0 + kCropBandRows, S);
+  const CropParams p = params[f];
+  const int* tab_h = table + ((size_t)(f * 2 + 0) * S) * kCropRowInts;
+  const int* tab_v = table + ((size_t)(f * 2 + 1) * S) * kCropRowInts;
+  // rows of the (cropped) input this band's vertical windows read
+  const int r0 = __ldg(tab_v + (size_t)y0 * kCropRowInts);
+  const int r1 = __ldg(tab_v + (size_t)(y1 - 1) * kCropRowInts) + __ldg(tab_v + (size_t)(y1 - 1) * kCropRowInts + 1);
+  const int nrows = min(r1 - r0, max_rows);
+  const uint8_t* src = store + ((size_t)p.src * Hs + p.i) * Ws * 3 + (size_t)p.j * 3;
+  const bool same_w = p.w == S, same_h = p.h == S;  // Pillow skips a pass whose size does not change
+  // ---- horizontal pass: tile[r][c][xx] = clip8(2^21 + sum_k kk[xx][k] * in[r0+r][xmin+k][c])
+  for (int it = threadIdx.x; it < nrows * 3 * S; it += kCropThreads) {
+    const int xx = it % S;
+    const int rc = it / S;
+    const int c = rc % 3, r = rc / 3;
+    const uint8_t* row = src + (size_t)(r0 + r) * Ws * 3 + c;
+    int v;
+    if (same_w) {
+      v = row[xx * 3];
+    } else {
+      const int* k = tab_h + (size_t)xx * kCropRowInts;
+      const int xmin = __ldg(k), cnt = __ldg(k + 1);
+      int acc = 1 << (kPrecisionBits - 1);
+      for (int x = 0; x < cnt; ++x) acc += (int)row[(xmin + x) * 3] * __ldg(k + 2 + x);
+      v = clip8(acc);
+    }
+    tile[it] = (uint8_t)v;
+  }
+  __syncthreads();
+  // ---- vertical pass + flip + ToTensor + Normalize
+  const int b = f / T, t = f - b * T;
+  const int band = y1 - y0;
+  for (int it = threadIdx.x; it < band * 3 * S; it += kCropThreads) {
+    const int xx = it % S;
+    const int yc = it / S;
+    const int y = y0 + yc % band, c = yc / band;
+    int v;
+    const int* k = tab_v + (size_t)y * kCropRowInts;
+    const int ymin = __ldg(k) - r0, cnt = __ldg(k + 1);
+    if (same_h) {
+      v = tile[((size_t)ymin * 3 + c) * S + xx];  // identity weights: count 1
+    } else {
+      int acc = 1 << (kPrecisionBits - 1);
+      for (int x = 0; x < cnt; ++x) acc += (int)tile[((size_t)(ymin + x) * 3 + c) * S + xx] * __ldg(k + 2 + x);
+      v = clip8(acc);
+    }
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const float val = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean), sd);
+    const int xo = p.flip ? S - 1 - xx : xx;
+    out[(((size_t)(b * 3 + c) * T + t) * S + y) * S + xo] = val;
+  }
+}
+
+}  // namespace gdl
+
+using namespace gdl;
+
+extern "C" int64_t gdl_crop_table_ints(int frames, int S) {
+  if (frames <= 0 || S <= 0) return GDL_EINVAL;
+  return (int64_t)frames * 2 * S * kCropRowInts;
+}
+
+// Rows of shared memory a band may need for frames of Hs x Ws: the band's windows span at most
+// kCropBandRows*scale + 2*support + 2 input rows.
+static int crop_max_rows(int Hs, int S) {
+  const double scale = (double)Hs / S;
+  const double fs = scale < 1.0 ? 1.0 : scale;
+  return (int)(kCropBandRows * scale + 2.0 * fs + 3.0);
+}
+
+extern "C" int gdl_crop_resize_normalize(const uint8_t* store, int64_t store_frames, int Hs, int Ws,
+                                         const int32_t* params, int frames, int T, int S, const float* mean3,
+                                         const float* std3, float* out, int32_t* table, gdl_stream_t s) {
+  GDL_REQUIRE(store && params && out && table && mean3 && std3, "gdl_crop_resize_normalize: null pointer");
+  GDL_REQUIRE(store_frames > 0 && Hs > 0 && Ws > 0 && frames > 0 && T > 0 && frames % T == 0 && S > 0 && S <= 1024,
+              "gdl_crop_resize_normalize: bad shape");
+  const int hmax = Hs > Ws ? Hs : Ws;
+  const int ks = ((hmax + S - 1) / S) * 2 + 1;  // ceil(max scale) * 2 + 1 (>= 3)
+  GDL_REQUIRE(ks <= kCropKMax, "gdl_crop_resize_normalize: frames larger than 7.5x the output size are not supported");
+  const int max_rows = crop_max_rows(Hs, S);
+  const size_t smem = (size_t)max_rows * 3 * S;
+  GDL_REQUIRE(smem <= 200 * 1024, "gdl_crop_resize_normalize: band tile does not fit in shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(crop_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(crop_resample)");
+    attr_set = true;
+  }
+  const CropParams* cp = reinterpret_cast<const CropParams*>(params);
+  crop_coeff_kernel<<<dim3(frames, 2), 256, 0, (cudaStream_t)s>>>(cp, table, S);
+  GDL_CHECK_LAUNCH("crop_coeff_kernel");
+  dim3 grid((S + kCropBandRows - 1) / kCropBandRows, frames);
+  crop_resample_kernel<<<grid, kCropThreads, smem, (cudaStream_t)s>>>(store, cp, table, out, Hs, Ws, T, S, max_rows,
+                                                                     mean3[0], mean3[1], mean3[2], std3[0], std3[1],
+                                                                     std3[2]);
+  GDL_CHECK_LAUNCH("crop_resample_kernel");
+  return GDL_OK;
+}

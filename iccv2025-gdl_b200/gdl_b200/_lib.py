@@ -88,6 +88,8 @@ SIGNATURES = {
     "gdl_optim_scratch_floats": (_l, [_l, _i]),
     "gdl_grad_stats": (_i, [_p, _l, _p, _p, _p, _i, _f, _p, _p, _p]),
     "gdl_sgd_momentum": (_i, [_p, _p, _p, _l, _f, _f, _f, _i, _p, _p]),
+    "gdl_crop_table_ints": (_l, [_i, _i]),
+    "gdl_crop_resize_normalize": (_i, [_p, _l, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -417,3 +417,14 @@ def grad_stats(grad, numel, seg_end, seg_group, seg_inv_numel, nseg, max_norm, s
 def sgd_momentum(param, grad, buf, numel, lr, mu, wd, first_step, stats):
     check(_lib.load().gdl_sgd_momentum(_ptr(param), _ptr(grad), _ptr(buf), numel, lr, mu, wd,
                                        int(first_step), _ptr(stats), _stream()), "gdl_sgd_momentum")
+
+
+# ---------------------------------------------------------------------------------- data pipeline
+@_op("crop_resize_normalize", 2,
+     lambda store, n, Hs, Ws, params, frames, T, S, mean, std, out, table: ("bytes", frames * 3.0 * S * S * 4.0))
+def crop_resize_normalize(store, store_frames, Hs, Ws, params, frames, T, S, mean3, std3, out, table):
+    """uint8 frame store + host-drawn crop boxes -> normalised fp32 [frames/T, 3, T, S, S] (datapipe.cu).
+    mean3 / std3 are ctypes float[3] (host constants)."""
+    check(_lib.load().gdl_crop_resize_normalize(_ptr(store), store_frames, Hs, Ws, _ptr(params), frames, T, S,
+                                                C.cast(mean3, C.c_void_p), C.cast(std3, C.c_void_p), _ptr(out),
+                                                _ptr(table), _stream()), "gdl_crop_resize_normalize")

@@ -133,6 +133,7 @@ class DGLStep:
         self._stage = [(torch.zeros(B, self.F_, self.Tt, device=dev), torch.zeros(B, 3, T, self.H, self.W, device=dev),
                         torch.zeros(B, device=dev, dtype=torch.int64)) for _ in range(2)]
         self._cur, self._pending = 0, None
+        self._crop_params = None  # device copies of the crop-box tables (prefetch with a VisualPipeline)
         self.copy_stream = torch.cuda.Stream(dev)
         self._stage_ready = [torch.cuda.Event() for _ in range(2)]
         self._stage_free = [torch.cuda.Event() for _ in range(2)]
@@ -322,17 +323,31 @@ class DGLStep:
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
 
-    def prefetch(self, spec, image, label):
+    def prefetch(self, spec, image, label, pipeline=None):
         """Start the H2D copy of the NEXT batch (pinned host tensors) on the copy stream into the staging
         set that the running step does not read; the next step() without arguments consumes it.  This is the
         pin_memory + non_blocking pattern of the reference's DataLoader (main_dgl.py:284-288,93-95) made
-        explicit, so that PCIe traffic overlaps the previous step's kernels."""
+        explicit, so that PCIe traffic overlaps the previous step's kernels.
+
+        pipeline: a datapipe.VisualPipeline — `image` is then the int32 [B*T, 6] table of host-drawn crop boxes
+        (datapipe.draw_frame_params) and the fp32 frames are produced ON the device from the resident uint8
+        frame store (bit-identical to the reference transform), so only the spectrograms and 24 bytes per frame
+        cross PCIe."""
         nxt = 1 - self._cur
         cs = self.copy_stream
         cs.wait_event(self._stage_free[nxt])  # the layout kernels that last read this set have run
         with torch.cuda.stream(cs):
-            for dst, src in zip(self._stage[nxt], (spec, image, label)):
-                dst.copy_(src, non_blocking=True)
+            s_spec, s_image, s_label = self._stage[nxt]
+            s_spec.copy_(spec, non_blocking=True)
+            s_label.copy_(label, non_blocking=True)
+            if pipeline is None:
+                s_image.copy_(image, non_blocking=True)
+            else:
+                if self._crop_params is None:
+                    self._crop_params = [torch.empty(self.B * self.T, 6, device=self.device, dtype=torch.int32)
+                                         for _ in range(2)]
+                self._crop_params[nxt].copy_(image, non_blocking=True)
+                pipeline(self._crop_params[nxt], out=s_image)
             self._stage_ready[nxt].record(cs)
         self._pending = nxt
 

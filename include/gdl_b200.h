@@ -265,6 +265,22 @@ int gdl_grad_stats(const float* grad, int64_t numel, const int64_t* seg_end,
 int gdl_sgd_momentum(float* param, float* grad, float* momentum_buf, int64_t numel, float lr,
                      float mu, float wd, int first_step, const float* stats, gdl_stream_t s);
 
+/* ---- visual data pipeline (reference dataset/CramedDataset.py:76-89,96-101; KSDataset.py:160-173,183-190) ---
+ * RandomResizedCrop(S) | Resize((S,S)) -> RandomHorizontalFlip -> ToTensor -> Normalize for `frames` frames,
+ * driven by the crop boxes / flips torchvision drew on the HOST: bit-exact with
+ * torchvision's PIL backend (Pillow Resample.c 8-bit two-pass bilinear, 22-bit fixed-point coefficients).
+ *   store   uint8 [store_frames][Hs][Ws][3] decoded RGB frames resident in HBM (device pointer)
+ *   params  int32 [frames][6] on the device: {store index, top i, left j, height h, width w, flip}
+ *           (the test split's Resize((S,S)) is {idx, 0, 0, Hs, Ws, 0})
+ *   mean3 / std3  HOST pointers to the three Normalize constants
+ *   out     fp32 [frames/T][3][T][S][S] — the `image` tensor the reference's DataLoader yields (main_dgl.py:93)
+ *   table   int32 [gdl_crop_table_ints(frames, S)] scratch for the per-frame resample coefficients
+ * Frames up to 7.5x the output size (Hs, Ws <= 7.5*S).  Asynchronous, no allocation. */
+int64_t gdl_crop_table_ints(int frames, int S);
+int gdl_crop_resize_normalize(const uint8_t* store, int64_t store_frames, int Hs, int Ws, const int32_t* params,
+                              int frames, int T, int S, const float* mean3, const float* std3, float* out,
+                              int32_t* table, gdl_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

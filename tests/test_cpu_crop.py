@@ -1,0 +1,69 @@
+"""CPU checks of the visual data-pipeline oracle (oracle/crop_oracle.py, test infrastructure): bit-exact with
+torchvision's PIL backend run live, with the committed golden digests, and the host-side random draws consume
+torch's RNG exactly like the reference transform (dataset/CramedDataset.py:76-89)."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "iccv2025-gdl_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+from oracle.crop_oracle import crop_resize_flip_normalize, precompute_coeffs  # noqa: E402
+
+
+def _golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "crop_golden.npz"))
+
+
+def test_oracle_matches_golden_digests():
+    from make_crop_golden import image_of
+    g = _golden()
+    for k, (H, W, i, j, h, w, flip) in enumerate(g["cases"].tolist()):
+        got = np.ascontiguousarray(crop_resize_flip_normalize(image_of(k, H, W), i, j, h, w, flip))
+        assert hashlib.sha256(got.tobytes()).hexdigest() == str(g["digests"][k]), k
+        assert np.array_equal(got.reshape(-1)[:: got.size // 16][:16], g["probes"][k])
+
+
+def test_oracle_matches_torchvision_live():
+    from make_crop_golden import reference
+    rs = np.random.RandomState(7)
+    for _ in range(12):
+        H, W = int(rs.randint(20, 400)), int(rs.randint(20, 400))
+        h, w = int(rs.randint(1, H + 1)), int(rs.randint(1, W + 1))
+        i, j, flip = int(rs.randint(0, H - h + 1)), int(rs.randint(0, W - w + 1)), int(rs.randint(2))
+        img = rs.randint(0, 256, size=(H, W, 3), dtype=np.uint8)
+        ref = reference(img, i, j, h, w, flip)
+        got = crop_resize_flip_normalize(img, i, j, h, w, flip)
+        assert np.array_equal(ref.view(np.uint32), got.view(np.uint32)), (H, W, i, j, h, w, flip)
+
+
+def test_coefficients_sum_to_one_in_fixed_point():
+    for in_size in (1, 57, 224, 360, 480, 900):
+        bounds, kk = precompute_coeffs(in_size, 224)
+        assert (bounds[:, 0] >= 0).all() and (bounds[:, 0] + bounds[:, 1] <= in_size).all()
+        assert np.abs(kk.sum(1) - (1 << 22)).max() <= kk.shape[1]  # rounding of each coefficient
+
+
+@pytest.mark.parametrize("mode", ["train", "test"])
+def test_host_draws_follow_the_reference_transform(mode):
+    """draw_frame_params consumes torch's global RNG exactly like the reference's Compose([...]) and, fed to
+    the oracle, reproduces its output bit for bit."""
+    from gdl_b200.datapipe import draw_frame_params
+    from gdl_b200.synthetic import _transform, synth_image
+    for seed in range(4):
+        img = synth_image("crop/%d" % seed, (480, 360))
+        torch.manual_seed(seed)
+        ref = _transform(mode)(img)
+        state = torch.get_rng_state()
+        torch.manual_seed(seed)
+        p = draw_frame_params(5, 360, 480, mode)
+        assert torch.equal(torch.get_rng_state(), state)
+        assert p[0] == 5
+        got = crop_resize_flip_normalize(np.asarray(img), *p[1:])
+        assert np.array_equal(ref.numpy().view(np.uint32), got.view(np.uint32))
