@@ -22,7 +22,7 @@ namespace gdl {
 
 constexpr int kCropKMax = 16;                 // coefficients per output sample: ceil(scale)*2+1 <= 16, scale <= 7.5
 constexpr int kCropRowInts = 2 + kCropKMax;   // xmin, count, coefficients
-constexpr int kCropBandRows = 8;
+constexpr int kCropBandRows = 16;
 constexpr int kCropThreads = 256;
 constexpr int kPrecisionBits = 32 - 8 - 2;    // Resample.c PRECISION_BITS for 8-bit channels
 
@@ -30,7 +30,9 @@ struct CropParams {  // one frame: which stored frame, crop box (top, left, heig
   int src, i, j, h, w, flip;
 };
 
-// table[frame][axis (0 = horizontal / width, 1 = vertical / height)][S][kCropRowInts]
+// table[frame][axis (0 = horizontal / width, 1 = vertical / height)][kCropRowInts][S]: entry q of output sample xx
+// at [q][xx] (q = 0 first input index, 1 count, 2.. coefficients), so that a warp working on consecutive xx
+// reads consecutive ints (with [S][q] every lane touched its own sector: 32 wavefronts per coefficient load)
 __global__ void crop_coeff_kernel(const CropParams* __restrict__ params, int* __restrict__ table, int S) {
   const int f = blockIdx.x, axis = blockIdx.y;
   const CropParams p = params[f];
@@ -61,9 +63,9 @@ __global__ void crop_coeff_kernel(const CropParams* __restrict__ params, int* __
       }
       k[x] = w;
     }
-    int* row = tab + (size_t)xx * kCropRowInts;
+    int* row = tab + xx;  // stride S between entries
     row[0] = xmin;
-    row[1] = xmax;
+    row[S] = xmax;
 #pragma unroll
     for (int x = 0; x < kCropKMax; ++x) {
       int q = 0;
@@ -72,7 +74,7 @@ __global__ void crop_coeff_kernel(const CropParams* __restrict__ params, int* __
         q = v < 0.0 ? (int)__dadd_rn(-0.5, __dmul_rn(v, (double)(1 << kPrecisionBits)))
                     : (int)__dadd_rn(0.5, __dmul_rn(v, (double)(1 << kPrecisionBits)));
       }
-      row[2 + x] = q;
+      row[(size_t)(2 + x) * S] = q;
     }
   }
 }
@@ -95,51 +97,58 @@ __global__ void __launch_bounds__(kCropThreads) crop_resample_kernel(
   const int* tab_h = table + ((size_t)(f * 2 + 0) * S) * kCropRowInts;
   const int* tab_v = table + ((size_t)(f * 2 + 1) * S) * kCropRowInts;
   // rows of the (cropped) input this band's vertical windows read
-  const int r0 = __ldg(tab_v + (size_t)y0 * kCropRowInts);
-  const int r1 = __ldg(tab_v + (size_t)(y1 - 1) * kCropRowInts) + __ldg(tab_v + (size_t)(y1 - 1) * kCropRowInts + 1);
+  const int r0 = __ldg(tab_v + y0);
+  const int r1 = __ldg(tab_v + (y1 - 1)) + __ldg(tab_v + S + (y1 - 1));
   const int nrows = min(r1 - r0, max_rows);
   const uint8_t* src = store + ((size_t)p.src * Hs + p.i) * Ws * 3 + (size_t)p.j * 3;
   const bool same_w = p.w == S, same_h = p.h == S;  // Pillow skips a pass whose size does not change
+  // One warp per (row, channel) line, lanes over xx: no per-item integer division, coefficient and pixel reads
+  // of a warp are contiguous / near-contiguous.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = kCropThreads / 32;
   // ---- horizontal pass: tile[r][c][xx] = clip8(2^21 + sum_k kk[xx][k] * in[r0+r][xmin+k][c])
-  for (int it = threadIdx.x; it < nrows * 3 * S; it += kCropThreads) {
-    const int xx = it % S;
-    const int rc = it / S;
-    const int c = rc % 3, r = rc / 3;
+  for (int rc = warp; rc < nrows * 3; rc += kWarps) {
+    const int r = rc / 3, c = rc - r * 3;
     const uint8_t* row = src + (size_t)(r0 + r) * Ws * 3 + c;
-    int v;
-    if (same_w) {
-      v = row[xx * 3];
-    } else {
-      const int* k = tab_h + (size_t)xx * kCropRowInts;
-      const int xmin = __ldg(k), cnt = __ldg(k + 1);
-      int acc = 1 << (kPrecisionBits - 1);
-      for (int x = 0; x < cnt; ++x) acc += (int)row[(xmin + x) * 3] * __ldg(k + 2 + x);
-      v = clip8(acc);
+    uint8_t* trow = tile + (size_t)rc * S;
+    for (int xx = lane; xx < S; xx += 32) {
+      int v;
+      if (same_w) {
+        v = row[xx * 3];
+      } else {
+        const int* k = tab_h + xx;
+        const int xmin = __ldg(k), cnt = __ldg(k + S);
+        const uint8_t* px = row + xmin * 3;
+        int acc = 1 << (kPrecisionBits - 1);
+        for (int x = 0; x < cnt; ++x) acc += (int)px[x * 3] * __ldg(k + (2 + x) * S);
+        v = clip8(acc);
+      }
+      trow[xx] = (uint8_t)v;
     }
-    tile[it] = (uint8_t)v;
   }
   __syncthreads();
   // ---- vertical pass + flip + ToTensor + Normalize
   const int b = f / T, t = f - b * T;
   const int band = y1 - y0;
-  for (int it = threadIdx.x; it < band * 3 * S; it += kCropThreads) {
-    const int xx = it % S;
-    const int yc = it / S;
-    const int y = y0 + yc % band, c = yc / band;
-    int v;
-    const int* k = tab_v + (size_t)y * kCropRowInts;
-    const int ymin = __ldg(k) - r0, cnt = __ldg(k + 1);
-    if (same_h) {
-      v = tile[((size_t)ymin * 3 + c) * S + xx];  // identity weights: count 1
-    } else {
-      int acc = 1 << (kPrecisionBits - 1);
-      for (int x = 0; x < cnt; ++x) acc += (int)tile[((size_t)(ymin + x) * 3 + c) * S + xx] * __ldg(k + 2 + x);
-      v = clip8(acc);
-    }
+  for (int yc = warp; yc < band * 3; yc += kWarps) {
+    const int c = yc / band, y = y0 + (yc - c * band);
+    const int* k = tab_v + y;  // warp-uniform: broadcast reads
+    const int ymin = __ldg(k) - r0, cnt = __ldg(k + S);
     const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
-    const float val = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean), sd);
-    const int xo = p.flip ? S - 1 - xx : xx;
-    out[(((size_t)(b * 3 + c) * T + t) * S + y) * S + xo] = val;
+    const uint8_t* tcol = tile + ((size_t)ymin * 3 + c) * S;
+    float* orow = out + (((size_t)(b * 3 + c) * T + t) * S + y) * S;
+    for (int xx = lane; xx < S; xx += 32) {
+      int v;
+      if (same_h) {
+        v = tcol[xx];  // identity weights
+      } else {
+        int acc = 1 << (kPrecisionBits - 1);
+        for (int x = 0; x < cnt; ++x) acc += (int)tcol[(size_t)x * 3 * S + xx] * __ldg(k + (2 + x) * S);
+        v = clip8(acc);
+      }
+      const float val = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean), sd);
+      orow[p.flip ? S - 1 - xx : xx] = val;
+    }
   }
 }
 

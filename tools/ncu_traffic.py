@@ -15,7 +15,7 @@ for r in rows:
     d = launch.setdefault(int(r[0]), {"name": re.sub(r"^void ", "", re.sub(r"\(.*", "", r[4])), "grid": r[8]})
     d[r[12]] = float(r[14].replace(",", "")) * UNIT.get(r[13], 1.0)
 L = list(launch.values())
-steps = max(1, sum(1 for d in L if d["name"].startswith("gdl::stem_fwd_kernel")) // 2)  # 2 stems per step
+steps = max(1, sum(1 for d in L if "stem_fwd_kernel" in d["name"]) // 2)  # 2 stems per step
 TP = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
 agg = OrderedDict()
 for d in L:
