@@ -40,6 +40,7 @@ CONV_CASES = [
     (3, 65, 47, 64, 64, 3, 1, 1),
     (5, 14, 14, 128, 256, 3, 2, 1),
     (40, 9, 6, 512, 512, 3, 1, 1),
+    (40, 56, 56, 64, 64, 3, 1, 1),   # >= 148 items of 256 pixels: the resident-weights variant of conv_flat
 ]
 
 
