@@ -39,6 +39,7 @@ struct FlatTap {
 struct FlatParams {
   CUtensorMap tm_x[4];  // {Cs, Ws, Hs, N} views of the source (one per parity plane), box {64, P, 1, 1}
   CUtensorMap tm_w;  // {K, rows} packed weights, box {64, BN}
+  CUtensorMap tm_w_half;  // CL kernels: box {64, BN/2} (each CTA of the pair loads one half and multicasts it)
   bf16* dst;
   const bf16* add_src;
   float* stats;  // optional [gridDim.x * 4 epilogue warps][2][Cd]: per-warp sum / sum of squares of the bf16 outputs
@@ -70,7 +71,12 @@ __device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
 // RES: the whole packed weight matrix of the layer (taps x slabs tiles of BN x 64) is loaded ONCE per CTA and stays in
 // shared memory (64 -> 64 channel 3x3 layers: 9 tiles = 72 KB), instead of being streamed from L2 for every 256-pixel
 // item: the weight ring is 2/3 of the L2 -> SM traffic of those layers.  One class, one channel tile.
-template <int BN, int MT, int WST, bool STATS, bool RES = false>
+// CL: CTA pairs (cluster of 2).  The two CTAs of a pair work on neighbouring pixel tiles of the SAME channel tile,
+// so they consume the same sequence of weight tiles: each loads one half of every tile and TMA-multicasts it into
+// both shared memories (half the L2 -> SM weight traffic per SM, which is what bounds these kernels — see RES).
+// A weight stage is refilled only after BOTH consumers released it (tcgen05.commit multicast, barrier count 2).
+// NOT YET VALIDATED ON HARDWARE: opt-in (GDL_FLAT_CLUSTER=1), written after the round's GPU budget was spent.
+template <int BN, int MT, int WST, bool STATS, bool RES = false, bool CL = false>
 __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid_constant__ FlatParams p) {
   constexpr int W_BYTES = BN * 128;
   constexpr int TM = MT * 128;
@@ -91,7 +97,13 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
   const int warp = warp_uniform_idx();
   const int slabs = p.Cs >> 6;
   const int WS = p.win_stages;
-  const int per_class = p.ntiles * p.mtiles;
+  const int rank = CL ? (int)cluster_ctarank() : 0;
+  const int item_first = CL ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int item_stride = CL ? int(gridDim.x >> 1) : int(gridDim.x);
+  const int mt_count = CL ? (p.mtiles + 1) / 2 : p.mtiles;  // pixel-tile slots per (class, channel tile)
+  const int mt_max = CL ? 2 * mt_count : p.mtiles;            // a pair's odd tail tile is all padding
+  const int per_class = p.ntiles * mt_count;
+  const int items_total = p.nclass * per_class;
 
   if (tid == 0) {
     for (int i = 0; i < kMaxWin; ++i) {
@@ -100,7 +112,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
     }
     for (int i = 0; i < WST; ++i) {
       mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
+      mbar_init(&w_empty[i], CL ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -118,6 +130,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();  // the peer's barriers exist before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
@@ -134,12 +147,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
           tma_load_2d(smem_base + w_off + (slab * p.ntaps[0] + t) * W_BYTES, &p.tm_w, &w_full[0],
                       p.taps[0][t].wk + slab * 64, 0);
     }
-    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
+    for (int item = item_first; item < items_total; item += item_stride) {
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
-      const int nt = rem / p.mtiles;
-      const int mt_i = rem - nt * p.mtiles;
-      const int q0 = (p.rev ? p.mtiles - 1 - mt_i : mt_i) * TM;
+      const int nt = rem / mt_count;
+      const int mt_i = (rem - nt * mt_count) * (CL ? 2 : 1) + rank;
+      const int q0 = (p.rev ? mt_max - 1 - mt_i : mt_i) * TM;
       const int n0 = nt * BN;
       const int rho_a = floor_div(q0 + p.smin, p.P);
       const int rho_b = floor_div(q0 + TM + p.smax - 1, p.P);
@@ -162,8 +175,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
             for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
               const int st = wcount % WST;
               if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
-              mbar_arrive_expect_tx(&w_full[st], W_BYTES);
-              tma_load_2d(smem_base + w_off + st * W_BYTES, &p.tm_w, &w_full[st], p.taps[cls][t].wk + slab * 64, n0);
+              mbar_arrive_expect_tx(&w_full[st], W_BYTES);  // own half + the peer's half
+              if (CL)
+                tma_load_2d_multicast(smem_base + w_off + st * W_BYTES + rank * (W_BYTES / 2), &p.tm_w_half, &w_full[st],
+                                      p.taps[cls][t].wk + slab * 64, n0 + rank * (BN / 2), (uint16_t)3);
+              else
+                tma_load_2d(smem_base + w_off + st * W_BYTES, &p.tm_w, &w_full[st], p.taps[cls][t].wk + slab * 64, n0);
             }
         }
       }
@@ -186,12 +203,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       mbar_wait(&w_full[0], 0);
       tc_fence_after();
     }
-    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++it) {
+    for (int item = item_first; item < items_total; item += item_stride, ++it) {
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
-      const int nt = rem / p.mtiles;
-      const int mt_i = rem - nt * p.mtiles;
-      const int q0 = (p.rev ? p.mtiles - 1 - mt_i : mt_i) * TM;
+      const int nt = rem / mt_count;
+      const int mt_i = (rem - nt * mt_count) * (CL ? 2 : 1) + rank;
+      const int q0 = (p.rev ? mt_max - 1 - mt_i : mt_i) * TM;
       const int rho_a = floor_div(q0 + p.smin, p.P);
       const int o = q0 + p.smin - rho_a * p.P;  // first window row inside the stage
       const int acc = it & 1;
@@ -224,7 +241,10 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
                 mma_bf16_acc(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi),
                              desc_join(b_lo + 2 * k, ab_hi), idesc);
             }
-            if (!RES) mma_commit(&w_empty[st]);
+            if (CL)
+              mma_commit_multicast(&w_empty[st], (uint16_t)3);
+            else if (!RES)
+              mma_commit(&w_empty[st]);
           }
           mma_commit(&win_empty[ws]);
         }
@@ -262,12 +282,12 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       }
     };
     int it = 0;
-    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++it) {
+    for (int item = item_first; item < items_total; item += item_stride, ++it) {
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
-      const int nt = rem / p.mtiles;
-      const int mt_i = rem - nt * p.mtiles;
-      const int q0 = (p.rev ? p.mtiles - 1 - mt_i : mt_i) * TM;
+      const int nt = rem / mt_count;
+      const int mt_i = (rem - nt * mt_count) * (CL ? 2 : 1) + rank;
+      const int q0 = (p.rev ? mt_max - 1 - mt_i : mt_i) * TM;
       const int n0 = nt * BN;
       const int acc = it & 1;
       if (STATS && nt != st_nt) {
@@ -371,13 +391,14 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();  // no CTA of the pair exits while the other may still signal its barriers
   if (warp == 4) tmem_dealloc(tmem_base, 2 * MT * BN);
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int BN, int MT, int WST, bool RES = false>
+template <int BN, int MT, int WST, bool RES = false, bool CL = false>
 static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   constexpr int TM = MT * 128;
   const int nrows_max = (TM + p.smax - p.smin - 1 + p.P - 1) / p.P + 1;
@@ -396,6 +417,34 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   p.items_total = p.nclass * p.ntiles * p.mtiles;
   int total = ws * p.win_stage_bytes + fixed + 1024;
   if (total < 116 * 1024) total = 116 * 1024;  // one CTA per SM: the kernel relies on TMEM base 0
+  if constexpr (CL) {
+    if (RES || p.stats != nullptr) return 0;
+    static bool cl_attr_set = false;
+    if (!cl_attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, false, false, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_flat cluster)");
+      cl_attr_set = true;
+    }
+    const int64_t pairs = (int64_t)p.nclass * p.ntiles * ((p.mtiles + 1) / 2);
+    int grid2 = int(2 * pairs < kNumSMs ? 2 * pairs : kNumSMs) & ~1;
+    if (grid2 < 2) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid2);
+    cfg.blockDim = dim3(kFlatThreads);
+    cfg.dynamicSmemBytes = total;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_flat_kernel<BN, MT, WST, false, false, true>, p);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_flat_kernel(cluster)");
+    return 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, false, RES>,
@@ -552,7 +601,15 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   if (mt_force) mt = mt_force;
   int rc = 0;
   if (BN == 128) {
-    if (mt == 2) rc = launch_flat<128, 2, 4>(p, Q, s);
+    // GDL_FLAT_CLUSTER=1: CTA pairs with multicast weight tiles (see the kernel comment; not yet validated on a B200)
+    static const int cluster = env_int3("GDL_FLAT_CLUSTER", 0);
+    if (cluster && mt == 2 && stats == nullptr) {
+      const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
+      if (!th) return GDL_ECUDA;
+      p.tm_w_half = *th;
+      rc = launch_flat<128, 2, 4, false, true>(p, Q, s);
+    }
+    if (rc == 0 && mt == 2) rc = launch_flat<128, 2, 4>(p, Q, s);
     if (rc == 0) rc = launch_flat<128, 1, 4>(p, Q, s);
   } else {
     // GDL_FLAT_RESIDENT (default 1): 64 -> 64 channel 3x3 layers keep their 72 KB of weights in shared memory

@@ -41,6 +41,7 @@ CONV_CASES = [
     (5, 14, 14, 128, 256, 3, 2, 1),
     (40, 9, 6, 512, 512, 3, 1, 1),
     (40, 56, 56, 64, 64, 3, 1, 1),   # >= 148 items of 256 pixels: the resident-weights variant of conv_flat
+    (64, 28, 28, 128, 128, 3, 1, 1), # >= 148 items with 128-channel tiles (MT = 2; the opt-in CTA-pair variant)
 ]
 
 
