@@ -152,6 +152,7 @@ class DGLStep:
         self._init_head()
         self.stream_a, self.stream_v = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.steps_done = 0
+        self.momentum_loaded = False  # set by train.adopt_momentum when a checkpoint's buffers were copied in
         self._graph = None
         self._graph_b = None
         self._graph_update = None
@@ -307,7 +308,8 @@ class DGLStep:
         ar = self.arena
         ops.grad_stats(ar.grad, ar.numel, ar.seg_end, ar.seg_group, ar.seg_inv, ar.nseg, self.max_norm,
                        ar.scratch, self.stats[4:8])
-        ops.sgd_momentum(ar.param, ar.grad, ar.momentum, ar.numel, lr, self.mu, self.wd, first, self.stats[4:8])
+        ops.sgd_momentum(ar.param, ar.grad, ar.momentum, ar.numel, lr, self.mu, self.wd,
+                         first and not self.momentum_loaded, self.stats[4:8])
         self.enc_a.repack()
         self.enc_v.repack()
         if self.film is not None:

@@ -31,10 +31,29 @@ def _get_step(args, model, optimizer, spec, image):
     st = DGLStep(inner, B, tuple(spec.shape[1:]), tuple(image.shape[2:]), alpha=args.alpha, lr=g['lr'],
                  momentum=g.get('momentum', 0.9), weight_decay=g.get('weight_decay', 1e-4), max_norm=40.0,
                  world_size=world, process_group=torch.distributed.group.WORLD if world > 1 else None)
-    for p, o in zip(st.arena.params, st.arena.offsets):  # checkpoint compatibility
-        optimizer.state[p]['momentum_buffer'] = st.arena.momentum[o:o + p.numel()].view(p.shape)
+    adopt_momentum(st.arena, optimizer, st)
     inner._gdl_step, inner._gdl_step_key = st, key
     return st
+
+
+def adopt_momentum(arena, optimizer, step=None):
+    """Checkpoint compatibility in both directions (reference main_dgl.py:396-412 saves `optimizer.state_dict()`):
+    momentum buffers already present in `optimizer.state` — loaded from a checkpoint by
+    `optimizer.load_state_dict`, or left by a previous DGLStep of another batch geometry — are copied INTO the
+    arena, then `optimizer.state[p]['momentum_buffer']` is re-pointed at the arena views so the next
+    `optimizer.state_dict()` carries what the fused SGD kernel maintains.  When anything was adopted the
+    step's first update must use `mu * buf + g` instead of torch's first-step `buf = g`."""
+    loaded = False
+    for p, o in zip(arena.params, arena.offsets):
+        view = arena.momentum[o:o + p.numel()].view(p.shape)
+        buf = optimizer.state.get(p, {}).get('momentum_buffer')
+        if buf is not None and buf.data_ptr() != view.data_ptr():
+            view.copy_(buf)
+            loaded = True
+        optimizer.state[p]['momentum_buffer'] = view
+    if loaded and step is not None:
+        step.momentum_loaded = True
+    return loaded
 
 
 def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler, writer=None):

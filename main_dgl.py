@@ -60,6 +60,8 @@ def get_arguments(argv=None):
     parser.add_argument('--drop', default=0, type=int)
     # additions (defaults preserve the reference behaviour)
     parser.add_argument('--synthetic_len', default=0, type=int, help='synthetic dataset length (0 = CREMA-D sizes)')
+    parser.add_argument('--resume', default=None, type=str,
+                        help='checkpoint written by this script or by the reference (main_dgl.py:396-412) to continue from')
     return parser.parse_args(argv)
 
 
@@ -116,6 +118,17 @@ def main(argv=None):
     test_loader = DataLoader(test_dataset, batch_size=per_rank, shuffle=False, num_workers=8, pin_memory=True,
                              drop_last=True)  # the reference drops the test tail too (main_dgl.py:287-288)
 
+    start_epoch = 0
+    if args.resume:
+        # the reference saves {'saved_epoch', 'model' (module.-prefixed keys), 'optimizer', 'scheduler', ...} but has
+        # no way to load it back; the momentum buffers are adopted by the fused optimizer on the first batch
+        ckpt = torch.load(args.resume, map_location=device)
+        model.load_state_dict(ckpt['model'])
+        optimizer.load_state_dict(ckpt['optimizer'])
+        scheduler.load_state_dict(ckpt['scheduler'])
+        start_epoch = int(ckpt['saved_epoch']) + 1
+        print('Resumed from {} (epoch {}, acc {})'.format(args.resume, ckpt['saved_epoch'], ckpt.get('acc')))
+
     if args.train:
         os.makedirs(args.ckpt_path, exist_ok=True)
         best_acc = 0.0
@@ -123,7 +136,7 @@ def main(argv=None):
         if rank == 0:
             with open(log, 'a+', newline='') as f:
                 csv.writer(f).writerow([1000, 1000, 1000])  # run separator, main_dgl.py:292-295
-        for epoch in range(args.epochs):
+        for epoch in range(start_epoch, args.epochs):
             print('Epoch: {}: '.format(epoch))
             batch_loss, batch_loss_a, batch_loss_v, *_ = train_epoch(args, epoch, model, device, train_loader,
                                                                      optimizer, scheduler)

@@ -131,3 +131,53 @@ def test_late_bucket_is_a_contiguous_tail_of_each_encoder():
         pass
     else:
         raise AssertionError("late_split accepted a non-tail parameter set")
+
+
+def test_checkpoint_momentum_is_adopted_by_the_arena():
+    """Resume path: momentum buffers that `optimizer.load_state_dict` restored are copied
+    into the fused optimizer's arena and `optimizer.state_dict()` keeps carrying the arena's values."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "iccv2025-gdl_b200"))
+    import gdl_b200
+    from gdl_b200.step import ParamArena
+    from gdl_b200.train import adopt_momentum
+
+    def build():
+        args = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modality="full")
+        gdl_b200.setup_seed(0)
+        m = gdl_b200.AVClassifier_DGL(args)
+        return m, torch.optim.SGD(m.parameters(), lr=0.001, momentum=0.9, weight_decay=1e-4)
+
+    # "previous run": an arena whose momentum the fused kernel has been updating, saved the reference way
+    m0, opt0 = build()
+    a0 = ParamArena(m0, torch.device("cpu"))
+    assert adopt_momentum(a0, opt0) is False            # fresh run: nothing to adopt, buffers alias the arena
+    a0.momentum.copy_(torch.arange(a0.numel, dtype=torch.float32) * 1e-6)
+    saved = {"model": m0.state_dict(), "optimizer": opt0.state_dict()}
+    # never-trained parameters (fc_auxi) carry no optimizer state, exactly like torch.optim.SGD
+    assert len(saved["optimizer"]["state"]) == len(a0.params) < len(list(m0.parameters()))
+
+    # "resumed run"
+    m1, opt1 = build()
+    m1.load_state_dict(saved["model"])
+    opt1.load_state_dict(saved["optimizer"])
+    a1 = ParamArena(m1, torch.device("cpu"))
+
+    class _Step:
+        momentum_loaded = False
+    st = _Step()
+    assert adopt_momentum(a1, opt1, st) is True and st.momentum_loaded
+
+    def views(a):
+        return [a.momentum[o:o + p.numel()] for p, o in zip(a.params, a.offsets)]
+    for v0, v1 in zip(views(a0), views(a1)):            # (the alignment padding between tensors is not state)
+        assert torch.equal(v0, v1)
+    p = a1.params[3]
+    assert opt1.state[p]["momentum_buffer"].data_ptr() == a1.momentum[a1.offsets[3]:].data_ptr()
+    for v in views(a1):                                 # the fused kernel keeps updating the arena ...
+        v.mul_(2.0)
+    again = opt1.state_dict()["state"]                  # ... and the next checkpoint carries those values
+    total = sum(v["momentum_buffer"].double().sum().item() for v in again.values())
+    want = sum(v.double().sum().item() for v in views(a1))
+    assert abs(total - want) <= 1e-9 * max(1.0, abs(want))
