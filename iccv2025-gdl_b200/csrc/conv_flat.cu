@@ -600,9 +600,10 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   int mt = items2 >= kNumSMs ? 2 : 1;
   if (mt_force) mt = mt_force;
   int rc = 0;
+  // GDL_FLAT_CLUSTER=1: CTA pairs with multicast weight tiles (see the kernel comment; forward parity verified on
+  // one 128-channel case, speed not yet measured on a B200 — off by default)
+  static const int cluster = env_int3("GDL_FLAT_CLUSTER", 0);
   if (BN == 128) {
-    // GDL_FLAT_CLUSTER=1: CTA pairs with multicast weight tiles (see the kernel comment; not yet validated on a B200)
-    static const int cluster = env_int3("GDL_FLAT_CLUSTER", 0);
     if (cluster && mt == 2 && stats == nullptr) {
       const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
       if (!th) return GDL_ECUDA;
@@ -617,6 +618,12 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
     static const int resident = env_int3("GDL_FLAT_RESIDENT", 1);
     if (resident && mt == 2 && Cs == 64 && Cd == 64 && (kind == 0 || kind == 1) && stats == nullptr)
       rc = launch_flat<64, 2, 6, true>(p, Q, s);
+    if (rc == 0 && cluster && mt == 2 && stats == nullptr) {  // e.g. the 128 -> 64 channel stride-2 data gradients
+      const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
+      if (!th) return GDL_ECUDA;
+      p.tm_w_half = *th;
+      rc = launch_flat<64, 2, 6, false, true>(p, Q, s);
+    }
     if (rc == 0 && mt == 2) rc = launch_flat<64, 2, 6>(p, Q, s);
     if (rc == 0) rc = launch_flat<64, 1, 6>(p, Q, s);
   }
