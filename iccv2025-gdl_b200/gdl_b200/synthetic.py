@@ -124,6 +124,50 @@ class SyntheticCramed(Dataset):
         return spectrogram, images, label
 
 
+class SyntheticCramedDevice(SyntheticCramed):
+    """SyntheticCramed for the device-side visual pipeline (gdl_b200/datapipe.py): the item carries the crop
+    boxes / flips instead of the pixels — drawn from the same RNG stream, in the same order, as
+    SyntheticCramed's torchvision transform — and the decoded frames live in one uint8 store (frame t of item i
+    at index i * fps + t) that the caller uploads once (`attach_pipeline`)."""
+
+    device_pipeline = None  # set by attach_pipeline; read by gdl_b200.train.train_epoch / valid
+
+    def __getstate__(self):  # DataLoader workers never see the CUDA-side pipeline
+        d = dict(self.__dict__)
+        d.pop("device_pipeline", None)
+        return d
+
+    def frame_store(self):
+        """uint8 [len * fps, H, W, 3]: what Image.open(...).convert('RGB') yields for every frame the dataset reads."""
+        fps = self.args.fps
+        out = np.empty((self.len * fps, self.frame_size[1], self.frame_size[0], 3), dtype=np.uint8)
+        for idx in range(self.len):
+            for i in range(fps):
+                out[idx * fps + i] = np.asarray(synth_image("%s/%d" % (self.key(idx), i), self.frame_size))
+        return torch.from_numpy(out)
+
+    def attach_pipeline(self, device):
+        from .datapipe import DeviceFrameStore, VisualPipeline
+        self.device_pipeline = VisualPipeline(DeviceFrameStore(self.frame_store(), device), self.args.fps)
+        return self.device_pipeline
+
+    def __getitem__(self, idx):
+        from .datapipe import draw_frame_params
+        samples, rate = synth_wave(self.key(idx), 2.5, 22050)
+        resamples = np.tile(samples, 3)[:22050 * 3]
+        resamples[resamples > 1.] = 1.
+        resamples[resamples < -1.] = -1.
+        spectrogram = np.log(np.abs(stft(resamples, n_fft=512, hop_length=353)) + 1e-7)
+        fps = self.args.fps
+        select_index = np.random.choice(self.frames_in_dir, size=fps, replace=False)  # drawn, unused (:92-93)
+        select_index.sort()
+        W, H = self.frame_size
+        params = torch.tensor([draw_frame_params(idx * fps + i, H, W, self.mode) for i in range(fps)],
+                              dtype=torch.int32)
+        label = _seed_of(("label", self.key(idx))) % N_LABELS["CREMAD"]
+        return spectrogram, params, label
+
+
 class SyntheticKS(Dataset):
     """Kinetics-Sounds / VGGSound sample contract and draw order (dataset/KSDataset.py:136-201)."""
 

@@ -18,17 +18,24 @@ LOG_EVERY = 100  # the reference prints every 100 steps (main_dgl.py:125,144)
 GRAD_CSV = 'audio_visual_grad_vanilla.csv'  # main_dgl.py:148
 
 
-def _get_step(args, model, optimizer, spec, image):
+def _pipeline_of(dataloader):
+    """The dataset's device-side visual pipeline (datapipe.VisualPipeline), if it delivers crop boxes instead of
+    pixels (synthetic.SyntheticCramedDevice); None for the reference contract (fp32 frames)."""
+    return getattr(getattr(dataloader, "dataset", None), "device_pipeline", None)
+
+
+def _get_step(args, model, optimizer, spec, image, pipeline=None):
     inner = getattr(model, "module", model)
     B = spec.shape[0]
-    key = (B, tuple(spec.shape[1:]), tuple(image.shape[2:]))
+    thw = (pipeline.T, pipeline.S, pipeline.S) if pipeline is not None else tuple(image.shape[2:])
+    key = (B, tuple(spec.shape[1:]), thw)
     st = getattr(inner, "_gdl_step", None)
     if st is not None and getattr(inner, "_gdl_step_key", None) == key:
         return st
     g = optimizer.param_groups[0]
     world = torch.distributed.get_world_size() if torch.distributed.is_available() and \
         torch.distributed.is_initialized() else 1
-    st = DGLStep(inner, B, tuple(spec.shape[1:]), tuple(image.shape[2:]), alpha=args.alpha, lr=g['lr'],
+    st = DGLStep(inner, B, tuple(spec.shape[1:]), thw, alpha=args.alpha, lr=g['lr'],
                  momentum=g.get('momentum', 0.9), weight_decay=g.get('weight_decay', 1e-4), max_norm=40.0,
                  world_size=world, process_group=torch.distributed.group.WORLD if world > 1 else None)
     adopt_momentum(st.arena, optimizer, st)
@@ -83,12 +90,19 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler, wr
         del pending[:]
 
     # one batch of look-ahead: the H2D copy of batch k+1 (copy stream) overlaps the kernels of step k
+    pipe = _pipeline_of(dataloader)
+
+    def prefetch(step, batch):
+        if pipe is None:
+            step.prefetch(*batch)
+        else:  # batch[1] is the int32 [B, T, 6] table of host-drawn crop boxes
+            step.prefetch(batch[0], batch[1].reshape(-1, 6), batch[2], pipeline=pipe)
     it = iter(dataloader)
     nxt = next(it, None)
     st = None
     if nxt is not None:
-        st = _get_step(args, model, optimizer, nxt[0], nxt[1])
-        st.prefetch(*nxt)
+        st = _get_step(args, model, optimizer, nxt[0], nxt[1], pipe)
+        prefetch(st, nxt)
     step_i = -1
     while nxt is not None:
         step_i += 1
@@ -98,10 +112,10 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler, wr
         stats = st.step(lr=optimizer.param_groups[0]['lr'])
         nxt = next(it, None)
         if nxt is not None:
-            st2 = _get_step(args, model, optimizer, nxt[0], nxt[1])
+            st2 = _get_step(args, model, optimizer, nxt[0], nxt[1], pipe)
             if st2 is not st:  # geometry changed (last partial batch without drop_last): new engine
                 st = st2
-            st.prefetch(*nxt)
+            prefetch(st, nxt)
         hist[len(pending)].copy_(stats)
         pending.append(step_i)
         nsteps += 1
@@ -128,8 +142,11 @@ def valid(args, model, device, dataloader):
     with torch.no_grad():
         model.eval()
         print(inner.args.drop)
+        pipe = _pipeline_of(dataloader)
         for spec, image, label in dataloader:
             spec, image, label = spec.to(device), image.to(device), label.to(device)
+            if pipe is not None:
+                image = pipe(image.reshape(-1, 6))
             out, out_a, out_v = model(spec.unsqueeze(1).float(), image.float())
             for i, o in enumerate((out, out_a, out_v)):  # softmax is monotone: arg-max of the logits
                 correct[i] += (o.argmax(1) == label).sum()

@@ -98,12 +98,22 @@ def main(argv=None):
         raise ValueError('Incorrect optimizer: {}'.format(args.optimizer))
     scheduler = optim.lr_scheduler.MultiStepLR(optimizer, eval(args.lr_decay_step), args.lr_decay_ratio)
 
-    if args.audio_path not in ('synthetic', 'synthetic_exact'):
+    if args.audio_path not in ('synthetic', 'synthetic_exact', 'synthetic_device'):
         raise NotImplementedError("this environment ships no datasets: pass --audio_path synthetic (random tensors) "
                                   "or synthetic_exact (the reference's per-item random-draw order on seeded images), "
                                   "or plug the reference's dataset classes (same (spec, images, label) contract) in")
     n = args.synthetic_len or None
-    if args.audio_path == 'synthetic_exact':
+    if args.audio_path == 'synthetic_device':
+        # the reference's draw order with the pixels left on the GPU: items carry crop boxes, the frames are
+        # produced by gdl_crop_resize_normalize from a device-resident uint8 store (CREMA-D contract only)
+        from gdl_b200.synthetic import SyntheticCramedDevice
+        if args.dataset != 'CREMAD':
+            raise NotImplementedError('synthetic_device implements the CREMA-D sample contract only')
+        train_dataset = SyntheticCramedDevice(args, 'train', n or 512)
+        test_dataset = SyntheticCramedDevice(args, 'test', (n and max(n // 8, args.batch_size)) or 64)
+        train_dataset.attach_pipeline(device)
+        test_dataset.attach_pipeline(device)
+    elif args.audio_path == 'synthetic_exact':
         from gdl_b200.synthetic import SyntheticCramed, SyntheticKS
         cls = SyntheticCramed if args.dataset == 'CREMAD' else SyntheticKS
         train_dataset = cls(args, 'train', n or 6698)

@@ -67,3 +67,33 @@ def test_host_draws_follow_the_reference_transform(mode):
         assert p[0] == 5
         got = crop_resize_flip_normalize(np.asarray(img), *p[1:])
         assert np.array_equal(ref.numpy().view(np.uint32), got.view(np.uint32))
+
+
+def test_device_dataset_delivers_the_reference_batch():
+    """synthetic.SyntheticCramedDevice (crop boxes + a uint8 frame store) describes exactly the batch that
+    SyntheticCramed (the reference's per-item torchvision transform) produces from the same RNG state."""
+    import argparse
+    import pickle
+    from gdl_b200.synthetic import SyntheticCramed, SyntheticCramedDevice
+    args = argparse.Namespace(fps=2)
+    for mode in ("train", "test"):
+        ref_ds = SyntheticCramed(args, mode, 3)
+        dev_ds = SyntheticCramedDevice(args, mode, 3)
+        store = dev_ds.frame_store().numpy()
+        assert store.shape == (6, 360, 480, 3)
+        for idx in range(3):
+            torch.manual_seed(20 + idx)
+            np.random.seed(20 + idx)
+            spec_r, images, label_r = ref_ds[idx]
+            state = (torch.get_rng_state(), np.random.get_state()[1].copy())
+            torch.manual_seed(20 + idx)
+            np.random.seed(20 + idx)
+            spec_d, params, label_d = dev_ds[idx]
+            assert torch.equal(torch.get_rng_state(), state[0]) and np.array_equal(np.random.get_state()[1], state[1])
+            assert np.array_equal(spec_r, spec_d) and label_r == label_d
+            assert params.dtype == torch.int32 and tuple(params.shape) == (2, 6)
+            for t, (src, i, j, h, w, flip) in enumerate(params.tolist()):
+                assert src == idx * 2 + t
+                got = crop_resize_flip_normalize(store[src], i, j, h, w, flip)
+                assert np.array_equal(images[:, t].numpy().view(np.uint32), got.view(np.uint32))
+        assert "device_pipeline" not in pickle.loads(pickle.dumps(dev_ds)).__dict__
