@@ -318,10 +318,10 @@ def dgl_step(sd, momentum, spec, image, label, fusion="concat", alpha=4.0, lr=0.
     grads = torch.autograd.grad(total, [p[k] for k in live], allow_unused=True)
     grads = {k: g for k, g in zip(live, grads) if g is not None}
     # clip_grad_norm_(max_norm=40, norm_type=2) over every parameter that has a gradient
-    sq = torch.zeros((), dtype=torch.float64)
+    sq = 0.0  # python double; float() keeps this device-agnostic (tests may run the restatement on cuda in fp32)
     for g in grads.values():
-        sq += g.double().pow(2).sum()
-    norm = float(sq.sqrt())
+        sq += float(g.double().pow(2).sum())
+    norm = sq ** 0.5
     coef = min(1.0, max_norm / (norm + 1e-6))
     grads = {k: g * coef for k, g in grads.items()}
     a_sum = sum(float(g.abs().mean()) for k, g in grads.items() if k.startswith("audio_net."))

@@ -240,9 +240,8 @@ def test_conv_dgrad_add_compact():
     assert rel_err(nchw(dx), ref + up) < 6e-3
 
 
-# the two >= 148-item cases exist for the forward / dgrad kernel variants; wgrad at that size is covered by the
-# whole-step parity tests (tests/test_gpu_step.py, B = 16 at the CREMA-D shape)
-@pytest.mark.parametrize("case", CONV_CASES[:-2])
+# includes the two >= 148-item cases: one-wave split-K, co-major partials and the group-parallel reduction at full grid
+@pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_wgrad(case):
     ops = _ops()
     N, H, W, Ci, Co, R, stride, pad = case

@@ -93,8 +93,16 @@ def test_step_cremad_shape_batch16():
         for g, r in zip(got[:3], ref["losses"]):
             assert abs(g - r) <= 1e-2 * abs(r), (s, got[:3], ref["losses"])
         for i in range(3):
-            agree = (step.logits[i].argmax(1).cpu() == ref["logits"][i].argmax(1)).float().mean().item()
-            assert agree >= 0.995 if s == 0 else agree >= 0.8, (s, i, agree)
+            # north_star: arg-max agreement >= 99.5 %.  With 16 rows that means every row, on both steps, except
+            # rows the fp32 reference itself cannot separate at bf16 resolution (top-2 margin below 2^-8 of the
+            # logit scale); the statistically meaningful count (3 x 256 rows, two steps) is in
+            # tests/test_gpu_parity_at_size.py.
+            rl = ref["logits"][i]
+            top2 = rl.topk(2, dim=1).values
+            separable = (top2[:, 0] - top2[:, 1]) > rl.abs().max() * 2.0 ** -8
+            same = step.logits[i].argmax(1).cpu() == rl.argmax(1)
+            assert bool((same | ~separable).all()), (s, i, same.float().mean().item())
+            assert same.float().mean().item() >= (0.995 if s == 0 else 0.93), (s, i, same.float().mean().item())
         assert abs(got[3] - ref["grad_norm"]) <= 3e-2 * ref["grad_norm"]
         if s == 0:
             for k, g32 in ref["grads"].items():
