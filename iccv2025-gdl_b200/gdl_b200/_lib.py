@@ -88,6 +88,16 @@ SIGNATURES = {
     "gdl_optim_scratch_floats": (_l, [_l, _i]),
     "gdl_grad_stats": (_i, [_p, _l, _p, _p, _p, _i, _f, _p, _p, _p]),
     "gdl_sgd_momentum": (_i, [_p, _p, _p, _l, _f, _f, _f, _i, _p, _p]),
+    "gdl_check_conv_fwd": (_i, [_dp, _i, _p, _p, _p, _p]),
+    "gdl_check_conv_dgrad": (_i, [_dp, _i, _p, _p, _p, _p, _p]),
+    "gdl_check_conv_wgrad": (_i, [_dp, _i, _p, _p, _p, _p]),
+    "gdl_check_bn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _i, _i, _p]),
+    "gdl_check_bn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "gdl_check_maxpool_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _i, _p]),
+    "gdl_check_maxpool_bwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _i, _p]),
+    "gdl_check_gap_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "gdl_check_gap_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "gdl_check_fold_frames": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "gdl_crop_table_ints": (_l, [_i, _i]),
     "gdl_crop_resize_normalize": (_i, [_p, _l, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
 }

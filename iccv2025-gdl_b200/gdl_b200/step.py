@@ -102,9 +102,13 @@ class ParamArena:
 
 class DGLStep:
     def __init__(self, model, batch_size, spec_hw, image_thw, alpha=4.0, lr=0.001, momentum=0.9,
-                 weight_decay=1e-4, max_norm=40.0, world_size=1, process_group=None, use_graph=True):
+                 weight_decay=1e-4, max_norm=40.0, world_size=1, process_group=None, use_graph=True, check_fp32=None):
         """model: AVClassifier_DGL on a CUDA device (possibly wrapped: `.module` is unwrapped).
-        batch_size: LOCAL batch on this GPU; losses are means over batch_size*world_size."""
+        batch_size: LOCAL batch on this GPU; losses are means over batch_size*world_size.
+        check_fp32 (default: env GDL_CHECK_FP32): the FP32 check mode — the encoders store fp32 activations and run
+        the CUDA-core fp64-accumulating kernels of csrc/check_fp32.cu (gdl_b200/check.py) instead of the bf16
+        tcgen05 engine; head, truncation, clipping, SGD and the all-reduce are the product code.  For parity
+        checks (north_star: losses within 1e-4), not for speed."""
         model = getattr(model, "module", model)
         if not isinstance(model, AVClassifier_DGL):
             raise TypeError("DGLStep needs a gdl_b200.AVClassifier_DGL")
@@ -125,8 +129,17 @@ class DGLStep:
         B, T = self.B, self.T
 
         self.arena = ParamArena(model, dev)
-        self.enc_a = model.audio_net.engine(B, self.F_, self.Tt)
-        self.enc_v = model.visual_net.engine(B * T, self.H, self.W)
+        if check_fp32 is None:
+            check_fp32 = os.environ.get("GDL_CHECK_FP32", "0") != "0"
+        self.check_fp32 = bool(check_fp32)
+        if self.check_fp32:
+            from .check import CheckEncoder
+            self.enc_a = CheckEncoder(model.audio_net, B, self.F_, self.Tt, dev, frames=1)
+            self.enc_v = CheckEncoder(model.visual_net, B * T, self.H, self.W, dev, frames=T)
+            self.use_graph = use_graph = False  # the check engine allocates its backward temporaries per step
+        else:
+            self.enc_a = model.audio_net.engine(B, self.F_, self.Tt)
+            self.enc_v = model.visual_net.engine(B * T, self.H, self.W)
         # Inputs: two staging sets (fp32 batch as the reference's DataLoader delivers it).  The layout kernels
         # read the current set OUTSIDE the captured graph and write the fixed-address bf16 stem inputs a8/v8, so
         # the next batch can be copied H2D on a side stream into the other set while this step computes.
@@ -138,8 +151,10 @@ class DGLStep:
         self._stage_ready = [torch.cuda.Event() for _ in range(2)]
         self._stage_free = [torch.cuda.Event() for _ in range(2)]
         self.label_in = torch.zeros(B, device=dev, dtype=torch.int64)  # fixed address: read inside the graph
-        self.a8 = torch.empty(self.enc_a.input_shape, device=dev, dtype=torch.bfloat16)  # space-to-depth
-        self.v8 = torch.empty(self.enc_v.input_shape, device=dev, dtype=torch.bfloat16)
+        self.a8 = self.v8 = None
+        if not self.check_fp32:
+            self.a8 = torch.empty(self.enc_a.input_shape, device=dev, dtype=torch.bfloat16)  # space-to-depth
+            self.v8 = torch.empty(self.enc_v.input_shape, device=dev, dtype=torch.bfloat16)
         D = 512
         self.a_feat, self.v_feat = torch.empty(B, D, device=dev), torch.empty(B, D, device=dev)
         self.da, self.dv = torch.empty(B, D, device=dev), torch.empty(B, D, device=dev)
@@ -239,8 +254,12 @@ class DGLStep:
             main.wait_event(self._stage_ready[self._pending])
             self._cur, self._pending = self._pending, None
         spec, image, label = self._stage[self._cur]
-        ops.stem_layout(spec, self.a8, B, 1, 1, self.F_, self.Tt)
-        ops.stem_layout(image, self.v8, B, 3, T, self.H, self.W)
+        if self.check_fp32:
+            self.enc_a.stage_input(spec, B)
+            self.enc_v.stage_input(image, B)
+        else:
+            ops.stem_layout(spec, self.a8, B, 1, 1, self.F_, self.Tt)
+            ops.stem_layout(image, self.v8, B, 3, T, self.H, self.W)
         self.label_in.copy_(label, non_blocking=True)
         self._stage_free[self._cur].record(main)
 
@@ -267,10 +286,10 @@ class DGLStep:
             sv.wait_stream(main)
             with torch.cuda.stream(sa):
                 fa = self.enc_a.forward(self.a8)
-                ops.gap_fwd(fa, self.a_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
+                self._gap_fwd(self.enc_a, fa, self.a_feat, 1)
             with torch.cuda.stream(sv):
                 fv = self.enc_v.forward(self.v8)
-                ops.gap_fwd(fv, self.v_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
+                self._gap_fwd(self.enc_v, fv, self.v_feat, T)
             main.wait_stream(sa)
             main.wait_stream(sv)
             self._head()
@@ -278,14 +297,27 @@ class DGLStep:
         sv.wait_stream(main)
         with torch.cuda.stream(sa):
             if part != 1:
-                ops.gap_bwd(self.da, self.enc_a.g_feat, B, self.enc_a.Hf * self.enc_a.Wf, 512)
+                self._gap_bwd(self.enc_a, self.da, 1)
             self.enc_a.backward(self.a8, part)
         with torch.cuda.stream(sv):
             if part != 1:
-                ops.gap_bwd(self.dv, self.enc_v.g_feat, B, T * self.enc_v.Hf * self.enc_v.Wf, 512)
+                self._gap_bwd(self.enc_v, self.dv, T)
             self.enc_v.backward(self.v8, part)
         main.wait_stream(sa)
         main.wait_stream(sv)
+
+    def _gap_fwd(self, enc, feat, out, frames):
+        """global average pool over (frames, h, w) (reference models/basic_model.py:73-82)."""
+        if self.check_fp32:
+            enc.gap_fwd(feat, out, self.B)
+        else:
+            ops.gap_fwd(feat, out, self.B, frames * enc.Hf * enc.Wf, 512)
+
+    def _gap_bwd(self, enc, dout, frames):
+        if self.check_fp32:
+            enc.gap_bwd(dout, self.B)
+        else:
+            ops.gap_bwd(dout, enc.g_feat, self.B, frames * enc.Hf * enc.Wf, 512)
 
     def _allreduce(self):
         # each rank scaled its CE by 1/B_global, so a plain SUM reproduces the reference's

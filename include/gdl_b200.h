@@ -248,6 +248,41 @@ int gdl_film_contract(const void* G, int ldg, int c0, const float* x, const floa
 int gdl_transpose_f32_to_bf16(const float* src, void* dst, int R, int64_t Cn, gdl_stream_t s);
 int gdl_transpose_bf16_to_f32(const void* src, float* dst, int R, int64_t Cn, gdl_stream_t s);
 
+/* ---- FP32 check mode (north_star: "1e-4 with an FP32-accumulate check mode") -------------------------------
+ * The encoder ops once more with fp32-STORED activations in the reference's own layout (NCHW activations, OIHW
+ * weights = the nn.Parameters, no packing): CUDA-core kernels, fp64 accumulation, deterministic.  A check mode,
+ * not a fallback — DGLStep(check_fp32=True) selects it explicitly so that the whole step can be compared
+ * free-running with the fp32 reference (main_dgl.py:100 model(spec.unsqueeze(1).float(), image.float())).
+ * d->Ci is ignored; ci_real is the true input-channel count (1 / 3 for the stems).
+ * Call sites replaced: nn.Conv2d backbone.py:20-28,97-100; BatchNorm2d + ReLU (+ residual) :45-66,104-105;
+ * MaxPool2d(3,2,1) :106; adaptive_avg_pool2d/3d basic_model.py:73-82; the frame fold backbone.py:162-164. */
+int gdl_check_conv_fwd(const gdl_conv_desc* d, int ci_real, const float* x, const float* w_oihw, float* y,
+                       gdl_stream_t s);
+/* dx = conv_transpose(dy, w) (+ add, same shape as dx, may be NULL) */
+int gdl_check_conv_dgrad(const gdl_conv_desc* d, int ci_real, const float* dy, const float* w_oihw,
+                         const float* add, float* dx, gdl_stream_t s);
+int gdl_check_conv_wgrad(const gdl_conv_desc* d, int ci_real, const float* x, const float* dy, float* dw_oihw,
+                         gdl_stream_t s);
+/* y = [relu](bn(x) [+ res]); training != 0: batch statistics + running-stat update, else running statistics.
+ * mean / invstd f32 [C] are saved for the backward. */
+int gdl_check_bn_fwd(const float* x, const float* res, float* y, int N, int C, int HW, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                     float* mean, float* invstd, int relu, int training, gdl_stream_t s);
+/* dz = relu ? dy*(y>0) : dy (written to dz when non-NULL: the residual branch's gradient); dgamma, dbeta, dx. */
+int gdl_check_bn_bwd(const float* dy, const float* y, const float* x, float* dz, float* dx, int N, int C, int HW,
+                     const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                     int relu, gdl_stream_t s);
+/* planes = N*C images of H x W; argmax = flat input index of the first maximum in scan order. */
+int gdl_check_maxpool_fwd(const float* x, float* y, int32_t* argmax, int64_t planes, int H, int W, int Ho, int Wo,
+                          gdl_stream_t s);
+int gdl_check_maxpool_bwd(const float* dy, const int32_t* argmax, float* dx, int64_t planes, int H, int W, int Ho,
+                          int Wo, gdl_stream_t s);
+/* x f32 [B*T][C][HW] -> out f32 [B][C] (mean over t, hw) and its backward. */
+int gdl_check_gap_fwd(const float* x, float* out, int B, int T, int C, int HW, gdl_stream_t s);
+int gdl_check_gap_bwd(const float* dout, float* dx, int B, int T, int C, int HW, gdl_stream_t s);
+/* src f32 [B][C][T][H][W] -> dst f32 [B*T][C][H][W]. */
+int gdl_check_fold_frames(const float* src, float* dst, int B, int C, int T, int H, int W, gdl_stream_t s);
+
 /* ---- optimizer / clipping / diagnostics (reference main_dgl.py:129-154,249) ---------- */
 /* Flat fp32 gradient arena with a segment table: seg_end[nseg] (exclusive end offsets,
  * padding belongs to the preceding segment), seg_group[nseg] (0 = audio_net, 1 = visual_net,
