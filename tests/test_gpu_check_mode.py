@@ -50,7 +50,9 @@ def _run(fusion, dataset, B, shape, nsteps, lr=0.01, label_max=None, check_grads
                 gg = names[k].grad.detach().float().cpu()  # clipped in place by the SGD kernel, like the reference
                 rows.append((cos(gg, g), gg.double().norm().item() / max(g.double().norm().item(), 1e-30), k))
         agree = [(step.logits[i].argmax(1).cpu() == ref["logits"][i].argmax(1)).float().mean().item() for i in range(3)]
-        dmax = max((names[k].detach().cpu() - v).abs().max().item() / (v.abs().max().item() + 1e-12)
+        # updated parameters (momentum, weight decay, clip all applied): error relative to the tensor's scale, where
+        # a zero-initialised bias has the scale of one update (lr)
+        dmax = max((names[k].detach().cpu() - v).abs().max().item() / (v.abs().max().item() + lr)
                    for k, v in sd.items() if k in names)
         bmax = max((bufs[k].detach().float().cpu() - v.float()).abs().max().item() / (v.float().abs().max().item() + 1e-12)
                    for k, v in sd.items() if k in bufs)
