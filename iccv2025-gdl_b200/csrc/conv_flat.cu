@@ -39,7 +39,7 @@ struct FlatTap {
 struct FlatParams {
   CUtensorMap tm_x[4];  // {Cs, Ws, Hs, N} views of the source (one per parity plane), box {64, P, 1, 1}
   CUtensorMap tm_w;  // {K, rows} packed weights, box {64, BN}
-  CUtensorMap tm_w_half;  // CL kernels: box {64, BN/2} (each CTA of the pair loads one half and multicasts it)
+  CUtensorMap tm_w_half;  // CTA-pair kernel: box {64, BN/2} (each CTA of a pair holds one half of every weight tile)
   bf16* dst;
   const bf16* add_src;
   float* stats;  // optional [gridDim.x * 4 epilogue warps][2][Cd]: per-warp sum / sum of squares of the bf16 outputs
@@ -71,12 +71,10 @@ __device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
 // RES: the whole packed weight matrix of the layer (taps x slabs tiles of BN x 64) is loaded ONCE per CTA and stays in
 // shared memory (64 -> 64 channel 3x3 layers: 9 tiles = 72 KB), instead of being streamed from L2 for every 256-pixel
 // item: the weight ring is 2/3 of the L2 -> SM traffic of those layers.  One class, one channel tile.
-// CL: CTA pairs (cluster of 2).  The two CTAs of a pair work on neighbouring pixel tiles of the SAME channel tile,
-// so they consume the same sequence of weight tiles: each loads one half of every tile and TMA-multicasts it into
-// both shared memories (half the L2 -> SM weight traffic per SM, which is what bounds these kernels — see RES).
-// A weight stage is refilled only after BOTH consumers released it (tcgen05.commit multicast, barrier count 2).
-// NOT YET VALIDATED ON HARDWARE: opt-in (GDL_FLAT_CLUSTER=1), written after the round's GPU budget was spent.
-template <int BN, int MT, int WST, bool STATS, bool RES = false, bool CL = false>
+// (A cluster-of-2 variant that TMA-MULTICAST each weight tile into both CTAs was validated and measured in round 2:
+// 0.97-1.01x on every layer — L2 already de-duplicates concurrent requests for the same lines and every SM still
+// receives and reads the whole tile — and was removed; the CTA-pair kernel below splits the tile instead.)
+template <int BN, int MT, int WST, bool STATS, bool RES = false>
 __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid_constant__ FlatParams p) {
   constexpr int W_BYTES = BN * 128;
   constexpr int TM = MT * 128;
@@ -97,11 +95,10 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
   const int warp = warp_uniform_idx();
   const int slabs = p.Cs >> 6;
   const int WS = p.win_stages;
-  const int rank = CL ? (int)cluster_ctarank() : 0;
-  const int item_first = CL ? int(blockIdx.x >> 1) : int(blockIdx.x);
-  const int item_stride = CL ? int(gridDim.x >> 1) : int(gridDim.x);
-  const int mt_count = CL ? (p.mtiles + 1) / 2 : p.mtiles;  // pixel-tile slots per (class, channel tile)
-  const int mt_max = CL ? 2 * mt_count : p.mtiles;            // a pair's odd tail tile is all padding
+  const int item_first = int(blockIdx.x);
+  const int item_stride = int(gridDim.x);
+  const int mt_count = p.mtiles;  // pixel-tile slots per (class, channel tile)
+  const int mt_max = p.mtiles;
   const int per_class = p.ntiles * mt_count;
   const int items_total = p.nclass * per_class;
 
@@ -112,7 +109,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
     }
     for (int i = 0; i < WST; ++i) {
       mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], CL ? 2 : 1);
+      mbar_init(&w_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -130,7 +127,6 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (CL) cluster_sync_all();  // the peer's barriers exist before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
@@ -151,7 +147,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
       const int nt = rem / mt_count;
-      const int mt_i = (rem - nt * mt_count) * (CL ? 2 : 1) + rank;
+      const int mt_i = rem - nt * mt_count;
       const int q0 = (p.rev ? mt_max - 1 - mt_i : mt_i) * TM;
       const int n0 = nt * BN;
       const int rho_a = floor_div(q0 + p.smin, p.P);
@@ -175,12 +171,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
             for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
               const int st = wcount % WST;
               if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
-              mbar_arrive_expect_tx(&w_full[st], W_BYTES);  // own half + the peer's half
-              if (CL)
-                tma_load_2d_multicast(smem_base + w_off + st * W_BYTES + rank * (W_BYTES / 2), &p.tm_w_half, &w_full[st],
-                                      p.taps[cls][t].wk + slab * 64, n0 + rank * (BN / 2), (uint16_t)3);
-              else
-                tma_load_2d(smem_base + w_off + st * W_BYTES, &p.tm_w, &w_full[st], p.taps[cls][t].wk + slab * 64, n0);
+              mbar_arrive_expect_tx(&w_full[st], W_BYTES);
+              tma_load_2d(smem_base + w_off + st * W_BYTES, &p.tm_w, &w_full[st], p.taps[cls][t].wk + slab * 64, n0);
             }
         }
       }
@@ -207,7 +199,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
       const int nt = rem / mt_count;
-      const int mt_i = (rem - nt * mt_count) * (CL ? 2 : 1) + rank;
+      const int mt_i = rem - nt * mt_count;
       const int q0 = (p.rev ? mt_max - 1 - mt_i : mt_i) * TM;
       const int rho_a = floor_div(q0 + p.smin, p.P);
       const int o = q0 + p.smin - rho_a * p.P;  // first window row inside the stage
@@ -241,10 +233,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
                 mma_bf16_acc(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi),
                              desc_join(b_lo + 2 * k, ab_hi), idesc);
             }
-            if (CL)
-              mma_commit_multicast(&w_empty[st], (uint16_t)3);
-            else if (!RES)
-              mma_commit(&w_empty[st]);
+            if (!RES) mma_commit(&w_empty[st]);
           }
           mma_commit(&win_empty[ws]);
         }
@@ -286,7 +275,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int cls = item / per_class;
       const int rem = item - cls * per_class;
       const int nt = rem / mt_count;
-      const int mt_i = (rem - nt * mt_count) * (CL ? 2 : 1) + rank;
+      const int mt_i = rem - nt * mt_count;
       const int q0 = (p.rev ? mt_max - 1 - mt_i : mt_i) * TM;
       const int n0 = nt * BN;
       const int acc = it & 1;
@@ -391,14 +380,271 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (CL) cluster_sync_all();  // no CTA of the pair exits while the other may still signal its barriers
   if (warp == 4) tmem_dealloc(tmem_base, 2 * MT * BN);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant: tcgen05.mma.cta_group::2 (tc05.cuh).  A cluster of two CTAs (one TPC) owns 2*MT*128 CONSECUTIVE
+// flat pixels of one channel tile: CTA r holds the window of its own MT*128 pixels and HALF (BN/2 rows) of every
+// weight tile; the leader (rank 0) issues one M = 256 MMA per K step that reads A and its half of B from each
+// CTA's shared memory and accumulates each CTA's 128 rows in that CTA's TMEM.  Per SM this halves both the weight
+// bytes fetched from L2 and the B bytes read from shared memory per MMA — the two resources that hold the
+// single-CTA kernel at ~55 % tensor-pipe activity (an M128 x N128 x K16 MMA reads 8 KB of operands in 64 clocks =
+// the whole 128 B/clk of shared-memory bandwidth, while TMA writes the next tiles into the same memory).
+// The A descriptor is shared by both CTAs, so both place the first pixel of their window at the SAME shared-memory
+// offset: window rows land (P-1-o) pixel rows into the stage (o = the tile's phase inside its first padded row).
+//   full barriers  (window / weights): in the LEADER, 2 arrivals (each producer announces its own bytes;
+//                  both CTAs' TMA loads complete_tx on the leader's barrier: cp.async.bulk.tensor.cta_group::2)
+//   empty barriers (window / weights / accumulator-ready): one per CTA, released by tcgen05.commit.cta_group::2
+//                  multicast to both
+//   tmem_empty     : in the leader, 8 arrivals (one per epilogue warp of both CTAs, remote arrive from the peer)
+template <int BN, int MT, int WST>
+__global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __grid_constant__ FlatParams p) {
+  constexpr int HB = BN / 2;
+  constexpr int W_BYTES = HB * 128;
+  constexpr int TM = MT * 128;
+  constexpr int kMaxWin = 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int w_off = p.win_stages * p.win_stage_bytes;
+  const int bar_off = w_off + WST * W_BYTES;
+  uint64_t* win_full = reinterpret_cast<uint64_t*>(smem + bar_off);
+  uint64_t* win_empty = win_full + kMaxWin;
+  uint64_t* w_full = win_empty + kMaxWin;
+  uint64_t* w_empty = w_full + WST;
+  uint64_t* tmem_full = w_empty + WST;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = warp_uniform_idx();
+  const int slabs = p.Cs >> 6;
+  const int WS = p.win_stages;
+  const int rank = (int)cluster_ctarank();
+  const int item_first = int(blockIdx.x >> 1);
+  const int item_stride = int(gridDim.x >> 1);
+  const int mt_count = (p.mtiles + 1) / 2;  // pairs of pixel tiles per (class, channel tile); an odd tail tile is padding
+  const int per_class = p.ntiles * mt_count;
+  const int items_total = p.nclass * per_class;
+
+  if (tid == 0) {
+    for (int i = 0; i < kMaxWin; ++i) {
+      mbar_init(&win_full[i], 2);
+      mbar_init(&win_empty[i], 1);
+    }
+    for (int i = 0; i < WST; ++i) {
+      mbar_init(&w_full[i], 2);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc2(tmem_slot, 2 * MT * BN);
+    tmem_relinquish2();
+  }
+  if (tid == 5 * 32) {
+    tma_prefetch_desc(&p.tm_x[0]);
+    tma_prefetch_desc(&p.tm_w_half);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit / remote complete_tx
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  auto tile_of = [&](int item, int& cls, int& nt, int& q0) {
+    cls = item / per_class;
+    const int rem = item - cls * per_class;
+    nt = rem / mt_count;
+    const int pr = rem - nt * mt_count;
+    q0 = ((p.rev ? mt_count - 1 - pr : pr) * 2 + rank) * TM;
+  };
+
+  if (warp == 5 && elect_one()) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    const int rows_img = p.Hs + 1;
+    const uint32_t row_bytes = (uint32_t)p.P * 128u;
+    int wincount = 0, wcount = 0;
+    for (int item = item_first; item < items_total; item += item_stride) {
+      int cls, nt, q0;
+      tile_of(item, cls, nt, q0);
+      const int n0 = nt * BN + rank * HB;
+      const int rho_a = floor_div(q0 + p.smin, p.P);
+      const int rho_b = floor_div(q0 + TM + p.smax - 1, p.P);
+      const int nrows = rho_b - rho_a + 1;
+      const int o = q0 + p.smin - rho_a * p.P;  // phase of the window's first pixel inside its first padded row
+      const int ngrp = p.ngroups[cls];
+      for (int slab = 0; slab < slabs; ++slab) {
+        for (int g = 0; g < ngrp; ++g, ++wincount) {
+          const int ws = wincount % WS;
+          if (wincount >= WS) mbar_wait(&win_empty[ws], ((wincount / WS) - 1) & 1);
+          const uint32_t full = mapa_u32(smem_u32(&win_full[ws]), 0);
+          mbar_arrive_expect_tx_cluster(full, (uint32_t)nrows * row_bytes);
+          const uint32_t sdst = smem_base + ws * p.win_stage_bytes + (uint32_t)(p.P - 1 - o) * 128u;
+          const CUtensorMap* tmx = &p.tm_x[p.gplane[cls][g]];
+          for (int i = 0; i < nrows; ++i) {
+            const int rho = rho_a + i;
+            const int n = floor_div(rho, rows_img);
+            const int h = rho - n * rows_img;
+            tma2_load_4d(sdst + i * row_bytes, tmx, full, slab * 64, 0, h, n);
+          }
+          for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
+            const int st = wcount % WST;
+            if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
+            const uint32_t wfull = mapa_u32(smem_u32(&w_full[st]), 0);
+            mbar_arrive_expect_tx_cluster(wfull, W_BYTES);
+            tma2_load_2d(smem_base + w_off + st * W_BYTES, &p.tm_w_half, wfull, p.taps[cls][t].wk + slab * 64, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 4 && rank == 0 && elect_one()) {
+    // ------------------------------ MMA issuer (leader only) ------------------------------
+    if (tmem_base != 0) {
+      printf("gdl: conv_flat2 expects TMEM base 0, got %u\n", tmem_base);
+      __trap();
+    }
+    constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+    const uint32_t ab_hi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo_sw128(smem_base, 16), b_lo0 = desc_lo_sw128(smem_base + w_off, 16);
+    int wincount = 0, wcount = 0, it = 0;
+    for (int item = item_first; item < items_total; item += item_stride, ++it) {
+      const int cls = item / per_class;
+      const int acc = it & 1;
+      if (it >= 2) {
+        mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t d_tmem = acc * (MT * BN);
+      const int ngrp = p.ngroups[cls];
+      for (int slab = 0; slab < slabs; ++slab) {
+        for (int g = 0; g < ngrp; ++g, ++wincount) {
+          const int ws = wincount % WS;
+          mbar_wait(&win_full[ws], (wincount / WS) & 1);
+          tc_fence_after();
+          // pixel q0 + shift sits (P - 1 + shift - smin) pixel rows into the stage, in both CTAs
+          const uint32_t a_win = a_lo0 + ((ws * p.win_stage_bytes) >> 4) + (p.P - 1 - p.smin) * 8;
+          for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
+            const int st = wcount % WST;
+            mbar_wait(&w_full[st], (wcount / WST) & 1);
+            tc_fence_after();
+            const uint32_t a_lo = a_win + p.taps[cls][t].shift * 8;
+            const uint32_t b_lo = b_lo0 + st * (W_BYTES >> 4);
+            const uint32_t first = (slab | t) != 0 ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+              mma2_bf16_ss(d_tmem + j * BN, desc_join(a_lo + j * 1024, ab_hi), desc_join(b_lo, ab_hi), idesc, first);
+#pragma unroll
+              for (int k = 1; k < 4; ++k)
+                mma2_bf16_acc(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi),
+                              desc_join(b_lo + 2 * k, ab_hi), idesc);
+            }
+            mma2_commit_both(&w_empty[st]);
+          }
+          mma2_commit_both(&win_empty[ws]);
+        }
+      }
+      mma2_commit_both(&tmem_full[acc]);
+    }
+  } else if (warp < 4) {
+    // ------------------------------ epilogue (both CTAs: own 128 rows x MT) ------------------------------
+    constexpr int NV = BN / 8;
+    const int lane = tid & 31;
+    const uint32_t empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0), empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    int it = 0;
+    for (int item = item_first; item < items_total; item += item_stride, ++it) {
+      int cls, nt, q0;
+      tile_of(item, cls, nt, q0);
+      const int n0 = nt * BN;
+      const int acc = it & 1;
+      bf16* outp[MT];
+      const bf16* addp[MT];
+      bool validj[MT];
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int q = q0 + j * 128 + tid;
+        const int n = q / p.IS;
+        const int r2 = q - n * p.IS;
+        const int h = r2 / p.P, w = r2 - h * p.P;
+        const int hd = h * p.dscale + p.ph[cls], wd = w * p.dscale + p.pw[cls];
+        validj[j] = n < p.N && h < p.Hs && w < p.Ws && hd < p.Hd && wd < p.Wd;
+        const size_t off = ((size_t)((size_t)n * p.Hd + hd) * p.Wd + wd) * p.Cd + n0;
+        outp[j] = p.dst + off;
+        addp[j] = nullptr;
+        if (validj[j] && p.add_mode == 1)
+          addp[j] = p.add_src + off;
+        else if (validj[j] && p.add_mode == 2 && (p.ph[cls] | p.pw[cls]) == 0)
+          addp[j] = p.add_src + ((size_t)((size_t)n * p.Hs + h) * p.Ws + w) * p.Cd + n0;
+      }
+      U32B res[NV / 2];
+      const U32B zero32 = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      if (p.add_mode != 0) {
+#pragma unroll
+        for (int v = 0; v < NV / 2; ++v) res[v] = addp[0] ? ld_stream32(addp[0] + v * 16) : zero32;
+      }
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16) + acc * (MT * BN);
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        U32B nres[NV / 2];
+        if (p.add_mode != 0 && j + 1 < MT) {
+#pragma unroll
+          for (int v = 0; v < NV / 2; ++v) nres[v] = addp[j + 1] ? ld_stream32(addp[j + 1] + v * 16) : zero32;
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + j * BN + c0, r);
+          tmem_ld_wait();
+          if (validj[j]) {
+#pragma unroll
+            for (int g = 0; g < 4; g += 2) {
+              uint4 o[2];
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[(g + h2) * 8 + i]);
+                if (p.add_mode != 0) {
+                  float a[8];
+                  const U32B& rv = res[(c0 / 8 + g) / 2];
+                  unpack8(h2 == 0 ? rv.lo : rv.hi, a);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] += a[i];
+                }
+                o[h2] = pack8(f);
+              }
+              st_global32(outp[j] + c0 + g * 8, o[0], o[1]);
+            }
+          }
+        }
+        if (p.add_mode != 0 && j + 1 < MT) {
+#pragma unroll
+          for (int v = 0; v < NV / 2; ++v) res[v] = nres[v];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? empty1 : empty0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA exits (or frees TMEM) while the leader's MMAs may still read its shared memory
+  if (warp == 4) tmem_dealloc2(tmem_base, 2 * MT * BN);
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int BN, int MT, int WST, bool RES = false, bool CL = false>
+template <int BN, int MT, int WST, bool RES = false>
 static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   constexpr int TM = MT * 128;
   const int nrows_max = (TM + p.smax - p.smin - 1 + p.P - 1) / p.P + 1;
@@ -417,34 +663,6 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   p.items_total = p.nclass * p.ntiles * p.mtiles;
   int total = ws * p.win_stage_bytes + fixed + 1024;
   if (total < 116 * 1024) total = 116 * 1024;  // one CTA per SM: the kernel relies on TMEM base 0
-  if constexpr (CL) {
-    if (RES || p.stats != nullptr) return 0;
-    static bool cl_attr_set = false;
-    if (!cl_attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, false, false, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_flat cluster)");
-      cl_attr_set = true;
-    }
-    const int64_t pairs = (int64_t)p.nclass * p.ntiles * ((p.mtiles + 1) / 2);
-    int grid2 = int(2 * pairs < kNumSMs ? 2 * pairs : kNumSMs) & ~1;
-    if (grid2 < 2) return 0;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid2);
-    cfg.blockDim = dim3(kFlatThreads);
-    cfg.dynamicSmemBytes = total;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_flat_kernel<BN, MT, WST, false, false, true>, p);
-    if (e != cudaSuccess) return cuda_fail(e, "conv_flat_kernel(cluster)");
-    return 1;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, false, RES>,
@@ -466,6 +684,51 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   else
     conv_flat_kernel<BN, MT, WST, false><<<grid, kFlatThreads, total, s>>>(p);
   GDL_CHECK_LAUNCH("conv_flat_kernel");
+  return 1;
+}
+
+// CTA-pair kernel: p.tm_w_half must hold the {64, BN/2} weight map.  Returns 0 when not eligible.
+template <int BN, int MT, int WST>
+static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
+  constexpr int TM = MT * 128;
+  if (p.stats != nullptr) return 0;
+  const int nrows_max = (TM + p.smax - p.smin - 1 + p.P - 1) / p.P + 1;
+  // + P-1 pixel rows: both CTAs of a pair start their window at the same offset whatever its phase in the padded row
+  p.win_stage_bytes = ((nrows_max * p.P + p.P - 1) * 128 + 1023) / 1024 * 1024;
+  const int fixed = WST * (BN / 2) * 128 + 512;
+  int ws = (kFlatSmemBudget - fixed) / p.win_stage_bytes;
+  if (ws > 4) ws = 4;
+  if (ws < 2) return 0;
+  p.win_stages = ws;
+  p.mtiles = int((Q + TM - 1) / TM);
+  p.ntiles = p.Cd / BN;
+  p.items_total = p.nclass * p.ntiles * p.mtiles;
+  int total = ws * p.win_stage_bytes + fixed + 1024;
+  if (total < 116 * 1024) total = 116 * 1024;  // one CTA per SM (TMEM base 0)
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(conv_flat2_kernel<BN, MT, WST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_flat2)");
+    attr_set = true;
+  }
+  const int64_t pairs = (int64_t)p.nclass * p.ntiles * ((p.mtiles + 1) / 2);
+  const int grid2 = int(2 * pairs < kNumSMs ? 2 * pairs : kNumSMs) & ~1;
+  if (grid2 < 2) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid2);
+  cfg.blockDim = dim3(kFlatThreads);
+  cfg.dynamicSmemBytes = total;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST>, p);
+  if (e != cudaSuccess) return cuda_fail(e, "conv_flat2_kernel");
   return 1;
 }
 
@@ -600,15 +863,15 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   int mt = items2 >= kNumSMs ? 2 : 1;
   if (mt_force) mt = mt_force;
   int rc = 0;
-  // GDL_FLAT_CLUSTER=1: CTA pairs with multicast weight tiles (see the kernel comment; forward parity verified on
-  // one 128-channel case, speed not yet measured on a B200 — off by default)
-  static const int cluster = env_int3("GDL_FLAT_CLUSTER", 0);
+  // GDL_FLAT_PAIR (default 1): CTA-pair kernel (cta_group::2) for the 128-channel tiles when there are at least 74
+  // pairs of 256-pixel tiles (one wave of clusters)
+  static const int pair = env_int3("GDL_FLAT_PAIR", 1);
   if (BN == 128) {
-    if (cluster && mt == 2 && stats == nullptr) {
+    if (pair && mt == 2 && stats == nullptr && items2 >= kNumSMs) {
       const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
       if (!th) return GDL_ECUDA;
       p.tm_w_half = *th;
-      rc = launch_flat<128, 2, 4, false, true>(p, Q, s);
+      rc = launch_flat2<128, 2, 6>(p, Q, s);
     }
     if (rc == 0 && mt == 2) rc = launch_flat<128, 2, 4>(p, Q, s);
     if (rc == 0) rc = launch_flat<128, 1, 4>(p, Q, s);
@@ -618,12 +881,6 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
     static const int resident = env_int3("GDL_FLAT_RESIDENT", 1);
     if (resident && mt == 2 && Cs == 64 && Cd == 64 && (kind == 0 || kind == 1) && stats == nullptr)
       rc = launch_flat<64, 2, 6, true>(p, Q, s);
-    if (rc == 0 && cluster && mt == 2 && stats == nullptr) {  // e.g. the 128 -> 64 channel stride-2 data gradients
-      const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
-      if (!th) return GDL_ECUDA;
-      p.tm_w_half = *th;
-      rc = launch_flat<64, 2, 6, false, true>(p, Q, s);
-    }
     if (rc == 0 && mt == 2) rc = launch_flat<64, 2, 6>(p, Q, s);
     if (rc == 0) rc = launch_flat<64, 1, 6>(p, Q, s);
   }

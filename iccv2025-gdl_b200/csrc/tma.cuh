@@ -61,6 +61,25 @@ __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst_smem, const C
       : "memory");
 }
 
+// cta_group::2 forms: the box lands in THIS CTA's shared memory, the transaction bytes complete on the mbarrier
+// given by a shared::cluster address, which may live in the other CTA of the pair (the leader's "full" barrier).
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                             int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                             int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // smem -> global tile store (bulk async group); out-of-bounds elements are clipped.
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2,
                                              int c3) {

@@ -41,7 +41,12 @@ CONV_CASES = [
     (5, 14, 14, 128, 256, 3, 2, 1),
     (40, 9, 6, 512, 512, 3, 1, 1),
     (40, 56, 56, 64, 64, 3, 1, 1),   # >= 148 items of 256 pixels: the resident-weights variant of conv_flat
-    (64, 28, 28, 128, 128, 3, 1, 1), # >= 148 items with 128-channel tiles (MT = 2; the opt-in CTA-pair variant)
+    (64, 28, 28, 128, 128, 3, 1, 1), # >= 148 items with 128-channel tiles: the CTA-pair kernel (cta_group::2), fwd + dgrad
+    (48, 56, 56, 64, 128, 3, 2, 1),  # CTA-pair kernel, stride-2 forward through the four parity planes
+    (96, 28, 28, 128, 256, 3, 2, 1), # CTA-pair kernel, stride-2 forward and the four-class stride-2 data gradient
+    (96, 28, 28, 128, 256, 1, 2, 0), # CTA-pair kernel, 1x1 stride-2 forward (strided view)
+    (192, 14, 14, 128, 256, 1, 1, 0),# CTA-pair kernel, 1x1 data gradient on the compact grid
+    (47, 28, 28, 128, 128, 3, 1, 1), # CTA-pair kernel with an ODD number of 256-pixel tiles (the last pair's peer is padding)
 ]
 
 
@@ -217,10 +222,11 @@ def test_conv_dgrad(case, add_mode):
     assert rel_err(nchw(dx), ref) < 6e-3, rel_err(nchw(dx), ref)
 
 
-def test_conv_dgrad_add_compact():
+@pytest.mark.parametrize("geom", [(2, 13, 9, 64, 128), (96, 28, 28, 128, 256)])  # the second: CTA-pair kernel
+def test_conv_dgrad_add_compact(geom):
     """add_mode 2: gradient of the 1x1/s2 downsample branch added at even pixels."""
     ops = _ops()
-    N, H, W, Ci, Co = 2, 13, 9, 64, 128
+    N, H, W, Ci, Co = geom
     case = (N, H, W, Ci, Co, 3, 2, 1)
     xb, wb = _mk(*case)
     d = ops.conv_desc(N, H, W, Ci, Co, 3, 3, 2, 1)
