@@ -239,13 +239,16 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
   return r;
 }
-// arrive / arrive.expect_tx on an mbarrier given by its shared::cluster address (possibly in the peer CTA)
+// arrive / arrive.expect_tx on an mbarrier given by its shared::cluster address (possibly in the peer CTA).
+// Default semantics (.release.cta), as CUTLASS's umma_arrive_2x1SM_sm0: a .release.cluster arrive compiles to
+// MEMBAR.ALL.GPU in front of every arrive — measured 2x on the whole kernel when the TMA producer did one per stage.
+// Nothing is published through ordinary stores here: operand bytes arrive by TMA complete_tx, accumulator hand-over
+// is ordered by tcgen05.fence::before/after_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr),
-               "r"(bytes)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes)
                : "memory");
 }
 

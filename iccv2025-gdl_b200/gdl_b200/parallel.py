@@ -46,3 +46,43 @@ def allreduce_finish(works, tensors, group=None):
         w.wait()
     for t in tensors:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+class ChunkShardBatchSampler(torch.utils.data.Sampler):
+    """Batch sampler for one rank of a data-parallel run that reproduces what nn.DataParallel does to the reference's
+    DataLoader (main_dgl.py:244,284-288): ONE global sample order (any sampler — RandomSampler for shuffle=True,
+    which draws its permutation seed from the global torch RNG at every epoch exactly like the reference's loader),
+    cut into global batches of `global_batch` with drop_last=True, and each global batch split CONTIGUOUSLY in
+    torch.chunk order: rank r yields rows [r*B/N, (r+1)*B/N) (shard_range).  So replica r's BatchNorm sees exactly
+    the rows reference device r would see, and rank 0 == device 0.
+
+    Every rank must build it over the same order: all ranks run the same script from the same seed, so their global
+    RNGs — and hence the RandomSampler permutations — agree; `order_digest` lets the caller verify that with one
+    tiny all-reduce per epoch."""
+
+    def __init__(self, sampler, global_batch, rank, world):
+        if global_batch % world:
+            raise ValueError("batch_size {} is not divisible by the {} ranks".format(global_batch, world))
+        self.sampler, self.B, self.rank, self.world = sampler, int(global_batch), int(rank), int(world)
+        self.order_digest = None
+
+    def __len__(self):
+        return len(self.sampler) // self.B  # drop_last=True like every loader of the reference
+
+    def __iter__(self):
+        order = list(self.sampler)
+        self.order_digest = sum((i + 1) * (int(v) % 65521) for i, v in enumerate(order[:4096])) % (1 << 31)
+        lo, hi = shard_range(self.rank, self.world, self.B)
+        for k in range(len(order) // self.B):
+            yield order[k * self.B + lo:k * self.B + hi]
+
+
+def assert_same_order(digest, group=None):
+    """All ranks iterate the same global order (see ChunkShardBatchSampler): MIN == MAX of the digests."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or digest is None:
+        return
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor([digest, -digest], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    if int(t[0]) != -int(t[1]):
+        raise RuntimeError("data-parallel ranks drew different sample orders (global RNG out of sync)")

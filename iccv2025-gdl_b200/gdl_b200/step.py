@@ -31,6 +31,11 @@ _SEG_ALIGN = 64  # floats; keeps every tensor 256-byte aligned inside the arenas
 # reference main_dgl.py:244 nn.DataParallel's reduce-add).  0 = one all-reduce after the whole backward.
 AR_OVERLAP = os.environ.get("GDL_AR_OVERLAP", "1") != "0"
 
+# The step is captured lazily (second step, and again when MultiStepLR changes lr) while a DataLoader's pin-memory
+# thread may be calling cudaHostAlloc / cudaEventQuery: in the default "global" capture mode those calls from OTHER
+# threads are illegal and can invalidate the capture; "thread_local" restricts the check to the capturing thread.
+_CAPTURE_MODE = "thread_local"
+
 
 def _pad(n):
     return (n + _SEG_ALIGN - 1) // _SEG_ALIGN * _SEG_ALIGN
@@ -402,7 +407,7 @@ class DGLStep:
                 torch.cuda.synchronize()
                 if self.world_size == 1:
                     self._graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(self._graph):
+                    with torch.cuda.graph(self._graph, capture_error_mode=_CAPTURE_MODE):
                         self._enqueue(self.lr, False)
                     self._graph_update = None
                 else:
@@ -410,15 +415,15 @@ class DGLStep:
                     # the overlapped buckets graph(fwd + late bwd) -> [NCCL bucket 1 || graph(early bwd)] ->
                     # NCCL bucket 2 -> graph(update)
                     self._graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(self._graph):
+                    with torch.cuda.graph(self._graph, capture_error_mode=_CAPTURE_MODE):
                         self._enqueue_compute(part=0 if self.overlap else None)
                     self._graph_b = None
                     if self.overlap:
                         self._graph_b = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(self._graph_b):
+                        with torch.cuda.graph(self._graph_b, capture_error_mode=_CAPTURE_MODE):
                             self._enqueue_compute(part=1)
                     self._graph_update = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(self._graph_update):
+                    with torch.cuda.graph(self._graph_update, capture_error_mode=_CAPTURE_MODE):
                         self._enqueue_update(self.lr, False)
                 self._graph_lr = self.lr
                 # capture does not execute: the replay below runs this step

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """CLI-compatible entry point for the reference's main_dgl.py (same flags, same defaults,
-same prints / csv / checkpoint naming), running the B200-native DGL step.
+same prints / csv / checkpoint file names, same evaluation-mode checkpoint loading), running the B200-native DGL step.
+Deviations: --optimizer AdaGrad / Adam raise NotImplementedError (the fused update is SGD-momentum, the reference
+default); no TensorBoard branch; `--resume` and `--synthetic_len` are additions.
 
     python main_dgl.py --train --ckpt_path ckpt --dataset CREMAD --fusion_method concat \
         --fps 3 --alpha 4 --batch_size 64 --audio_path synthetic
@@ -94,8 +96,13 @@ def main(argv=None):
 
     if args.optimizer == 'sgd':
         optimizer = optim.SGD(model.parameters(), lr=args.learning_rate, momentum=0.9, weight_decay=1e-4)
+    elif args.optimizer in ('AdaGrad', 'Adam'):
+        # accepted by the reference (main_dgl.py:251-256); every shipped script uses sgd and the fused update
+        # kernel implements SGD-momentum only
+        raise NotImplementedError('optimizer {}: the B200 DGL step implements the reference default (sgd) only'
+                                  .format(args.optimizer))
     else:
-        raise ValueError('Incorrect optimizer: {}'.format(args.optimizer))
+        raise ValueError('Incorrect optimizer: {}'.format(args.optimizer))  # reference main_dgl.py:259
     scheduler = optim.lr_scheduler.MultiStepLR(optimizer, eval(args.lr_decay_step), args.lr_decay_ratio)
 
     if args.audio_path not in ('synthetic', 'synthetic_exact', 'synthetic_device'):
@@ -122,14 +129,21 @@ def main(argv=None):
         train_dataset = SyntheticAV(args, 'train', n)
         test_dataset = SyntheticAV(args, 'test', n and max(n // 8, args.batch_size))
     per_rank = args.batch_size // world
-    sampler = torch.utils.data.distributed.DistributedSampler(train_dataset, shuffle=True) if world > 1 else None
-    train_loader = DataLoader(train_dataset, batch_size=per_rank, shuffle=sampler is None, sampler=sampler,
-                              num_workers=8, pin_memory=True, drop_last=True)
+    shard_sampler = None
+    if world > 1:
+        # the reference's DataLoader(shuffle=True) order, cut into global batches that are split contiguously in
+        # DataParallel chunk order (main_dgl.py:244): rank r's BatchNorm sees the rows reference device r would
+        from gdl_b200.parallel import ChunkShardBatchSampler
+        shard_sampler = ChunkShardBatchSampler(torch.utils.data.RandomSampler(train_dataset), args.batch_size, rank, world)
+        train_loader = DataLoader(train_dataset, batch_sampler=shard_sampler, num_workers=8, pin_memory=True)
+    else:
+        train_loader = DataLoader(train_dataset, batch_size=per_rank, shuffle=True, num_workers=8, pin_memory=True,
+                                  drop_last=True)
     test_loader = DataLoader(test_dataset, batch_size=per_rank, shuffle=False, num_workers=8, pin_memory=True,
                              drop_last=True)  # the reference drops the test tail too (main_dgl.py:287-288)
 
-    start_epoch = 0
-    if args.resume:
+    start_epoch, best_acc = 0, 0.0
+    if args.resume and args.train:
         # the reference saves {'saved_epoch', 'model' (module.-prefixed keys), 'optimizer', 'scheduler', ...} but has
         # no way to load it back; the momentum buffers are adopted by the fused optimizer on the first batch
         ckpt = torch.load(args.resume, map_location=device)
@@ -137,37 +151,59 @@ def main(argv=None):
         optimizer.load_state_dict(ckpt['optimizer'])
         scheduler.load_state_dict(ckpt['scheduler'])
         start_epoch = int(ckpt['saved_epoch']) + 1
+        best_acc = float(ckpt.get('acc', 0.0))  # a resumed run only overwrites "best" with something better
         print('Resumed from {} (epoch {}, acc {})'.format(args.resume, ckpt['saved_epoch'], ckpt.get('acc')))
 
     if args.train:
         os.makedirs(args.ckpt_path, exist_ok=True)
-        best_acc = 0.0
         log = os.path.join(args.ckpt_path, args.dataset + '_' + args.modality + '.csv')
         if rank == 0:
             with open(log, 'a+', newline='') as f:
                 csv.writer(f).writerow([1000, 1000, 1000])  # run separator, main_dgl.py:292-295
         for epoch in range(start_epoch, args.epochs):
             print('Epoch: {}: '.format(epoch))
-            batch_loss, batch_loss_a, batch_loss_v, *_ = train_epoch(args, epoch, model, device, train_loader,
-                                                                     optimizer, scheduler)
+            args.epoch_now = epoch
+            batch_loss, batch_loss_a, batch_loss_v, a_div, v_div, a_re, v_re = train_epoch(
+                args, epoch, model, device, train_loader, optimizer, scheduler)
+            if shard_sampler is not None:
+                from gdl_b200.parallel import assert_same_order
+                assert_same_order(shard_sampler.order_digest)
             acc, acc_a, acc_v = valid(args, model, device, test_loader)
             if rank == 0:
                 with open(log, 'a+', newline='') as f:
                     csv.writer(f).writerow([acc, acc_a, acc_v])
-            if acc > best_acc and epoch and rank == 0:
+            if acc > best_acc and epoch:
                 best_acc = float(acc)
-                name = 'best_model_{}_of_dataset_{}_{}_alpha_{}_optimizer_{}_modulate_starts_{}_ends_{}_' \
-                       'epoch_{}_acc_{}.pth'.format(args.fusion_method, args.dataset, args.modulation, args.alpha,
-                                                    args.optimizer, args.modulation_starts, args.modulation_ends,
-                                                    epoch, acc)
-                torch.save({'saved_epoch': epoch, 'modulation': args.modulation, 'alpha': args.alpha,
-                            'fusion': args.fusion_method, 'acc': acc, 'model': model.state_dict(),
-                            'optimizer': optimizer.state_dict(), 'scheduler': scheduler.state_dict()},
-                           os.path.join(args.ckpt_path, name))
+                # the reference's exact file name (main_dgl.py:358-367: no fusion field, no '_' before 'optimizer')
+                name = 'best_model_of_dataset_{}_{}_alpha_{}' \
+                       'optimizer_{}_modulate_starts_{}_ends_{}_' \
+                       'epoch_{}_acc_{}.pth'.format(args.dataset, args.modulation, args.alpha, args.optimizer,
+                                                    args.modulation_starts, args.modulation_ends, epoch, acc)
+                if rank == 0:
+                    torch.save({'saved_epoch': epoch, 'modulation': args.modulation, 'alpha': args.alpha,
+                                'fusion': args.fusion_method, 'acc': acc, 'model': model.state_dict(),
+                                'optimizer': optimizer.state_dict(), 'scheduler': scheduler.state_dict()},
+                               os.path.join(args.ckpt_path, name))
                 print('The best model has been saved at {}.'.format(os.path.join(args.ckpt_path, name)))
-            print("Loss: {:.3f}, Acc: {:.3f}".format(batch_loss, acc))
+                print("Loss: {:.3f}, Acc: {:.3f}".format(batch_loss, acc))
+            else:
+                print("Loss: {:.3f}, Acc: {:.3f}, Best Acc: {:.3f}".format(batch_loss, acc, best_acc))
             print("Audio Acc: {:.3f}， Visual Acc: {:.3f} ".format(acc_a, acc_v))
+            print("Audio similar: {:.3f}， Visual similar: {:.3f} ".format(a_div, v_div))
+            print("Audio regurize: {:.3f}， Visual regurize: {:.3f} ".format(a_re, v_re))
     else:
+        # reference main_dgl.py:396-418: args.ckpt_path IS the checkpoint file in evaluation mode
+        path = args.resume or args.ckpt_path
+        if not os.path.isfile(path):
+            raise FileNotFoundError("evaluation mode loads a trained model: --ckpt_path (or --resume) must name a "
+                                    "checkpoint file written by --train, got {!r}".format(path))
+        loaded_dict = torch.load(path, map_location=device)
+        assert loaded_dict['modulation'] == args.modulation, \
+            'inconsistency between modulation method of loaded model and args !'
+        assert loaded_dict['fusion'] == args.fusion_method, \
+            'inconsistency between fusion method of loaded model and args !'
+        model.load_state_dict(loaded_dict['model'])
+        print('Trained model loaded!')
         acc, acc_a, acc_v = valid(args, model, device, test_loader)
         print('Accuracy: {}, accuracy_a: {}, accuracy_v: {}'.format(acc, acc_a, acc_v))
 

@@ -181,3 +181,39 @@ def test_checkpoint_momentum_is_adopted_by_the_arena():
     total = sum(v["momentum_buffer"].double().sum().item() for v in again.values())
     want = sum(v.double().sum().item() for v in views(a1))
     assert abs(total - want) <= 1e-9 * max(1.0, abs(want))
+
+
+def test_chunk_shard_sampler_reproduces_dataparallel_split():
+    """ChunkShardBatchSampler: the N ranks' index lists of step k, concatenated in rank order, are exactly global
+    batch k of the reference's DataLoader(shuffle=True, drop_last=True) (same torch RNG seed => same RandomSampler
+    permutation), i.e. rank r holds the rows nn.DataParallel's chunk would give device r (main_dgl.py:244,284-288);
+    a second epoch reshuffles (the ADVICE item: DistributedSampler without set_epoch replayed one order)."""
+    sys.path.insert(0, os.path.join(ROOT, "iccv2025-gdl_b200"))
+    from torch.utils.data import BatchSampler, RandomSampler
+    from gdl_b200.parallel import ChunkShardBatchSampler, shard_range
+    data = list(range(203))
+    B, world = 16, 4
+    torch.manual_seed(7)
+    ref_sampler = BatchSampler(RandomSampler(data), B, drop_last=True)
+    ref_epochs = [list(ref_sampler), list(ref_sampler)]
+    per_rank = []
+    for r in range(world):
+        torch.manual_seed(7)  # every rank runs the same script from the same seed
+        s = ChunkShardBatchSampler(RandomSampler(data), B, r, world)
+        assert len(s) == 203 // B
+        e0 = list(s)
+        d0 = s.order_digest
+        e1 = list(s)
+        per_rank.append(((e0, e1), (d0, s.order_digest)))
+    for ep in range(2):
+        for k, gb in enumerate(ref_epochs[ep]):
+            cat = sum((per_rank[r][0][ep][k] for r in range(world)), [])
+            assert cat == gb
+            for r in range(world):
+                lo, hi = shard_range(r, world, B)
+                assert per_rank[r][0][ep][k] == gb[lo:hi]
+    assert ref_epochs[0] != ref_epochs[1]
+    assert len({pr[1] for pr in per_rank}) == 1  # identical digests on every rank, both epochs
+    import pytest
+    with pytest.raises(ValueError):
+        ChunkShardBatchSampler(RandomSampler(data), 10, 0, 4)

@@ -138,3 +138,36 @@ def test_train_epoch_dropin(tmp_path):
     # momentum is visible through the torch optimizer for reference-format checkpoints
     p = model.audio_net.conv1.weight
     assert "momentum_buffer" in opt.state[p] and float(opt.state[p]["momentum_buffer"].abs().sum()) > 0
+
+
+def test_train_epoch_over_a_pinning_dataloader_with_graph_capture(tmp_path):
+    """The step's CUDA graphs are captured lazily on the SECOND step — while a real DataLoader's pin-memory thread is
+    calling cudaHostAlloc / cudaEventQuery (the combination main_dgl.py runs: pin_memory=True, num_workers > 0).
+    capture_error_mode="thread_local" keeps those foreign-thread calls legal.  6 steps: eager, capture, 4 replays."""
+    from torch.utils.data import DataLoader, Dataset
+    from gdl_b200.train import train_epoch
+    from oracle.synth import SHAPES, make_batch
+
+    class DS(Dataset):
+        def __len__(self):
+            return 24
+
+        def __getitem__(self, i):
+            spec, image, label = make_batch(1, 6, "tiny", seed=100 + i)
+            return spec[0], image[0], label[0]
+
+    args, model = make_model("concat")
+    dp = _Wrap(model)
+    opt = torch.optim.SGD(dp.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    loader = DataLoader(DS(), batch_size=4, shuffle=False, num_workers=2, pin_memory=True, drop_last=True)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        res = train_epoch(args, 0, dp, torch.device("cuda"), loader, opt, None)
+        rows = list(csv.reader(open("audio_visual_grad_vanilla.csv")))
+    finally:
+        os.chdir(cwd)
+    torch.cuda.synchronize()
+    assert len(rows) == 6 and all(float(r[0]) > 0 and float(r[1]) > 0 for r in rows)
+    assert all(x == x and 0 < x < 50 for x in res[:3])  # finite epoch-mean losses
+    assert model._gdl_step._graph is not None           # the captured path really ran
