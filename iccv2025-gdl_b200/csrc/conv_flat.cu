@@ -859,15 +859,23 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   p.tm_w = *tw;
   // MT = 2 halves the weight traffic per MMA (measured 1.2-1.4x on every layer of the bench geometry);
   // MT = 1 only when the problem would not fill one wave of CTAs otherwise
-  const int64_t items2 = (int64_t)p.nclass * (Cd / BN) * ((Q + 255) / 256);
-  int mt = items2 >= kNumSMs ? 2 : 1;
+  // Tile shape by a wave-count model (small per-GPU batches: layer3/4 have a few hundred tiles, and a static
+  // persistent grid pays whole rounds).  Relative cost of one round: a single CTA with MT = 1 pays the full weight
+  // stream per 128 pixels (1.15), MT = 2 shares it (2.0 for twice the pixels), a CTA pair halves it again (1.7).
+  const int64_t per_px = (int64_t)p.nclass * (Cd / BN);
+  const int64_t items2 = per_px * ((Q + 255) / 256), items1 = per_px * ((Q + 127) / 128);
+  const int64_t pairs2 = per_px * ((Q + 511) / 512);
+  const double cost_mt2 = 2.0 * double((items2 + kNumSMs - 1) / kNumSMs);
+  const double cost_mt1 = 1.15 * double((items1 + kNumSMs - 1) / kNumSMs);
+  const double cost_pair = 1.7 * double((pairs2 + kNumSMs / 2 - 1) / (kNumSMs / 2));
+  int mt = cost_mt2 <= cost_mt1 ? 2 : 1;
+  const bool pair_wins = cost_pair <= (mt == 2 ? cost_mt2 : cost_mt1);
   if (mt_force) mt = mt_force;
   int rc = 0;
-  // GDL_FLAT_PAIR (default 1): CTA-pair kernel (cta_group::2) for the 128-channel tiles when there are at least 74
-  // pairs of 256-pixel tiles (one wave of clusters)
+  // GDL_FLAT_PAIR (default 1): CTA-pair kernel (cta_group::2) where the wave-count model above prefers it
   static const int pair = env_int3("GDL_FLAT_PAIR", 1);
   if (BN == 128) {
-    if (pair && mt == 2 && stats == nullptr && items2 >= kNumSMs) {
+    if (pair && pair_wins && !mt_force && stats == nullptr) {
       const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
       if (!th) return GDL_ECUDA;
       p.tm_w_half = *th;
@@ -879,8 +887,18 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
     // GDL_FLAT_RESIDENT (default 1): 64 -> 64 channel 3x3 layers keep their 72 KB of weights in shared memory
     // (measured: 56x56 forward / dgrad 700-730 -> 800+ TF, step 23.11 -> 22.82 ms; step parity tests green)
     static const int resident = env_int3("GDL_FLAT_RESIDENT", 1);
-    if (resident && mt == 2 && Cs == 64 && Cd == 64 && (kind == 0 || kind == 1) && stats == nullptr)
-      rc = launch_flat<64, 2, 6, true>(p, Q, s);
+    // GDL_FLAT_PAIR64: CTA-pair kernel for 64-channel tiles (N = 64 MMAs read 6 KB of operands per 32 clocks on one
+    // SM, 5 KB as a pair).  1 = wherever eligible (instead of the resident-weights kernel too), 2 = only where the
+    // resident-weights kernel does not apply (e.g. the 128 -> 64 channel stride-2 data gradients), 0 = off.
+    static const int pair64 = env_int3("GDL_FLAT_PAIR64", 2);
+    const bool res_ok = resident && mt == 2 && Cs == 64 && Cd == 64 && (kind == 0 || kind == 1) && stats == nullptr;
+    if (pair && pair64 && pair_wins && !mt_force && stats == nullptr && !(pair64 == 2 && res_ok)) {
+      const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
+      if (!th) return GDL_ECUDA;
+      p.tm_w_half = *th;
+      rc = launch_flat2<64, 2, 8>(p, Q, s);
+    }
+    if (rc == 0 && res_ok) rc = launch_flat<64, 2, 6, true>(p, Q, s);
     if (rc == 0 && mt == 2) rc = launch_flat<64, 2, 6>(p, Q, s);
     if (rc == 0) rc = launch_flat<64, 1, 6>(p, Q, s);
   }
