@@ -461,6 +461,7 @@ __global__ void pack_weights_multi_kernel(const gdl_pack_entry* __restrict__ tab
     if (valid) {
       const int r = tap / e.S, s2 = tap - r * e.S;
       v = e.w[(((size_t)co * e.ci_real + ci) * e.R + r) * e.S + s2];
+      if (e.scale != nullptr) v *= e.scale[co];  // eval mode: BatchNorm scale folded into the weights
     }
     const bf16 b = __float2bfloat16_rn(v);
     reinterpret_cast<bf16*>(e.wp)[li] = b;
@@ -621,19 +622,16 @@ static int launch_wgrad(const WgradParams& p, const WgradPlan& w, cudaStream_t s
   return GDL_OK;
 }
 
-// conv_halo.cu
-int try_conv3x3_halo(int N, int H, int W, int Cs, int Cd, const void* src, const void* wt, int64_t wt_rows,
-                     int64_t wt_k, void* dst, const void* add_src, int add_mode, int flip, cudaStream_t s);
-
 // conv_flat.cu
 int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t sH, int64_t sN, const void* src,
                   const void* wt, int64_t wt_rows, int64_t wt_k, void* dst, int Hd, int Wd, int Cd,
                   const void* add_src, int add_mode, cudaStream_t s, float* stats = nullptr,
-                  int* stats_rows = nullptr);
+                  int* stats_rows = nullptr, const float* bias = nullptr, int relu = 0);
 
-// Which TMA kernel serves a 3x3/s1 convolution.  Measured at the bench geometry (tools/conv_bench.py) the
-// flat-window kernel beats the 16x8-tile halo kernel on every layer (1.1x at 56x56 ... 2.1x at 7x7), so it
-// is the default; GDL_FLAT: 0 off, 1 only where the halo tiles are poorly filled, 2 always.
+// GDL_FLAT=0 routes every convolution to the generic gather kernels below (conv_igemm_kernel / conv_wgrad_kernel:
+// cp.async im2col gather, any geometry) instead of the flat-window TMA kernels — the fallback for geometries the flat
+// kernels do not cover (rows wider than 255 pixels, channel counts that are not multiples of 64), exercised by
+// tests/test_gpu_kernels.py::test_generic_gather_kernels.  Default: flat wherever eligible.
 static int flat_policy() {
   static int v = -1;
   if (v < 0) {
@@ -642,26 +640,24 @@ static int flat_policy() {
   }
   return v;
 }
-static bool prefer_flat_s1(int H, int W) {
-  const int pol = flat_policy();
-  if (pol == 0) return false;
-  if (pol >= 2) return true;
-  static int thr = -1;
-  if (thr < 0) {
-    const char* e = getenv("GDL_FLAT_HALO_UTIL_PCT");
-    thr = e ? atoi(e) : 80;
+// 1x1 convolutions up to this many input channels take the flat kernel (round 1 stopped at 128: the 256 -> 512
+// downsample of layer4 ran on the legacy gather kernel at 8 % tensor-pipe activity)
+static int flat_1x1_max_ci() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GDL_FLAT_1X1_MAX_CI");
+    v = e ? atoi(e) : 512;
   }
-  const int th = (H + 15) / 16, tw = (W + 7) / 8;
-  return 100 * H * W < thr * (th * 16 * tw * 8);
+  return v;
 }
+static bool prefer_flat_s1(int, int) { return flat_policy() != 0; }
 
 // conv_wgrad_flat.cu
 int64_t wgrad_flat_workspace_bytes(int N, int Ho, int Wo, int Ci, int Co, int R, int stride);
 int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R, int stride, const void* x,
                    const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed,
                    int* tap_splits);
-// GDL_WFLAT: 0 off, 1 where the halo wgrad kernel is not eligible or its 16x8 tiles are poorly filled, 2 always
-// (default: measured equal or faster than the halo kernel on every layer of the bench geometry).
+// GDL_WFLAT=0: generic gather weight-gradient kernel instead of the flat-window one (see GDL_FLAT above)
 static int wflat_policy() {
   static int v = -1;
   if (v < 0) {
@@ -675,26 +671,7 @@ static bool wflat_shape_ok(const gdl_conv_desc* d) {
   if (d->R == 3) return d->pad == 1 && (d->stride == 1 || d->stride == 2);
   return d->R == 1 && d->pad == 0 && (d->stride == 1 || d->stride == 2);
 }
-static bool prefer_wflat(const gdl_conv_desc* d) {
-  const int pol = wflat_policy();
-  if (pol == 0 || !wflat_shape_ok(d)) return false;
-  if (pol >= 2) return true;
-  if (d->R == 3 && d->stride == 1) {
-    static int thr = -1;
-    if (thr < 0) {
-      const char* e = getenv("GDL_FLAT_HALO_UTIL_PCT");
-      thr = e ? atoi(e) : 80;
-    }
-    const int th = (d->Hi + 15) / 16, tw = (d->Wi + 7) / 8;
-    return 100 * d->Hi * d->Wi < thr * (th * 16 * tw * 8);
-  }
-  return true;
-}
-
-// conv_wgrad_halo.cu
-int64_t wgrad_halo_workspace_bytes(int N, int H, int W, int Ci, int Co);
-int try_wgrad3x3_halo(int N, int H, int W, int Ci, int Co, const void* x, const void* dy, float* partial,
-                      int64_t workspace_bytes, cudaStream_t s);
+static bool prefer_wflat(const gdl_conv_desc* d) { return wflat_policy() != 0 && wflat_shape_ok(d); }
 
 static int run_igemm(const ConvParams& p, cudaStream_t s) {
   if (p.Cd % 128 == 0) return launch_igemm<128, 3>(p, s);
@@ -711,10 +688,6 @@ extern "C" int64_t gdl_conv_wgrad_workspace_bytes(const gdl_conv_desc* d) {
   if (!desc_ok(d)) return GDL_EINVAL;
   WgradPlan w = plan_wgrad(d);
   int64_t need = (int64_t)w.splits * w.Kp * d->Co * (int64_t)sizeof(float);
-  if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1) {
-    int64_t h = wgrad_halo_workspace_bytes(d->N, d->Hi, d->Wi, d->Ci, d->Co);
-    if (h > need) need = h;
-  }
   if (wflat_shape_ok(d)) {
     int64_t f = wgrad_flat_workspace_bytes(d->N, d->Ho, d->Wo, d->Ci, d->Co, d->R, d->stride);
     if (f > need) need = f;
@@ -736,35 +709,41 @@ extern "C" int gdl_conv_pack_weights(const gdl_conv_desc* d, int ci_real, const 
   return GDL_OK;
 }
 
+// bias / res / relu: eval-mode epilogue y = [relu](conv + bias[co] [+ res]) (gdl_conv_fwd_bias_act); flat kernels only
 static int conv_fwd_impl(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y, float* stats,
-                         int* stats_rows, gdl_stream_t s) {
+                         int* stats_rows, gdl_stream_t s, const float* bias = nullptr, const void* res = nullptr,
+                         int relu = 0) {
+  const bool epi = bias != nullptr || res != nullptr || relu != 0;
+  const int amode = res != nullptr ? 1 : 0;
   GDL_REQUIRE(desc_ok(d), "gdl_conv_fwd: bad descriptor");
   GDL_REQUIRE(x && w_packed && y, "gdl_conv_fwd: null pointer");
   if (stats_rows) *stats_rows = 0;
   if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1 && d->Ci % 64 == 0) {
-    if (prefer_flat_s1(d->Hi, d->Wi)) {
+    if (prefer_flat_s1(d->Hi, d->Wi) || epi) {
       int rc = try_conv_flat(0, d->N, d->Hi, d->Wi, d->Ci, d->Ci, (int64_t)d->Wi * d->Ci,
                              (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y, d->Ho, d->Wo,
-                             d->Co, nullptr, 0, (cudaStream_t)s, stats, stats_rows);
+                             d->Co, res, amode, (cudaStream_t)s, stats, stats_rows, bias, relu);
       if (rc != 0) return rc < 0 ? rc : GDL_OK;
     }
-    int rc = try_conv3x3_halo(d->N, d->Hi, d->Wi, d->Ci, d->Co, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y,
-                              nullptr, 0, 0, (cudaStream_t)s);
-    if (rc != 0) return rc < 0 ? rc : GDL_OK;
   }
   if (d->R == 3 && d->S == 3 && d->stride == 2 && d->pad == 1 && d->Ci % 64 == 0 && flat_policy() != 0) {
     // stride 2: the four parity planes of x are stride-1 sources on the output grid
     int rc = try_conv_flat(4, d->N, d->Ho, d->Wo, d->Ci, d->Ci, (int64_t)d->Wi * d->Ci,
                            (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co, 9 * (int64_t)d->Ci, y, d->Ho, d->Wo,
-                           d->Co, nullptr, 0, (cudaStream_t)s, stats, stats_rows);
+                           d->Co, res, amode, (cudaStream_t)s, stats, stats_rows, bias, relu);
     if (rc != 0) return rc < 0 ? rc : GDL_OK;
   }
-  if (d->R == 1 && d->S == 1 && d->pad == 0 && d->Ci % 64 == 0 && d->Ci <= 128 && flat_policy() != 0) {
+  if (d->R == 1 && d->S == 1 && d->pad == 0 && d->Ci % 64 == 0 && d->Ci <= flat_1x1_max_ci() && flat_policy() != 0) {
     // 1x1 (stride 1 or 2): a single tap over the strided view x[:, ::stride, ::stride, :]
     int rc = try_conv_flat(3, d->N, d->Ho, d->Wo, d->Ci, (int64_t)d->stride * d->Ci,
                            (int64_t)d->stride * d->Wi * d->Ci, (int64_t)d->Hi * d->Wi * d->Ci, x, w_packed, d->Co,
-                           (int64_t)d->Ci, y, d->Ho, d->Wo, d->Co, nullptr, 0, (cudaStream_t)s, stats, stats_rows);
+                           (int64_t)d->Ci, y, d->Ho, d->Wo, d->Co, res, amode, (cudaStream_t)s, stats, stats_rows, bias,
+                           relu);
     if (rc != 0) return rc < 0 ? rc : GDL_OK;
+  }
+  if (epi) {
+    set_last_error("gdl_conv_fwd_bias_act: this geometry is not covered by the flat-window kernels");
+    return GDL_EINVAL;
   }
   ConvParams p{};
   p.src = (const bf16*)x;
@@ -798,6 +777,12 @@ extern "C" int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w
   return conv_fwd_impl(d, x, w_packed, y, nullptr, nullptr, s);
 }
 
+extern "C" int gdl_conv_fwd_bias_act(const gdl_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                                     const void* res, int relu, void* y, gdl_stream_t s) {
+  GDL_REQUIRE(bias != nullptr, "gdl_conv_fwd_bias_act: null bias");
+  return conv_fwd_impl(d, x, w_packed, y, nullptr, nullptr, s, bias, res, relu ? 1 : 0);
+}
+
 extern "C" int gdl_conv_fwd_stats(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
                                   float* bn_partial, int* bn_partial_rows, gdl_stream_t s) {
   GDL_REQUIRE(bn_partial && bn_partial_rows, "gdl_conv_fwd_stats: null pointer");
@@ -817,9 +802,6 @@ extern "C" int gdl_conv_dgrad(const gdl_conv_desc* d, const void* dy, const void
                              d->Wi, d->Ci, add_src, add_mode, (cudaStream_t)s);
       if (rc != 0) return rc < 0 ? rc : GDL_OK;
     }
-    int rc = try_conv3x3_halo(d->N, d->Hi, d->Wi, d->Co, d->Ci, dy, w_packed_T, d->Ci, 9 * (int64_t)d->Co, dx,
-                              add_src, add_mode, 1, (cudaStream_t)s);
-    if (rc != 0) return rc < 0 ? rc : GDL_OK;
   }
   if (d->R == 3 && d->S == 3 && d->stride == 2 && d->pad == 1 && add_mode != 1 && flat_policy() != 0) {
     // four output-parity classes, 1+2+2+4 taps instead of 9 zero-stuffed ones
@@ -876,19 +858,6 @@ extern "C" int gdl_conv_wgrad(const gdl_conv_desc* d, int ci_real, const void* x
       int Kp = d->R * d->S * d->Ci;
       if (tr) return launch_wgrad_reduce_t((const float*)workspace, dw_oihw, ns, ts, Kp, d->Co, d->Ci, d->R * d->S,
                                            (cudaStream_t)s);
-      int64_t total = (int64_t)Kp * d->Co;
-      wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)s>>>(
-          (const float*)workspace, dw_oihw, ns, Kp, d->Co, d->Ci, ci_real, d->R, d->S);
-      GDL_CHECK_LAUNCH("wgrad_reduce_kernel");
-      return GDL_OK;
-    }
-  }
-  if (d->R == 3 && d->S == 3 && d->stride == 1 && d->pad == 1 && d->Ci % 64 == 0 && ci_real == d->Ci) {
-    int ns = try_wgrad3x3_halo(d->N, d->Hi, d->Wi, d->Ci, d->Co, x, dy, (float*)workspace, workspace_bytes,
-                               (cudaStream_t)s);
-    if (ns < 0) return ns;
-    if (ns > 0) {
-      int Kp = 9 * d->Ci;
       int64_t total = (int64_t)Kp * d->Co;
       wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)s>>>(
           (const float*)workspace, dw_oihw, ns, Kp, d->Co, d->Ci, ci_real, d->R, d->S);

@@ -44,6 +44,8 @@ struct FlatParams {
   const bf16* add_src;
   float* stats;  // optional [gridDim.x * 4 epilogue warps][2][Cd]: per-warp sum / sum of squares of the bf16 outputs
   int add_mode;  // 0 none; 1 add_src has dst's shape; 2 add_src lives on the source grid (parity class (0,0) only)
+  const float* bias;  // optional per-output-channel bias [Cd] (eval mode: the folded BatchNorm shift), added before relu
+  int relu;           // eval-mode epilogue: clamp at zero after bias / residual
   int N, Hs, Ws, Cs;
   int Hd, Wd, Cd;
   int P, IS;
@@ -339,6 +341,16 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[i] += a[i];
                 }
+                if (p.bias != nullptr) {  // eval mode: folded BatchNorm shift (same 8 floats for every lane: L1 broadcast)
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (g + h2) * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (g + h2) * 8 + 4));
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
                 o[h2] = pack8(f);
               }
               st_global32(outp[j] + c0 + g * 8, o[0], o[1]);
@@ -619,6 +631,16 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[i] += a[i];
                 }
+                if (p.bias != nullptr) {  // eval mode: folded BatchNorm shift (same 8 floats for every lane: L1 broadcast)
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (g + h2) * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (g + h2) * 8 + 4));
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
                 o[h2] = pack8(f);
               }
               st_global32(outp[j] + c0 + g * 8, o[0], o[1]);
@@ -746,7 +768,8 @@ static int env_int3(const char* name, int dflt) {
 // wt is [Cd rows][K] bf16 with k = tap*Cs + c.  Returns 1 when launched, 0 when not eligible, <0 on error.
 int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t sH, int64_t sN, const void* src,
                   const void* wt, int64_t wt_rows, int64_t wt_k, void* dst, int Hd, int Wd, int Cd,
-                  const void* add_src, int add_mode, cudaStream_t s, float* stats, int* stats_rows) {
+                  const void* add_src, int add_mode, cudaStream_t s, float* stats, int* stats_rows, const float* bias,
+                  int relu) {
   static const int mt_force = env_int3("GDL_FLAT_MT", 0);
   if (Cs % 64 != 0 || Cd % 64 != 0) return 0;
   const int P = Ws + 1;
@@ -759,6 +782,8 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   p.dst = (bf16*)dst;
   p.add_src = (const bf16*)add_src;
   p.add_mode = add_mode;
+  p.bias = bias;
+  p.relu = relu;
   p.rev = g_sweep_rev;
   // The statistics butterfly costs ~1.3k instructions per 128x128 tile in the epilogue warps: it hides behind the
   // MMAs only when the reduction is long (measured: +2-8 % kernel time for K >= 1152, +30 % at K = 576, 2.4x for

@@ -70,7 +70,7 @@ __global__ void stem_layout_kernel(const float* __restrict__ src, bf16* __restri
 }
 
 // fp32 OIHW [64][C][7][7] -> bf16 [64][256]  (k = (a*4+b)*16 + (dy*2+dx)*C + c)
-__global__ void stem_pack_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int C) {
+__global__ void stem_pack_kernel(const float* __restrict__ w, const float* __restrict__ scale, bf16* __restrict__ wp, int C) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 64 * 256) return;
   int co = idx >> 8, k = idx & 255;
@@ -81,6 +81,7 @@ __global__ void stem_pack_kernel(const float* __restrict__ w, bf16* __restrict__
     int d = ch / C, c = ch - d * C;
     int r = 2 * a + (d >> 1), s = 2 * b + (d & 1);
     if (r < 7 && s < 7) v = w[((co * C + c) * 7 + r) * 7 + s];
+    if (scale != nullptr) v *= scale[co];  // eval mode: BatchNorm scale folded into the weights
   }
   wp[idx] = __float2bfloat16_rn(v);
 }
@@ -404,8 +405,16 @@ extern "C" int gdl_stem_layout(const float* src, void* dst, int B, int C, int T,
 
 extern "C" int gdl_stem_pack_weights(const float* w_oihw, void* w_packed, int C, gdl_stream_t s) {
   GDL_REQUIRE(w_oihw && w_packed && C > 0 && C <= 4, "gdl_stem_pack_weights: bad arguments");
-  stem_pack_kernel<<<64, 256, 0, (cudaStream_t)s>>>(w_oihw, (bf16*)w_packed, C);
+  stem_pack_kernel<<<64, 256, 0, (cudaStream_t)s>>>(w_oihw, nullptr, (bf16*)w_packed, C);
   GDL_CHECK_LAUNCH("stem_pack_kernel");
+  return GDL_OK;
+}
+
+extern "C" int gdl_stem_pack_weights_scaled(const float* w_oihw, const float* scale64, void* w_packed, int C,
+                                            gdl_stream_t s) {
+  GDL_REQUIRE(w_oihw && scale64 && w_packed && C >= 1 && C <= 4, "gdl_stem_pack_weights_scaled: bad arguments");
+  stem_pack_kernel<<<64, 256, 0, (cudaStream_t)s>>>(w_oihw, scale64, (bf16*)w_packed, C);
+  GDL_CHECK_LAUNCH("stem_pack_kernel(scaled)");
   return GDL_OK;
 }
 

@@ -197,3 +197,130 @@ extern "C" int gdl_crop_resize_normalize(const uint8_t* store, int64_t store_fra
   GDL_CHECK_LAUNCH("crop_resample_kernel");
   return GDL_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// audio half of the data pipeline: spectrogram = log(|librosa.stft(clip(wave), n_fft, hop)| + 1e-7)
+// (reference dataset/CramedDataset.py:60-66: 22 050 Hz * 3 s tiled, n_fft 512, hop 353;
+//  KSDataset.py:138-150 / VGGSoundDataset.py:112-122: 16 kHz, random 5-s window of the clip tiled to >= 10 s,
+//  n_fft 256, hop 128).  librosa.stft: center=True (n_fft/2 samples of padding on both sides), periodic Hann
+//  window, frames multiplied by the float64 window and transformed by a float64 FFT, the result stored as complex64;
+//  np.abs and np.log then run in float32.  The kernel follows those precisions: fp64 window product and radix-2 FFT
+//  in shared memory (low-energy bins of real audio sit 100+ dB under the frame's peak, below an fp32 FFT's noise
+//  floor), components rounded to fp32, hypotf, logf.  One CTA transforms kStftFrames consecutive frames of one item
+//  and writes out[b][f][t0 .. t0+kStftFrames) so every 32-byte sector of the [F][frames] plane is written whole.
+// ------------------------------------------------------------------------------------------
+namespace gdl {
+
+constexpr int kStftFrames = 8;
+constexpr int kStftMaxFft = 1024;
+
+struct StftItem {
+  int32_t clip, start;
+};
+
+__global__ void __launch_bounds__(kStftMaxFft / 2) log_stft_kernel(const float* __restrict__ waves, int64_t clip_stride,
+                                                                   const int32_t* __restrict__ clip_len,
+                                                                   const StftItem* __restrict__ items, int L, int n_fft,
+                                                                   int log2n, int hop, int frames, int pad_zero,
+                                                                   float* __restrict__ out) {
+  extern __shared__ double sm[];
+  double* re = sm;                  // [n_fft]
+  double* im = re + n_fft;          // [n_fft]
+  double* twr = im + n_fft;         // [n_fft/2]  cos(2 pi k / n)
+  double* twi = twr + n_fft / 2;    // [n_fft/2] -sin(2 pi k / n)
+  float* obuf = reinterpret_cast<float*>(twi + n_fft / 2);  // [n_fft/2 + 1][kStftFrames]
+  const int tid = threadIdx.x, half_n = n_fft >> 1, F = half_n + 1;
+  const int b = blockIdx.y, t0 = blockIdx.x * kStftFrames;
+  const StftItem it = items[b];
+  const float* w = waves + (int64_t)it.clip * clip_stride;
+  const int len = clip_len[it.clip];
+  {
+    double s, c;
+    sincospi(2.0 * (double)tid / (double)n_fft, &s, &c);
+    twr[tid] = c;
+    twi[tid] = -s;
+  }
+  for (int ft = 0; ft < kStftFrames; ++ft) {
+    const int t = t0 + ft;
+    __syncthreads();  // twiddles ready / previous frame's spectrum consumed
+    if (t < frames) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = tid + h * half_n;
+        int j = t * hop - half_n + k;  // index into the un-padded item
+        double v = 0.0;
+        bool inside = true;
+        if (j < 0) {
+          inside = !pad_zero;
+          j = -j;                       // np.pad(mode="reflect"): x[-j] = x[j]
+        } else if (j >= L) {
+          inside = !pad_zero;
+          j = 2 * (L - 1) - j;
+        }
+        if (inside) {
+          float x = w[(int)(((int64_t)it.start + j) % len)];  // np.tile(...)[start:start+L]
+          x = fminf(fmaxf(x, -1.f), 1.f);                     // samples[> 1] = 1, samples[< -1] = -1
+          double s, c;
+          sincospi(2.0 * (double)k / (double)n_fft, &s, &c);
+          v = (double)x * (0.5 - 0.5 * c);                    // scipy.signal.get_window("hann", n_fft, fftbins=True)
+        }
+        const int r = (int)(__brev((unsigned)k) >> (32 - log2n));
+        re[r] = v;
+        im[r] = 0.0;
+      }
+      for (int st = 0; st < log2n; ++st) {
+        __syncthreads();
+        const int hb = 1 << st;
+        const int pos = tid & (hb - 1);
+        const int i0 = ((tid >> st) << (st + 1)) + pos, i1 = i0 + hb;
+        const int tw = pos << (log2n - 1 - st);
+        const double wr = twr[tw], wi = twi[tw];
+        const double ar = re[i1] * wr - im[i1] * wi, ai = re[i1] * wi + im[i1] * wr;
+        const double br = re[i0], bi = im[i0];
+        re[i0] = br + ar;
+        im[i0] = bi + ai;
+        re[i1] = br - ar;
+        im[i1] = bi - ai;
+      }
+      __syncthreads();
+      for (int f = tid; f < F; f += half_n) {
+        const float mag = hypotf((float)re[f], (float)im[f]);  // np.abs of the complex64 bin
+        obuf[f * kStftFrames + ft] = logf(mag + 1e-7f);
+      }
+    }
+  }
+  __syncthreads();
+  const int nt = min(kStftFrames, frames - t0);
+  float* ob = out + (int64_t)b * F * frames + t0;
+  for (int i = tid; i < F * kStftFrames; i += half_n) {
+    const int f = i / kStftFrames, ft = i - f * kStftFrames;
+    if (ft < nt) ob[(int64_t)f * frames + ft] = obuf[i];
+  }
+}
+
+}  // namespace gdl
+
+extern "C" int gdl_log_stft(const float* waves, int64_t clip_stride, const int32_t* clip_len, const int32_t* params, int B,
+                            int L, int n_fft, int hop, int pad_mode, float* out, gdl_stream_t s) {
+  using namespace gdl;
+  GDL_REQUIRE(waves && clip_len && params && out, "gdl_log_stft: null pointer");
+  GDL_REQUIRE(B > 0 && hop > 0 && n_fft >= 64 && n_fft <= kStftMaxFft && (n_fft & (n_fft - 1)) == 0 && L > n_fft / 2,
+              "gdl_log_stft: bad shape (n_fft a power of two in [64, 1024], L > n_fft/2)");
+  GDL_REQUIRE(pad_mode == 0 || pad_mode == 1, "gdl_log_stft: pad_mode is 0 (reflect) or 1 (zeros)");
+  int log2n = 0;
+  while ((1 << log2n) < n_fft) ++log2n;
+  const int frames = 1 + L / hop;
+  const size_t smem = (size_t)(2 * n_fft + n_fft) * sizeof(double) + (size_t)(n_fft / 2 + 1) * kStftFrames * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(log_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(log_stft)");
+    attr_set = true;
+  }
+  dim3 grid((frames + kStftFrames - 1) / kStftFrames, B);
+  log_stft_kernel<<<grid, n_fft / 2, smem, (cudaStream_t)s>>>(waves, clip_stride, clip_len,
+                                                             reinterpret_cast<const StftItem*>(params), L, n_fft, log2n, hop,
+                                                             frames, pad_mode, out);
+  GDL_CHECK_LAUNCH("log_stft_kernel");
+  return GDL_OK;
+}

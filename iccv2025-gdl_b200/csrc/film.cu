@@ -19,7 +19,7 @@ namespace gdl {
 int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t sH, int64_t sN, const void* src,
                   const void* wt, int64_t wt_rows, int64_t wt_k, void* dst, int Hd, int Wd, int Cd,
                   const void* add_src, int add_mode, cudaStream_t s, float* stats = nullptr,
-                  int* stats_rows = nullptr);
+                  int* stats_rows = nullptr, const float* bias = nullptr, int relu = 0);
 int64_t wgrad_flat_workspace_bytes(int N, int Ho, int Wo, int Ci, int Co, int R, int stride);
 int try_wgrad_flat(int N, int Hi, int Wi, int Ho, int Wo, int Ci, int Co, int R, int stride, const void* x,
                    const void* dy, float* partial, int64_t workspace_bytes, cudaStream_t s, int transposed,

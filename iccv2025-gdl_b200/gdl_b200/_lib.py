@@ -18,7 +18,8 @@ class GdlError(RuntimeError):
 
 class PackEntry(C.Structure):  # mirrors gdl_pack_entry
     _fields_ = [("w", C.c_void_p), ("wp", C.c_void_p), ("wT", C.c_void_p), ("Co", C.c_int32), ("Ci", C.c_int32),
-                ("ci_real", C.c_int32), ("R", C.c_int32), ("S", C.c_int32), ("Kp", C.c_int32), ("start", C.c_int64)]
+                ("ci_real", C.c_int32), ("R", C.c_int32), ("S", C.c_int32), ("Kp", C.c_int32), ("start", C.c_int64),
+                ("scale", C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -42,6 +43,8 @@ SIGNATURES = {
     "gdl_conv_wgrad_workspace_bytes": (_l, [_dp]),
     "gdl_conv_pack_weights": (_i, [_dp, _i, _p, _p, _p, _p]),
     "gdl_conv_fwd": (_i, [_dp, _p, _p, _p, _p]),
+    "gdl_conv_fwd_bias_act": (_i, [_dp, _p, _p, _p, _p, _i, _p, _p]),
+    "gdl_stem_pack_weights_scaled": (_i, [_p, _p, _p, _i, _p]),
     "gdl_conv_dgrad": (_i, [_dp, _p, _p, _p, _p, _i, _p]),
     "gdl_conv_wgrad": (_i, [_dp, _i, _p, _p, _p, _p, _l, _p]),
     "gdl_stem_geometry": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
@@ -98,6 +101,7 @@ SIGNATURES = {
     "gdl_check_gap_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "gdl_check_gap_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "gdl_check_fold_frames": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "gdl_log_stft": (_i, [_p, _l, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "gdl_crop_table_ints": (_l, [_i, _i]),
     "gdl_crop_resize_normalize": (_i, [_p, _l, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
 }

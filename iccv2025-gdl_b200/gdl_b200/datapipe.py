@@ -76,3 +76,46 @@ class VisualPipeline:
         ops.crop_resize_normalize(self.store.frames, self.store.n, self.store.H, self.store.W, params.contiguous(),
                                   frames, self.T, self.S, self._mean, self._std, out, self._table)
         return out
+
+
+class DeviceWaveStore:
+    """Decoded mono waveforms resident on the GPU: fp32 [n_clips, max_len] (rows zero padded) + their lengths."""
+
+    def __init__(self, waves, device=None):
+        dev = device if device is not None else "cuda"
+        n = len(waves)
+        self.lengths = torch.tensor([len(w) for w in waves], dtype=torch.int32)
+        self.stride = int(self.lengths.max())
+        buf = torch.zeros(n, self.stride)
+        for i, w in enumerate(waves):
+            buf[i, :len(w)] = torch.as_tensor(w, dtype=torch.float32)
+        self.waves = buf.to(dev).contiguous()
+        self.lengths = self.lengths.to(dev)
+        self.n = n
+
+
+class AudioPipeline:
+    """params (int32 [B, 2] = {clip index, start sample}, device) -> fp32 [B, 1 + n_fft/2, 1 + L/hop] on the current
+    stream: the reference's spectrogram np.log(np.abs(librosa.stft(clip(samples), n_fft, hop)) + 1e-7)
+    (dataset/CramedDataset.py:60-66: L = 22050*3, n_fft 512, hop 353, start 0; KSDataset.py:138-150 /
+    VGGSoundDataset.py:112-122: L = 16000*5, n_fft 256, hop 128, start = the host-drawn random.randint) computed by
+    libgdl_b200.so's gdl_log_stft from waveforms that stay in HBM.  pad_mode "reflect" is librosa < 0.10 (the
+    reference's era), "constant" librosa >= 0.10."""
+
+    def __init__(self, store, L, n_fft, hop, pad_mode="reflect"):
+        ops.init()
+        if pad_mode not in ("reflect", "constant"):
+            raise ValueError("pad_mode must be 'reflect' or 'constant'")
+        self.store, self.L, self.n_fft, self.hop = store, int(L), int(n_fft), int(hop)
+        self.pad = 0 if pad_mode == "reflect" else 1
+        self.F, self.frames = 1 + self.n_fft // 2, 1 + self.L // self.hop
+
+    def __call__(self, params, out=None):
+        if params.dtype != torch.int32 or params.dim() != 2 or params.shape[1] != 2 or not params.is_cuda:
+            raise ValueError("params must be a CUDA int32 tensor [B, 2]")
+        B = params.shape[0]
+        if out is None:
+            out = torch.empty(B, self.F, self.frames, device=params.device)
+        ops.log_stft(self.store.waves, self.store.stride, self.store.lengths, params.contiguous(), B, self.L, self.n_fft,
+                     self.hop, self.pad, out)
+        return out

@@ -83,28 +83,22 @@ class _ConvBN:
     def repack(self):
         ops.conv_pack_weights(self.d, self.ci_real, self.conv.weight.data, self.wp, self.wT)
 
-    def forward(self, eng, inp, res=None, training=True):
+    def forward(self, eng, inp, res=None):
+        """Training-mode unit (eval mode is EncoderEngine.forward_eval: BatchNorm folded into the conv)."""
         bn = self.bn
         c = self.cdir
-        if training:
-            # batch statistics come out of the conv epilogue where the kernel supports it (no extra pass over x)
-            ops.sweep(c)
-            rows = ops.conv_fwd_stats(self.d, inp, self.wp, self.x, eng.bn_partial, self.ci_real)
-            ops.sweep((not c) if SWEEP else 0)
-            if rows:
-                ops.bn_stats_finalize(eng.bn_partial, rows, self.P, self.C, bn.weight.data, bn.bias.data, bn.eps,
-                                      bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
-                                      self.scale, self.shift)
-            else:
-                ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
-                             bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
-                             self.scale, self.shift)
+        # batch statistics come out of the conv epilogue where the kernel supports it (no extra pass over x)
+        ops.sweep(c)
+        rows = ops.conv_fwd_stats(self.d, inp, self.wp, self.x, eng.bn_partial, self.ci_real)
+        ops.sweep((not c) if SWEEP else 0)
+        if rows:
+            ops.bn_stats_finalize(eng.bn_partial, rows, self.P, self.C, bn.weight.data, bn.bias.data, bn.eps,
+                                  bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                                  self.scale, self.shift)
         else:
-            ops.sweep(c)
-            ops.conv_fwd(self.d, inp, self.wp, self.x, self.ci_real)
-            ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
-                               self.scale, self.shift, self.C)
-            c = (not c) if SWEEP else 0  # no statistics pass in between: apply runs opposite to the conv
+            ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
+                         bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                         self.scale, self.shift)
         ops.sweep(c)
         ops.bn_apply(self.x, res, self.y, self.P, self.C, self.scale, self.shift, self.relu)
         return self.y
@@ -134,20 +128,16 @@ class _StemBN(_ConvBN):
     def repack(self):
         ops.stem_pack_weights(self.conv.weight.data, self.wp, self.ci_real)
 
-    def forward(self, eng, x16, res=None, training=True):
+    def forward(self, eng, x16, res=None):
         ops.stem_fwd(x16, self.wp, self.x, self.N, self.H, self.W, self.ci_real)
         bn = self.bn
-        if training:
-            ops.sweep(1 if SWEEP else 0)
-            ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
-                         bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
-                         self.scale, self.shift)
-        else:
-            ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
-                               self.scale, self.shift, self.C)
+        ops.sweep(1 if SWEEP else 0)
+        ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
+                     bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                     self.scale, self.shift)
         # BN-apply + ReLU + MaxPool(3,2,1) in one pass (reference backbone.py:104-106)
-        ops.bn_relu_maxpool_fwd(self.x, self.scale, self.shift, eng.pool_y, eng.pool_idx,
-                                eng.pool_xmax if training else None, self.N, self.Ho, self.Wo, 64, eng.Hp, eng.Wp)
+        ops.bn_relu_maxpool_fwd(self.x, self.scale, self.shift, eng.pool_y, eng.pool_idx, eng.pool_xmax,
+                                self.N, self.Ho, self.Wo, 64, eng.Hp, eng.Wp)
         return eng.pool_y
 
 
@@ -191,6 +181,8 @@ class EncoderEngine:
         self.bn_partial = torch.empty(self.max_bn_partial, device=device, dtype=torch.float32)
         self.wgrad_stream = torch.cuda.Stream(device) if USE_WGRAD_STREAM else None
         self._readers = {}
+        self._manual_version = 0
+        self._eval_key_folded = None
         self._plan_backward()
         self.repack()
 
@@ -203,6 +195,7 @@ class EncoderEngine:
     def repack(self):
         """Refresh the bf16 shadows from the fp32 masters (after every optimizer step): one multi-tensor
         launch for the 19 block convolutions + the stem's own packer."""
+        self._manual_version += 1  # parameters / running statistics changed behind torch's version counters
         convs = [u for u in self.units if u is not self.stem]
         key = tuple(u.conv.weight.data_ptr() for u in convs)
         if getattr(self, "_pack_key", None) != key:  # the parameters moved (e.g. into the step's arena)
@@ -212,19 +205,78 @@ class EncoderEngine:
         self.stem.repack()
         ops.conv_pack_weights_multi(*self._pack_table)
 
+    # ------------------------------------------------------------------ eval mode: BatchNorm folded into the conv
+    def _eval_key(self):
+        v = self._manual_version
+        for u in self.units:
+            bn = u.bn
+            v += (u.conv.weight._version + bn.weight._version + bn.bias._version + bn.running_mean._version
+                  + bn.running_var._version)
+        return (v, tuple(u.conv.weight.data_ptr() for u in self.units))
+
+    def fold_eval(self):
+        """model.eval() (reference valid(), main_dgl.py:186): every BatchNorm uses its running statistics, so
+        conv -> BN is one affine map per output channel.  scale = gamma / sqrt(running_var + eps) is folded into
+        separate bf16 shadows (w' = w * scale, one multi-tensor pack launch with gdl_pack_entry.scale), and
+        shift = beta - running_mean * scale becomes the bias of the conv epilogue (gdl_conv_fwd_bias_act), together
+        with the residual add and the ReLU: an eval unit is ONE kernel, no BatchNorm pass.  Re-folded only when a
+        parameter / buffer changed (torch version counters + the engine's own counter for kernel-side updates)."""
+        key = self._eval_key()
+        if self._eval_key_folded == key:
+            return
+        dev = self.device
+        if not hasattr(self.stem, "wp_e"):
+            for u in self.units:
+                u.wp_e = torch.zeros_like(u.wp)
+                u.scale_e, u.shift_e = torch.empty(u.C, device=dev), torch.empty(u.C, device=dev)
+            self.ones64 = torch.ones(64, device=dev)
+        for u in self.units:
+            bn = u.bn
+            ops.bn_eval_affine(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps,
+                               u.scale_e, u.shift_e, u.C)
+        convs = [u for u in self.units if u is not self.stem]
+        entries = [(u.conv.weight.data, u.wp_e, None, u.C, u.d.Ci, u.ci_real, u.d.R, u.d.S, u.Kp, u.scale_e) for u in convs]
+        self._pack_table_eval = ops.make_pack_table(entries, dev)  # holds raw addresses: rebuilt with the fold
+        s = self.stem
+        ops.stem_pack_weights_scaled(s.conv.weight.data, s.scale_e, s.wp_e, s.ci_real)
+        ops.conv_pack_weights_multi(*self._pack_table_eval)
+        self._eval_key_folded = key
+
+    def forward_eval(self, x16):
+        """Eval-mode forward with folded BatchNorm: stem conv -> (+shift, ReLU, max-pool) -> 8 blocks of three fused
+        conv kernels (reference backbone.py:52-68 with model.eval())."""
+        self.fold_eval()
+        s = self.stem
+        ops.sweep(0)
+        ops.stem_fwd(x16, s.wp_e, s.x, s.N, s.H, s.W, s.ci_real)
+        ops.bn_relu_maxpool_fwd(s.x, self.ones64, s.shift_e, self.pool_y, self.pool_idx, None, s.N, s.Ho, s.Wo, 64,
+                                self.Hp, self.Wp)
+        u = self.pool_y
+        for (u1, u2, ud) in self.blocks:
+            ops.conv_fwd_bias_act(u1.d, u, u1.wp_e, u1.shift_e, None, 1, u1.y)
+            ident = u
+            if ud is not None:
+                ops.conv_fwd_bias_act(ud.d, u, ud.wp_e, ud.shift_e, None, 0, ud.y)
+                ident = ud.y
+            ops.conv_fwd_bias_act(u2.d, u1.y, u2.wp_e, u2.shift_e, ident, 1, u2.y)
+            u = u2.y
+        return u
+
     # ------------------------------------------------------------------ forward
     def forward(self, x16, training=True):
         """x16: bf16 space-to-depth input [N,Hp,Wp,16] -> bf16 [N,Hf,Wf,512] (the layer4 map,
-        reference backbone.py:175-181).  training=False uses the BN running statistics."""
+        reference backbone.py:175-181).  training=False: eval mode, BatchNorm folded into the convolutions."""
+        if not training:
+            return self.forward_eval(x16)
         s = self.stem
-        u = s.forward(self, x16, training=training)  # stem conv + BN + ReLU + max-pool -> pool_y
+        u = s.forward(self, x16)  # stem conv + BN + ReLU + max-pool -> pool_y
         for (u1, u2, ud) in self.blocks:
-            y1 = u1.forward(self, u, training=training)
+            y1 = u1.forward(self, u)
             ident = u
             if ud is not None:
-                ident = ud.forward(self, u, training=training)
+                ident = ud.forward(self, u)
             # bn2 + residual + relu (reference backbone.py:62-66)
-            u = u2.forward(self, y1, res=ident, training=training)
+            u = u2.forward(self, y1, res=ident)
         ops.sweep(0)
         return u
 

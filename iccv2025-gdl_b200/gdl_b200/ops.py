@@ -101,12 +101,16 @@ def conv_pack_weights(d, ci_real, w_oihw, w_packed, w_packed_T=None):
 
 
 def make_pack_table(entries, device):
-    """entries: [(w_oihw, w_packed, w_packed_T or None, Co, Ci, ci_real, R, S, Kp)] -> (device table, n, total).
+    """entries: [(w_oihw, w_packed, w_packed_T or None, Co, Ci, ci_real, R, S, Kp[, scale or None])] ->
+    (device table, n, total).  scale: fp32 [Co] folded into the rows (eval mode).
     The table holds raw device addresses: rebuild it if any tensor is re-allocated."""
     arr = (_lib.PackEntry * len(entries))()
     start = 0
-    for e, (w, wp, wT, Co, Ci, ci_real, R, S, Kp) in zip(arr, entries):
+    for e, ent in zip(arr, entries):
+        w, wp, wT, Co, Ci, ci_real, R, S, Kp = ent[:9]
+        scale = ent[9] if len(ent) > 9 else None
         e.w, e.wp, e.wT = w.data_ptr(), wp.data_ptr(), (wT.data_ptr() if wT is not None else None)
+        e.scale = scale.data_ptr() if scale is not None else None
         e.Co, e.Ci, e.ci_real, e.R, e.S, e.Kp, e.start = Co, Ci, ci_real, R, S, Kp, start
         start += Co * Kp
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -122,6 +126,13 @@ def conv_pack_weights_multi(table, n, total):
 def conv_fwd(d, x, w_packed, y, ci_real=None):
     check(_lib.load().gdl_conv_fwd(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(y), _stream()),
           "gdl_conv_fwd")
+
+
+@_op("conv_fwd", 1, lambda d, x, w, bias, res, relu, y: ("flops", conv_flops(d), _dstr(d)))
+def conv_fwd_bias_act(d, x, w_packed, bias, res, relu, y):
+    """Eval-mode fused unit: y = [relu](conv(x, w') + bias[co] [+ res]) with the BatchNorm scale folded into w'."""
+    check(_lib.load().gdl_conv_fwd_bias_act(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(res), int(relu),
+                                            _ptr(y), _stream()), "gdl_conv_fwd_bias_act")
 
 
 @_op("conv_fwd", 1, lambda d, x, w, y, partial, ci_real=None: ("flops", conv_flops(d, ci_real), _dstr(d)))
@@ -195,6 +206,12 @@ def stem_layout(src, dst, B, Cc, T, H, W):
 @_op("pack_weights", 1)
 def stem_pack_weights(w_oihw, w_packed, Cc):
     check(_lib.load().gdl_stem_pack_weights(_ptr(w_oihw), _ptr(w_packed), Cc, _stream()), "gdl_stem_pack_weights")
+
+
+@_op("pack_weights", 1)
+def stem_pack_weights_scaled(w_oihw, scale64, w_packed, Cc):
+    check(_lib.load().gdl_stem_pack_weights_scaled(_ptr(w_oihw), _ptr(scale64), _ptr(w_packed), Cc, _stream()),
+          "gdl_stem_pack_weights_scaled")
 
 
 @_op("conv_fwd", 1, lambda x16, w, y, N, H, W, Cc: ("flops", _stem_flops(N, H, W, Cc), "N%d %dx%d stem C%d s2d" % (N, H, W, Cc)))
@@ -428,3 +445,9 @@ def crop_resize_normalize(store, store_frames, Hs, Ws, params, frames, T, S, mea
     check(_lib.load().gdl_crop_resize_normalize(_ptr(store), store_frames, Hs, Ws, _ptr(params), frames, T, S,
                                                 C.cast(mean3, C.c_void_p), C.cast(std3, C.c_void_p), _ptr(out),
                                                 _ptr(table), _stream()), "gdl_crop_resize_normalize")
+
+
+@_op("log_stft", 1, lambda waves, stride, lens, params, B, L, n_fft, hop, pad, out: ("bytes", 4.0 * B * L + 4.0 * out.numel()))
+def log_stft(waves, clip_stride, clip_len, params, B, L, n_fft, hop, pad_mode, out):
+    check(_lib.load().gdl_log_stft(_ptr(waves), clip_stride, _ptr(clip_len), _ptr(params), B, L, n_fft, hop, pad_mode,
+                                   _ptr(out), _stream()), "gdl_log_stft")

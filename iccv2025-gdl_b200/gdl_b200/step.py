@@ -152,6 +152,7 @@ class DGLStep:
                         torch.zeros(B, device=dev, dtype=torch.int64)) for _ in range(2)]
         self._cur, self._pending = 0, None
         self._crop_params = None  # device copies of the crop-box tables (prefetch with a VisualPipeline)
+        self._audio_params = None  # device copies of the {clip, start} tables (prefetch with an AudioPipeline)
         self.copy_stream = torch.cuda.Stream(dev)
         self._stage_ready = [torch.cuda.Event() for _ in range(2)]
         self._stage_free = [torch.cuda.Event() for _ in range(2)]
@@ -362,7 +363,7 @@ class DGLStep:
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
 
-    def prefetch(self, spec, image, label, pipeline=None):
+    def prefetch(self, spec, image, label, pipeline=None, audio_pipeline=None):
         """Start the H2D copy of the NEXT batch (pinned host tensors) on the copy stream into the staging
         set that the running step does not read; the next step() without arguments consumes it.  This is the
         pin_memory + non_blocking pattern of the reference's DataLoader (main_dgl.py:284-288,93-95) made
@@ -371,14 +372,22 @@ class DGLStep:
         pipeline: a datapipe.VisualPipeline — `image` is then the int32 [B*T, 6] table of host-drawn crop boxes
         (datapipe.draw_frame_params) and the fp32 frames are produced ON the device from the resident uint8
         frame store (bit-identical to the reference transform), so only the spectrograms and 24 bytes per frame
-        cross PCIe."""
+        cross PCIe.
+        audio_pipeline: a datapipe.AudioPipeline — `spec` is then the int32 [B, 2] table {clip index, start sample}
+        and the log-STFT spectrograms are computed on the device from the resident waveforms (gdl_log_stft)."""
         nxt = 1 - self._cur
         cs = self.copy_stream
         cs.wait_event(self._stage_free[nxt])  # the layout kernels that last read this set have run
         with torch.cuda.stream(cs):
             s_spec, s_image, s_label = self._stage[nxt]
-            s_spec.copy_(spec, non_blocking=True)
             s_label.copy_(label, non_blocking=True)
+            if audio_pipeline is None:
+                s_spec.copy_(spec, non_blocking=True)
+            else:
+                if self._audio_params is None:
+                    self._audio_params = [torch.empty(self.B, 2, device=self.device, dtype=torch.int32) for _ in range(2)]
+                self._audio_params[nxt].copy_(spec, non_blocking=True)
+                audio_pipeline(self._audio_params[nxt], out=s_spec)
             if pipeline is None:
                 s_image.copy_(image, non_blocking=True)
             else:

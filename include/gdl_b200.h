@@ -68,11 +68,20 @@ typedef struct {
   void* wT;       /* bf16 [Ci][R*S*Co] or NULL */
   int32_t Co, Ci, ci_real, R, S, Kp;
   int64_t start;
+  const float* scale; /* NULL, or fp32 [Co]: row co is multiplied by scale[co] before rounding (eval mode: the
+                         BatchNorm running-statistics scale gamma/sqrt(var+eps) folded into the weights) */
 } gdl_pack_entry;
 int gdl_conv_pack_weights_multi(const gdl_pack_entry* table_dev, int n, int64_t total, gdl_stream_t s);
 /* y[N,Ho,Wo,Co] = conv(x[N,Hi,Wi,Ci], w).  Implicit GEMM, tcgen05 + TMEM accumulators. */
 int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
                  gdl_stream_t s);
+/* Eval-mode fused unit (reference valid(), main_dgl.py:168-222: model.eval() => BatchNorm2d uses its running
+ * statistics, backbone.py:45-66): with the BN scale folded into w_packed (gdl_pack_entry.scale) the whole
+ * conv -> BN -> (+identity) -> ReLU unit is y = [relu](conv(x, w') + bias[co] [+ res]), bias = beta - mean*scale,
+ * res NULL or a bf16 tensor of y's shape.  Flat-window geometries only (3x3 s1/s2 pad 1, 1x1 pad 0, Ci % 64 == 0);
+ * anything else returns GDL_EINVAL. */
+int gdl_conv_fwd_bias_act(const gdl_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                          const void* res, int relu, void* y, gdl_stream_t s);
 /* Same, and the BatchNorm statistics of y (reference backbone.py:45,48: train-mode BN follows every conv) are
  * accumulated in the epilogue: bn_partial receives *bn_partial_rows rows of [2][Co] floats (per-warp sum and sum
  * of squares of the bf16-rounded outputs) for gdl_bn_stats_finalize.  *bn_partial_rows == 0 means the shape took
@@ -106,6 +115,8 @@ int gdl_stem_geometry(int H, int W, int* Ho, int* Wo, int* Hp, int* Wp);
 int gdl_stem_layout(const float* src, void* x16, int B, int C, int T, int H, int W, gdl_stream_t s);
 /* fp32 OIHW [64][C][7][7] -> bf16 [64][256]. */
 int gdl_stem_pack_weights(const float* w_oihw, void* w_packed, int C, gdl_stream_t s);
+/* Same with output channel co multiplied by scale64[co] (eval mode: BatchNorm scale folded into the stem). */
+int gdl_stem_pack_weights_scaled(const float* w_oihw, const float* scale64, void* w_packed, int C, gdl_stream_t s);
 /* y bf16 [N,Ho,Wo,64]. */
 int gdl_stem_fwd(const void* x16, const void* w_packed, void* y, int N, int H, int W, gdl_stream_t s);
 int64_t gdl_stem_wgrad_workspace_bytes(int N, int H, int W);
@@ -315,6 +326,23 @@ int64_t gdl_crop_table_ints(int frames, int S);
 int gdl_crop_resize_normalize(const uint8_t* store, int64_t store_frames, int Hs, int Ws, const int32_t* params,
                               int frames, int T, int S, const float* mean3, const float* std3, float* out,
                               int32_t* table, gdl_stream_t s);
+
+/* ---- audio data pipeline (reference dataset/CramedDataset.py:60-66; KSDataset.py:138-150; VGGSoundDataset.py:112-122):
+ * spectrogram = np.log(np.abs(librosa.stft(clip(wave, -1, 1), n_fft, hop_length)) + 1e-7), computed on the device
+ * from decoded waveforms that stay resident in HBM.  librosa.stft semantics: center=True,
+ * periodic Hann window of n_fft samples, float64 window product and FFT, bins stored as complex64; abs / log in
+ * float32.  The random draws stay on the host in the reference's order (KS/VGG: random.randint for the window start).
+ *   waves     f32 [n_clips][clip_stride]   decoded mono waveforms (device)
+ *   clip_len  i32 [n_clips]                valid samples per clip (device)
+ *   params    i32 [B][2] (device)          {clip index, start sample}: sample i of item b is
+ *                                          wave[clip][(start + i) mod clip_len] — np.tile(samples, 3)[:L] with start 0
+ *                                          (CREMA-D) and the tile-to-10-s + [start : start + L] window of KS / VGGSound
+ *   L         samples per item (22050*3 or 16000*5); frames = 1 + L / hop
+ *   pad_mode  0 = reflect (librosa < 0.10, the era of the reference's README), 1 = zeros (librosa >= 0.10 default)
+ *   out       f32 [B][1 + n_fft/2][frames]  — the `spec` tensor the reference's DataLoader yields (main_dgl.py:93)
+ * n_fft a power of two in [64, 1024].  Asynchronous, no allocation. */
+int gdl_log_stft(const float* waves, int64_t clip_stride, const int32_t* clip_len, const int32_t* params, int B,
+                 int L, int n_fft, int hop, int pad_mode, float* out, gdl_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -171,3 +171,49 @@ def test_train_epoch_over_a_pinning_dataloader_with_graph_capture(tmp_path):
     assert len(rows) == 6 and all(float(r[0]) > 0 and float(r[1]) > 0 for r in rows)
     assert all(x == x and 0 < x < 50 for x in res[:3])  # finite epoch-mean losses
     assert model._gdl_step._graph is not None           # the captured path really ran
+
+
+def test_valid_with_folded_batchnorm_on_a_64_sample_test_set(tmp_path):
+    """SURVEY.md §8f rank 1 (reference valid(), main_dgl.py:168-222): eval-mode forward with BatchNorm folded into
+    the packed conv weights (one fused conv kernel per unit, no BN pass) on a 64-sample synthetic test set after a
+    few training steps: logits within 1e-2 of the fp32 oracle's eval forward on the SAME weights / running
+    statistics, (acc, acc_a, acc_v) exactly equal, and the fold follows load_state_dict."""
+    from gdl_b200.step import DGLStep
+    from gdl_b200.train import valid
+    from oracle import dgl_oracle as O
+    from oracle.synth import SHAPES, make_batch
+    args, model = make_model("concat")
+    Fq, Tt, T, H, W = SHAPES["tiny"]
+    step = DGLStep(model, 16, (Fq, Tt), (T, H, W), lr=0.01, use_graph=False)
+    for s in range(4):  # non-trivial running statistics and weights
+        step.step(*[t.cuda() for t in make_batch(16, 6, "tiny", seed=1 + s)])
+    torch.cuda.synchronize()
+    model.eval()
+    batches = [make_batch(16, 6, "tiny", seed=50 + i) for i in range(4)]  # 64 samples
+    msd = model.state_dict()
+    sd_same = {k: v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu() for k, v in msd.items()}
+    correct = torch.zeros(3)
+    worst = 0.0
+    with torch.no_grad():
+        for spec, image, label in batches:
+            got = model(spec.cuda().unsqueeze(1).float(), image.cuda().float())
+            ref = O.model_forward(sd_same, spec, image, "concat", training=False)
+            for i, (g, r) in enumerate(zip(got, ref)):
+                worst = max(worst, (g.cpu() - r).abs().max().item() / r.abs().max().item())
+                correct[i] += (r.argmax(1) == label).sum()
+    acc = valid(args, _Wrap(model), torch.device("cuda"), batches)
+    print("eval logits: max |diff| / max |logit| = %.4f; acc %s vs oracle %s" % (worst, acc, (correct / 64).tolist()))
+    assert worst <= 1e-2, worst
+    assert list(acc) == (correct / 64).tolist()
+    eng = model.audio_net.engine(16, Fq, Tt)
+    assert hasattr(eng.stem, "wp_e") and eng._eval_key_folded is not None   # the folded path really ran
+    # a changed state dict must re-fold: scaling every BN gamma of the audio encoder changes the audio logits
+    sd2 = {k: (v * 1.5 if k.startswith("audio_net") and k.endswith("bn2.weight") else v) for k, v in msd.items()}
+    before = model(batches[0][0].cuda().unsqueeze(1).float(), batches[0][1].cuda().float())[1].clone()
+    model.load_state_dict(sd2)
+    with torch.no_grad():
+        after = model(batches[0][0].cuda().unsqueeze(1).float(), batches[0][1].cuda().float())[1]
+        sd2c = {k: v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu() for k, v in sd2.items()}
+        ref2 = O.model_forward(sd2c, batches[0][0], batches[0][1], "concat", training=False)[1]
+    assert (after - before).abs().max().item() > 1e-3
+    assert (after.cpu() - ref2).abs().max().item() <= 1e-2 * ref2.abs().max().item()

@@ -129,3 +129,101 @@ def test_training_step_with_device_pipeline_is_bit_identical():
         results.append((step.read_stats(), step.arena.param.clone()))
     assert results[0][0] == results[1][0]
     assert torch.equal(results[0][1], results[1][1])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# audio half: gdl_log_stft vs the oracle restating librosa.stft (oracle/stft_oracle.py,
+# pinned to scipy.signal.stft by tests/test_cpu_stft.py).  Floating point: |log-spectrogram difference| <= 5e-5
+# (the reference computes the FFT in float64 and stores complex64; the kernel does the same on the device, so what
+# is left is the order of the FFT butterflies and a float32 hypot / log ulp).
+# ------------------------------------------------------------------------------------------------------------
+def _audio(n_clips, lens, seed):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    waves = []
+    for i in range(n_clips):
+        n = lens[i % len(lens)]
+        t = np.arange(n) / 16000.0
+        w = 0.6 * rs.randn(n) * np.exp(-t * rs.uniform(0.2, 3.0)) + 0.9 * np.sin(2 * np.pi * rs.uniform(80, 4000) * t)
+        waves.append((w * rs.uniform(0.3, 1.6)).astype(np.float32))   # some clips exceed [-1, 1]: clipping matters
+    return waves
+
+
+@pytest.mark.parametrize("geom", [("CREMAD", 22050 * 3, 512, 353, (257, 188)), ("KS", 16000 * 5, 256, 128, (129, 626))])
+@pytest.mark.parametrize("pad_mode", ["reflect", "constant"])
+def test_log_stft_matches_oracle(geom, pad_mode):
+    import numpy as np
+    from gdl_b200.datapipe import AudioPipeline, DeviceWaveStore
+    from oracle import stft_oracle as S
+    name, L, n_fft, hop, shape = geom
+    waves = _audio(6, [41234, 55125, 64000, 170000], seed=11)
+    store = DeviceWaveStore(waves, "cuda")
+    pipe = AudioPipeline(store, L, n_fft, hop, pad_mode)
+    rs = np.random.RandomState(2)
+    B = 9
+    clips = rs.randint(0, 6, size=B)
+    starts = np.zeros(B, dtype=np.int64) if name == "CREMAD" else rs.randint(0, 16000 * 5 + 1, size=B)
+    params = torch.tensor(np.stack([clips, starts], 1), dtype=torch.int32, device="cuda")
+    out = pipe(params)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (B,) + shape
+    worst = 0.0
+    for b in range(B):
+        ref = S.log_spectrogram(waves[clips[b]], int(starts[b]), L, n_fft, hop, pad_mode)
+        worst = max(worst, float(np.abs(out[b].cpu().numpy() - ref).max()))
+    assert worst <= 5e-5, worst
+
+
+def test_log_stft_golden_and_determinism():
+    """The committed scipy-generated vectors (tests/golden/stft_golden.npz), straight against the kernel."""
+    import numpy as np
+    from gdl_b200.datapipe import AudioPipeline, DeviceWaveStore
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stft_golden.npz"))
+    for name in ("noise", "tones", "clipped"):
+        w = g["wave_" + name]
+        store = DeviceWaveStore([w], "cuda")
+        for n_fft, hop in ((512, 353), (256, 128)):
+            pipe = AudioPipeline(store, len(w), n_fft, hop)
+            p = torch.zeros(1, 2, dtype=torch.int32, device="cuda")
+            a, b = pipe(p), pipe(p)
+            torch.cuda.synchronize()
+            assert torch.equal(a, b)
+            ref = g["spec_%s_%d_%d" % (name, n_fft, hop)]
+            assert np.abs(a[0].cpu().numpy() - ref).max() <= 5e-5, (name, n_fft)
+
+
+def test_step_fed_by_the_device_audio_pipeline():
+    """A training step whose spectrograms are produced on the device from resident waveforms equals (bit for bit in
+    its inputs' bf16 rounding aside, to 1e-3 in the losses) a step fed with host-computed spectrograms."""
+    import argparse
+    import numpy as np
+    import gdl_b200
+    from gdl_b200.datapipe import AudioPipeline, DeviceWaveStore
+    from gdl_b200.step import DGLStep
+    from oracle import stft_oracle as S
+    B, L, n_fft, hop = 4, 4000, 128, 67          # tiny geometry: spectrogram 65 x 60 = the "tiny" test shape
+    waves = _audio(5, [3000, 5100], seed=4)
+    clips, starts = np.array([0, 3, 2, 4]), np.array([0, 17, 2999, 801])
+    spec_host = torch.tensor(np.stack([S.log_spectrogram(waves[c], int(s), L, n_fft, hop) for c, s in zip(clips, starts)]))
+    assert tuple(spec_host.shape) == (B, 65, 60)
+    g = torch.Generator().manual_seed(3)
+    image = torch.randn(B, 3, 2, 64, 64, generator=g)
+    label = torch.randint(0, 6, (B,), generator=g)
+    res = []
+    for device_audio in (False, True):
+        args = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modality="full")
+        gdl_b200.setup_seed(0)
+        model = gdl_b200.AVClassifier_DGL(args)
+        model.apply(gdl_b200.weight_init)
+        model.cuda().train()
+        step = DGLStep(model, B, (65, 60), (2, 64, 64), lr=0.01, use_graph=False)
+        if device_audio:
+            pipe = AudioPipeline(DeviceWaveStore(waves, "cuda"), L, n_fft, hop)
+            params = torch.tensor(np.stack([clips, starts], 1), dtype=torch.int32).pin_memory()
+            step.prefetch(params, image.pin_memory(), label.pin_memory(), audio_pipeline=pipe)
+            step.step()
+        else:
+            step.step(spec_host.cuda(), image.cuda(), label.cuda())
+        res.append(step.read_stats())
+    for a, b in zip(res[0][:4], res[1][:4]):
+        assert abs(a - b) <= 1e-3 * abs(a), (res[0], res[1])

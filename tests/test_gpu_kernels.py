@@ -76,6 +76,37 @@ def test_conv_fwd(case):
     assert rel_err(nchw(y), ref) < 6e-3, rel_err(nchw(y), ref)
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[3] % 64 == 0])
+@pytest.mark.parametrize("use_res,relu", [(0, 1), (1, 1), (0, 0)])
+def test_conv_fwd_bias_act(case, use_res, relu):
+    """Eval-mode fused unit (gdl_conv_fwd_bias_act): y = [relu](conv(x, w * scale[co]) + bias[co] [+ res]) with the
+    scale folded into the packed weights by the multi-tensor pack (gdl_pack_entry.scale) — against conv2d +
+    eval-mode batch_norm-style affine in torch fp32."""
+    ops = _ops()
+    N, H, W, Ci, Co, R, stride, pad = case
+    xb, wb = _mk(*case)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    scale = torch.rand(Co, device="cuda", generator=g) + 0.5
+    bias = torch.randn(Co, device="cuda", generator=g)
+    d = ops.conv_desc(N, H, W, Ci, Co, R, R, stride, pad)
+    Kp = ops.conv_packed_k(d)
+    wp = torch.zeros(Co, Kp, device="cuda", dtype=torch.bfloat16)
+    table = ops.make_pack_table([(wb, wp, None, Co, Ci, Ci, R, R, Kp, scale)], torch.device("cuda"))
+    ops.conv_pack_weights_multi(*table)
+    res = torch.randn(N, d.Ho, d.Wo, Co, device="cuda", generator=g).to(torch.bfloat16) if use_res else None
+    y = torch.full((N, d.Ho, d.Wo, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd_bias_act(d, nhwc(xb), wp, bias, res, relu, y)
+    torch.cuda.synchronize()
+    wf = (wb * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).float()   # the fold rounds w * scale to bf16
+    ref = F.conv2d(xb, wf, stride=stride, padding=pad) + bias.view(1, -1, 1, 1)
+    if use_res:
+        ref = ref + nchw(res)
+    if relu:
+        ref = torch.relu(ref)
+    assert torch.isfinite(y.float()).all()
+    assert rel_err(nchw(y), ref) < 6e-3, rel_err(nchw(y), ref)
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_fwd_fused_bn_statistics(case):
     """gdl_conv_fwd_stats: the partial sums from the conv epilogue give the same BN statistics as a
@@ -653,3 +684,19 @@ def test_grad_stats_and_sgd():
         assert torch.allclose(param[o:o + n].view(s), p.detach(), atol=1e-6, rtol=1e-5)
         assert torch.allclose(grad[o:o + n].view(s), p.grad, atol=1e-6, rtol=1e-5)
     assert p0.shape == param.shape
+
+
+def test_generic_gather_kernels():
+    """The generic (cp.async im2col gather) forward / data-gradient / weight-gradient kernels are the library's
+    fallback for geometries outside the flat-window TMA kernels; GDL_FLAT=0 GDL_WFLAT=0 (read once per process)
+    routes every convolution to them, so the same parity cases are re-run in a subprocess with those switches."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GDL_FLAT="0", GDL_WFLAT="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "--no-header", "-x",
+                        "-p", "no:cacheprovider", "-k",
+                        "(test_conv_fwd or test_conv_dgrad or test_conv_wgrad) and not bias_act and not statistics"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
