@@ -88,6 +88,8 @@ __device__ __forceinline__ float warp_softmax_ce(const float* z, int n, int labe
 // ------------------------------------------------------------------------------------------
 // fused concat / sum head, phase A: one CTA per sample
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
 constexpr int kHeadThreads = 256;
 constexpr int kHeadMaxN = 512;
 constexpr int kHeadMaxD = 1024;
@@ -217,8 +219,6 @@ __global__ void loss_rows_sum_kernel(const float* __restrict__ loss_rows, float 
 // ------------------------------------------------------------------------------------------
 // gated head elementwise pieces
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
 __global__ void gated_fwd_kernel(const float* __restrict__ hx, const float* __restrict__ hy,
                                  float* __restrict__ m_out, float* __restrict__ m_x,
                                  float* __restrict__ m_y, int64_t numel) {
@@ -239,6 +239,144 @@ __global__ void gated_bwd_kernel(const float* __restrict__ hx, const float* __re
   float sx = sigmoidf_(x), sy = sigmoidf_(y);
   dhx[i] = dm_x[i] * (sx + x * sx * (1.f - sx));
   dhy[i] = dm_y[i] * (sy + y * sy * (1.f - sy));
+}
+
+
+// ------------------------------------------------------------------------------------------
+// fused GatedFusion_DGL head (reference models/fusion_modules.py:230-250 + main_dgl.py:102-122), one CTA per sample:
+//   hx = fc_x(a), hy = fc_y(v);  out = fc_out(sig(hx.detach()) * hy.detach()),
+//   out_x = fc_out(sig(hx) * hx), out_y = fc_out(sig(hy) * hy);  three softmax-CE;
+//   routing in registers: a <- alpha*dLa through fc_out, the gate and fc_x;  v <- alpha*dLv likewise;
+//   fc_out <- dLf only (phase B: dgl_gated_param_kernel);  fc_x / fc_y receive NO gradient (their unimodal
+//   gradient is wiped, and Lf sees them detached — SURVEY.md §8a quirk 2).
+// Replaces the chain of 15 generic launches (2 linear, gate, 3 x (linear + CE), 5 linear_bwd, gate_bwd).
+// ------------------------------------------------------------------------------------------
+constexpr int kGatedD = 512;
+
+__global__ void __launch_bounds__(kHeadThreads) dgl_gated_sample_kernel(
+    const float* __restrict__ a, const float* __restrict__ v, const float* __restrict__ Wx, const float* __restrict__ bx,
+    const float* __restrict__ Wy, const float* __restrict__ by, const float* __restrict__ Wo, const float* __restrict__ bo,
+    const int64_t* __restrict__ labels, float alpha, float inv_batch, float* __restrict__ logits, float* __restrict__ da,
+    float* __restrict__ dv, float* __restrict__ m_out_all, float* __restrict__ g_out_all, float* __restrict__ loss_rows,
+    int B, int n) {
+  constexpr int D = kGatedD;
+  __shared__ float s_a[D], s_v[D], s_hx[D], s_hy[D];
+  __shared__ float s_m[3][D];            // m_out, m_x, m_y; later reused for dhx (row 1) and dhy (row 2)
+  __shared__ float s_z[3][kHeadMaxN];
+  __shared__ float s_g[3][kHeadMaxN];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < D; i += kHeadThreads) {
+    s_a[i] = a[(int64_t)b * D + i];
+    s_v[i] = v[(int64_t)b * D + i];
+  }
+  __syncthreads();
+  for (int j = warp; j < D; j += kHeadThreads / 32) {  // hx, hy: one warp per output row
+    const float* wx = Wx + (int64_t)j * D;
+    const float* wy = Wy + (int64_t)j * D;
+    float px = 0.f, py = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      px = fmaf(wx[i], s_a[i], px);
+      py = fmaf(wy[i], s_v[i], py);
+    }
+    px = warp_sum(px);
+    py = warp_sum(py);
+    if (lane == 0) {
+      s_hx[j] = px + bx[j];
+      s_hy[j] = py + by[j];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < D; i += kHeadThreads) {
+    const float x = s_hx[i], y = s_hy[i];
+    const float sx = sigmoidf_(x), sy = sigmoidf_(y);
+    s_m[0][i] = sx * y;
+    s_m[1][i] = sx * x;
+    s_m[2][i] = sy * y;
+    m_out_all[(int64_t)b * D + i] = sx * y;
+  }
+  __syncthreads();
+  for (int j = warp; j < n; j += kHeadThreads / 32) {  // three logit sets share every row of fc_out
+    const float* wo = Wo + (int64_t)j * D;
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float w = wo[i];
+      p0 = fmaf(w, s_m[0][i], p0);
+      p1 = fmaf(w, s_m[1][i], p1);
+      p2 = fmaf(w, s_m[2][i], p2);
+    }
+    p0 = warp_sum(p0);
+    p1 = warp_sum(p1);
+    p2 = warp_sum(p2);
+    if (lane == 0) {
+      s_z[0][j] = p0 + bo[j];
+      s_z[1][j] = p1 + bo[j];
+      s_z[2][j] = p2 + bo[j];
+    }
+  }
+  __syncthreads();
+  const int label = int(labels[b]);
+  if (warp < 3) {
+    const float gs = warp == 0 ? inv_batch : alpha * inv_batch;
+    float loss = warp_softmax_ce(s_z[warp], n, label, gs, s_g[warp]);
+    if (lane == 0) loss_rows[(int64_t)b * 3 + warp] = loss;
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += kHeadThreads) {
+    logits[((int64_t)0 * B + b) * n + j] = s_z[0][j];
+    logits[((int64_t)1 * B + b) * n + j] = s_z[1][j];
+    logits[((int64_t)2 * B + b) * n + j] = s_z[2][j];
+    g_out_all[(int64_t)b * n + j] = s_g[0][j];
+  }
+  // unimodal gradients back through fc_out and the gates: dh = (Wo^T g) * d(sig(h) h)/dh
+  for (int i = tid; i < D; i += kHeadThreads) {
+    float gx = 0.f, gy = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float w = Wo[(int64_t)j * D + i];
+      gx = fmaf(s_g[1][j], w, gx);
+      gy = fmaf(s_g[2][j], w, gy);
+    }
+    const float x = s_hx[i], y = s_hy[i];
+    const float sx = sigmoidf_(x), sy = sigmoidf_(y);
+    s_m[1][i] = gx * (sx + x * sx * (1.f - sx));
+    s_m[2][i] = gy * (sy + y * sy * (1.f - sy));
+  }
+  __syncthreads();
+  // ... and through fc_x / fc_y to the pooled features (column access: consecutive threads, consecutive i)
+  for (int i = tid; i < D; i += kHeadThreads) {
+    float ga = 0.f, gv = 0.f;
+    for (int k = 0; k < D; ++k) {
+      ga = fmaf(s_m[1][k], Wx[(int64_t)k * D + i], ga);
+      gv = fmaf(s_m[2][k], Wy[(int64_t)k * D + i], gv);
+    }
+    da[(int64_t)b * D + i] = ga;
+    dv[(int64_t)b * D + i] = gv;
+  }
+}
+
+// phase B: dWo = sum_b g_out[b] (x) m_out[b], dbo = sum_b g_out[b]  (Lf only), losses; fixed order over the batch
+__global__ void dgl_gated_param_kernel(const float* __restrict__ m_out, const float* __restrict__ g_out,
+                                       const float* __restrict__ loss_rows, float inv_batch, float* __restrict__ dWo,
+                                       float* __restrict__ dbo, float* __restrict__ losses, int B, int n) {
+  constexpr int D = kGatedD;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nW = (int64_t)n * D;
+  if (idx < nW) {
+    const int j = int(idx / D), i = int(idx - (int64_t)j * D);
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(g_out[(int64_t)b * n + j], m_out[(int64_t)b * D + i], acc);
+    dWo[idx] = acc;
+  } else if (idx < nW + n) {
+    const int j = int(idx - nW);
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += g_out[(int64_t)b * n + j];
+    dbo[j] = acc;
+  } else if (idx < nW + n + 3) {
+    const int h = int(idx - nW - n);
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += loss_rows[(int64_t)b * 3 + h];
+    losses[h] = acc * inv_batch;
+  }
 }
 
 }  // namespace gdl
@@ -324,5 +462,27 @@ extern "C" int gdl_gated_bwd(const float* hx, const float* hy, const float* dm_x
   GDL_REQUIRE(hx && hy && dm_x && dm_y && dhx && dhy && numel > 0, "gdl_gated_bwd: bad arguments");
   gated_bwd_kernel<<<(unsigned)ceil_div64(numel, 256), 256, 0, (cudaStream_t)s>>>(hx, hy, dm_x, dm_y, dhx, dhy, numel);
   GDL_CHECK_LAUNCH("gated_bwd_kernel");
+  return GDL_OK;
+}
+
+extern "C" int64_t gdl_gated_head_scratch_floats(int B, int n) { return (int64_t)B * 512 + (int64_t)B * n + (int64_t)B * 3; }
+
+extern "C" int gdl_dgl_head_gated(const float* a, const float* v, const float* Wx, const float* bx, const float* Wy,
+                                  const float* by, const float* Wo, const float* bo, const int64_t* labels, float alpha,
+                                  float inv_batch, float* logits, float* losses, float* da, float* dv, float* dWo,
+                                  float* dbo, float* scratch, int B, int D, int n, gdl_stream_t s) {
+  GDL_REQUIRE(a && v && Wx && bx && Wy && by && Wo && bo && labels && logits && losses && da && dv && dWo && dbo && scratch,
+              "gdl_dgl_head_gated: null pointer");
+  GDL_REQUIRE(B > 0 && D == kGatedD && n > 0 && n <= kHeadMaxN, "gdl_dgl_head_gated: bad shape (D must be 512, n <= 512)");
+  float* m_out = scratch;
+  float* g_out = m_out + (int64_t)B * D;
+  float* loss_rows = g_out + (int64_t)B * n;
+  dgl_gated_sample_kernel<<<B, kHeadThreads, 0, (cudaStream_t)s>>>(a, v, Wx, bx, Wy, by, Wo, bo, labels, alpha, inv_batch,
+                                                                   logits, da, dv, m_out, g_out, loss_rows, B, n);
+  GDL_CHECK_LAUNCH("dgl_gated_sample_kernel");
+  const int64_t total = (int64_t)n * D + n + 3;
+  dgl_gated_param_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)s>>>(m_out, g_out, loss_rows, inv_batch,
+                                                                                       dWo, dbo, losses, B, n);
+  GDL_CHECK_LAUNCH("dgl_gated_param_kernel");
   return GDL_OK;
 }

@@ -348,6 +348,18 @@ def dgl_head_linear(kind, a, v, Wx_ptr, Wy_ptr, ldw, bx, by, labels, alpha, inv_
           "gdl_dgl_head_linear")
 
 
+def gated_head_scratch_floats(B, n):
+    return int(_lib.load().gdl_gated_head_scratch_floats(B, n))
+
+
+@_op("dgl_head", 2)
+def dgl_head_gated(a, v, Wx, bx, Wy, by, Wo, bo, labels, alpha, inv_batch, logits, losses, da, dv, dWo, dbo, scratch,
+                   B, D, n):
+    check(_lib.load().gdl_dgl_head_gated(_ptr(a), _ptr(v), _ptr(Wx), _ptr(bx), _ptr(Wy), _ptr(by), _ptr(Wo), _ptr(bo),
+                                         _ptr(labels), alpha, inv_batch, _ptr(logits), _ptr(losses), _ptr(da), _ptr(dv),
+                                         _ptr(dWo), _ptr(dbo), _ptr(scratch), B, D, n, _stream()), "gdl_dgl_head_gated")
+
+
 @_op("softmax_ce", 2)
 def softmax_ce(logits, labels, loss_scale, grad_scale, loss_out, dlogits, scratch, B, n):
     check(_lib.load().gdl_softmax_ce(_ptr(logits), _ptr(labels), loss_scale, grad_scale, _ptr(loss_out),

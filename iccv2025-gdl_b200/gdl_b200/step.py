@@ -193,10 +193,7 @@ class DGLStep:
         fm, B, n, dev = self.model.fusion_module, self.B, self.n, self.device
         self.film = None
         if isinstance(fm, GatedFusion_DGL):
-            z = lambda *s: torch.empty(*s, device=dev)
-            self.g = dict(hx=z(B, 512), hy=z(B, 512), mo=z(B, 512), mx=z(B, 512), my=z(B, 512),
-                          dl=z(3, B, n), dmx=z(B, 512), dmy=z(B, 512), dhx=z(B, 512), dhy=z(B, 512),
-                          sc=z(B))
+            self.gated_scratch = torch.empty(ops.gated_head_scratch_floats(B, n) + 64, device=dev)
         elif isinstance(fm, FiLM_DGL):
             from .film import FilmHead
             self.film = FilmHead(fm, B, n, dev)
@@ -222,24 +219,13 @@ class DGLStep:
             self.film.run(self)
 
     def _head_gated(self, fm):
-        """reference fusion_modules.py:230-250 with the DGL routing: fc_out <- Lf; a, v <- alpha*La/Lv
-        through fc_out, the gates and fc_x / fc_y; fc_x / fc_y themselves get no gradient."""
-        g, B, n = self.g, self.B, self.n
+        """reference fusion_modules.py:230-250 with the DGL routing, one fused pass (csrc/head.cu
+        dgl_gated_sample/param_kernel): fc_out <- Lf; a, v <- alpha*La/Lv through fc_out, the gates and fc_x / fc_y;
+        fc_x / fc_y themselves get no gradient."""
         Wo, bo = fm.fc_out.weight, fm.fc_out.bias
-        ops.linear_fwd(self.a_feat, fm.fc_x.weight.data, fm.fc_x.bias.data, g["hx"], B, 512, 512)
-        ops.linear_fwd(self.v_feat, fm.fc_y.weight.data, fm.fc_y.bias.data, g["hy"], B, 512, 512)
-        ops.gated_fwd(g["hx"], g["hy"], g["mo"], g["mx"], g["my"])
-        for i, m in enumerate((g["mo"], g["mx"], g["my"])):
-            ops.linear_fwd(m, Wo.data, bo.data, self.logits[i], B, 512, n)
-            gs = self.inv_batch if i == 0 else self.alpha * self.inv_batch
-            ops.softmax_ce(self.logits[i], self.label_in, self.inv_batch, gs, self.losses[i:i + 1], g["dl"][i],
-                           g["sc"], B, n)
-        ops.linear_bwd(g["dl"][0], g["mo"], None, None, Wo.grad, bo.grad, B, 512, n)          # Lf -> fc_out
-        ops.linear_bwd(g["dl"][1], None, Wo.data, g["dmx"], None, None, B, 512, n)
-        ops.linear_bwd(g["dl"][2], None, Wo.data, g["dmy"], None, None, B, 512, n)
-        ops.gated_bwd(g["hx"], g["hy"], g["dmx"], g["dmy"], g["dhx"], g["dhy"])
-        ops.linear_bwd(g["dhx"], None, fm.fc_x.weight.data, self.da, None, None, B, 512, 512)
-        ops.linear_bwd(g["dhy"], None, fm.fc_y.weight.data, self.dv, None, None, B, 512, 512)
+        ops.dgl_head_gated(self.a_feat, self.v_feat, fm.fc_x.weight.data, fm.fc_x.bias.data, fm.fc_y.weight.data,
+                           fm.fc_y.bias.data, Wo.data, bo.data, self.label_in, self.alpha, self.inv_batch, self.logits,
+                           self.losses, self.da, self.dv, Wo.grad, bo.grad, self.gated_scratch, self.B, 512, self.n)
 
     # ------------------------------------------------------------------ the step
     @property

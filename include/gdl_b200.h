@@ -220,6 +220,17 @@ int gdl_dgl_head_linear(int kind, const float* a, const float* v, const float* W
                         float alpha, float inv_batch, float* logits, float* losses, float* da,
                         float* dv, float* dWx, float* dWy, int lddw, float* dbx, float* dby,
                         float* scratch, int B, int D, int n, gdl_stream_t s);
+/* Fused GatedFusion_DGL head (reference models/fusion_modules.py:230-250, main_dgl.py:102-122; x_gate=True):
+ * hx = fc_x(a), hy = fc_y(v); out = fc_out(sigmoid(hx.detach()) * hy.detach()), out_a = fc_out(sigmoid(hx) * hx),
+ * out_v = fc_out(sigmoid(hy) * hy); three CE; da = alpha*dLa/da, dv = alpha*dLv/dv through fc_out, the gates and
+ * fc_x / fc_y; dWo/dbo = dLf/d(fc_out); fc_x / fc_y receive no gradient (never trained in the reference).
+ * Weights [512][512] / [n][512] row-major fp32; logits f32 [3,B,n]; losses f32 [3]; D must be 512.
+ * scratch f32 [gdl_gated_head_scratch_floats(B, n)]. */
+int64_t gdl_gated_head_scratch_floats(int B, int n);
+int gdl_dgl_head_gated(const float* a, const float* v, const float* Wx, const float* bx, const float* Wy,
+                       const float* by, const float* Wo, const float* bo, const int64_t* labels, float alpha,
+                       float inv_batch, float* logits, float* losses, float* da, float* dv, float* dWo, float* dbo,
+                       float* scratch, int B, int D, int n, gdl_stream_t s);
 /* Softmax-CE on given logits [B,n] (reference main_dgl.py:71,102-104 nn.CrossEntropyLoss):
  * loss_out[0] = loss_scale * sum_b loss_b; dlogits = grad_scale*(softmax-onehot) (may be NULL).
  * scratch f32 [B].  Used by the gated/film heads, whose layers run through gdl_linear_*. */

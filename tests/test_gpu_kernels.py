@@ -604,6 +604,49 @@ def test_dgl_head_linear(kind, B, n):
         assert torch.allclose(gt.double(), p.grad, **tol)
 
 
+@pytest.mark.parametrize("B,n", [(8, 6), (37, 34), (16, 309)])
+def test_dgl_head_gated_fused(B, n):
+    """Fused GatedFusion_DGL head vs an fp64 autograd restatement of reference fusion_modules.py:230-250 +
+    main_dgl.py:102-122 (two backward passes, fusion-module gradients wiped in between): logits, losses, the
+    encoder-facing gradients da / dv, fc_out's gradients from Lf; fc_x / fc_y get none."""
+    ops = _ops()
+    D, alpha = 512, 4.0
+    g = torch.Generator(device="cuda").manual_seed(9)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    a = rnd(B, D).abs().double().requires_grad_(True)
+    v = rnd(B, D).abs().double().requires_grad_(True)
+    labels = torch.randint(0, n, (B,), device="cuda", generator=g)
+    Wx, Wy = (rnd(D, D) * 0.05).double().requires_grad_(True), (rnd(D, D) * 0.05).double().requires_grad_(True)
+    bx, by = (rnd(D) * 0.1).double().requires_grad_(True), (rnd(D) * 0.1).double().requires_grad_(True)
+    Wo, bo = (rnd(n, D) * 0.05).double().requires_grad_(True), (rnd(n) * 0.1).double().requires_grad_(True)
+    hx, hy = F.linear(a, Wx, bx), F.linear(v, Wy, by)
+    out = F.linear(torch.sigmoid(hx.detach()) * hy.detach(), Wo, bo)
+    xo = F.linear(torch.sigmoid(hx) * hx, Wo, bo)
+    yo = F.linear(torch.sigmoid(hy) * hy, Wo, bo)
+    Lf, La, Lv = (F.cross_entropy(t, labels) for t in (out, xo, yo))
+    params = [Wx, Wy, bx, by, Wo, bo]
+    ((La + Lv) * alpha).backward(retain_graph=True)
+    for p in params:
+        p.grad = None                      # the reference wipes every fusion-module gradient (main_dgl.py:114-119)
+    Lf.backward()
+    assert Wx.grad is None and Wy.grad is None  # Lf sees hx / hy detached: fc_x / fc_y are never trained
+
+    f32 = lambda t: t.detach().float().contiguous()
+    logits = torch.empty(3, B, n, device="cuda")
+    losses = torch.empty(3, device="cuda")
+    da, dv = torch.empty(B, D, device="cuda"), torch.empty(B, D, device="cuda")
+    dWo, dbo = torch.empty(n, D, device="cuda"), torch.empty(n, device="cuda")
+    scratch = torch.empty(ops.gated_head_scratch_floats(B, n), device="cuda")
+    ops.dgl_head_gated(f32(a), f32(v), f32(Wx), f32(bx), f32(Wy), f32(by), f32(Wo), f32(bo), labels, alpha, 1.0 / B,
+                       logits, losses, da, dv, dWo, dbo, scratch, B, D, n)
+    torch.cuda.synchronize()
+    tol = dict(atol=2e-5, rtol=2e-4)
+    for got, ref in ((logits[0], out), (logits[1], xo), (logits[2], yo), (da, a.grad), (dv, v.grad), (dWo, Wo.grad),
+                     (dbo, bo.grad)):
+        assert torch.allclose(got.double(), ref.detach(), **tol)
+    assert torch.allclose(losses.double(), torch.stack([Lf, La, Lv]).detach(), **tol)
+
+
 def test_softmax_ce_and_gated():
     ops = _ops()
     B, n = 19, 34
