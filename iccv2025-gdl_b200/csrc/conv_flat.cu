@@ -30,6 +30,7 @@ using namespace tc05;
 constexpr int kFlatThreads = 192;
 constexpr int kFlatMaxTaps = 9;
 constexpr int kFlatSmemBudget = 227 * 1024 - 2048;
+constexpr int kFlatSmemFloor = 200 * 1024;
 
 struct FlatTap {
   int shift;  // row shift on the flat grid (may be negative)
@@ -183,8 +184,8 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
     // ------------------------------ MMA issuer ------------------------------
     // The single issuing thread is instruction-latency bound (an N=64 MMA retires in 32 clocks), so every
     // operand must live in uniform registers.  The TMEM base read from shared memory would not (ptxas emits
-    // an ELECT/R2UR waterfall per MMA), but with one CTA per SM (>= 116 KB of shared memory, enforced at
-    // launch) the allocation always starts at column 0: check it once and use the constant.
+    // an ELECT/R2UR waterfall per MMA), but the kernel is the only TMEM user of its SM (kFlatSmemFloor, enforced at
+    // launch: see launch_flat), so the allocation always starts at column 0: check it once and use the constant.
     if (tmem_base != 0) {
       printf("gdl: conv_flat expects TMEM base 0, got %u\n", tmem_base);
       __trap();
@@ -684,7 +685,12 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   p.ntiles = p.Cd / BN;
   p.items_total = p.nclass * p.ntiles * p.mtiles;
   int total = ws * p.win_stage_bytes + fixed + 1024;
-  if (total < 116 * 1024) total = 116 * 1024;  // one CTA per SM: the kernel relies on TMEM base 0
+  // TMEM base 0 (see the MMA issuer): the kernel must be the only TMEM user on its SM.  Variants that allocate all
+  // 512 columns get that from tcgen05.alloc itself (it blocks until the columns are free); the others take at
+  // least kFlatSmemFloor of shared memory, which leaves < 28 KB on the SM — less than any other TMEM-using kernel of
+  // this library needs (stem_fwd 104 KB, stem_wgrad 95 KB, the flat / generic GEMM kernels >= 100 KB), so none can be
+  // co-resident even when the audio and visual encoders run on two streams.
+  if (total < kFlatSmemFloor) total = kFlatSmemFloor;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, false, RES>,
@@ -726,7 +732,7 @@ static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   p.ntiles = p.Cd / BN;
   p.items_total = p.nclass * p.ntiles * p.mtiles;
   int total = ws * p.win_stage_bytes + fixed + 1024;
-  if (total < 116 * 1024) total = 116 * 1024;  // one CTA per SM (TMEM base 0)
+  if (total < kFlatSmemFloor) total = kFlatSmemFloor;  // sole TMEM user of its SM (see launch_flat)
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
