@@ -760,7 +760,7 @@ static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   return 1;
 }
 
-int g_fused_stats_min_k = 1 << 30;
+thread_local int g_fused_stats_min_k = 1 << 30;  // per calling thread, like gdl_set_sweep
 
 static int env_int3(const char* name, int dflt) {
   const char* v = getenv(name);

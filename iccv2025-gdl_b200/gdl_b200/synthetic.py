@@ -130,11 +130,13 @@ class SyntheticCramedDevice(SyntheticCramed):
     SyntheticCramed's torchvision transform — and the decoded frames live in one uint8 store (frame t of item i
     at index i * fps + t) that the caller uploads once (`attach_pipeline`)."""
 
-    device_pipeline = None  # set by attach_pipeline; read by gdl_b200.train.train_epoch / valid
+    device_pipeline = None        # set by attach_pipeline; read by gdl_b200.train.train_epoch / valid
+    device_audio_pipeline = None  # likewise: datapipe.AudioPipeline (spectrograms computed on the device)
 
-    def __getstate__(self):  # DataLoader workers never see the CUDA-side pipeline
+    def __getstate__(self):  # DataLoader workers never see the CUDA-side pipelines
         d = dict(self.__dict__)
         d.pop("device_pipeline", None)
+        d.pop("device_audio_pipeline", None)
         return d
 
     def frame_store(self):
@@ -146,18 +148,28 @@ class SyntheticCramedDevice(SyntheticCramed):
                 out[idx * fps + i] = np.asarray(synth_image("%s/%d" % (self.key(idx), i), self.frame_size))
         return torch.from_numpy(out)
 
-    def attach_pipeline(self, device):
-        from .datapipe import DeviceFrameStore, VisualPipeline
+    def wave_store(self):
+        """What librosa.load(path, sr=22050) yields for every clip (clip idx at row idx)."""
+        return [synth_wave(self.key(idx), 2.5, 22050)[0] for idx in range(self.len)]
+
+    def attach_pipeline(self, device, audio=True):
+        from .datapipe import AudioPipeline, DeviceFrameStore, DeviceWaveStore, VisualPipeline
         self.device_pipeline = VisualPipeline(DeviceFrameStore(self.frame_store(), device), self.args.fps)
+        self.device_audio = bool(audio)
+        if audio:  # CramedDataset.py:60-66: 3 s at 22 050 Hz, n_fft 512, hop 353
+            self.device_audio_pipeline = AudioPipeline(DeviceWaveStore(self.wave_store(), device), 22050 * 3, 512, 353)
         return self.device_pipeline
 
     def __getitem__(self, idx):
         from .datapipe import draw_frame_params
-        samples, rate = synth_wave(self.key(idx), 2.5, 22050)
-        resamples = np.tile(samples, 3)[:22050 * 3]
-        resamples[resamples > 1.] = 1.
-        resamples[resamples < -1.] = -1.
-        spectrogram = np.log(np.abs(stft(resamples, n_fft=512, hop_length=353)) + 1e-7)
+        if getattr(self, "device_audio", False):
+            spectrogram = torch.tensor([idx, 0], dtype=torch.int32)  # {clip, start}: np.tile(samples, 3)[:L] starts at 0
+        else:
+            samples, rate = synth_wave(self.key(idx), 2.5, 22050)
+            resamples = np.tile(samples, 3)[:22050 * 3]
+            resamples[resamples > 1.] = 1.
+            resamples[resamples < -1.] = -1.
+            spectrogram = np.log(np.abs(stft(resamples, n_fft=512, hop_length=353)) + 1e-7)
         fps = self.args.fps
         select_index = np.random.choice(self.frames_in_dir, size=fps, replace=False)  # drawn, unused (:92-93)
         select_index.sort()

@@ -24,18 +24,25 @@ def _pipeline_of(dataloader):
     return getattr(getattr(dataloader, "dataset", None), "device_pipeline", None)
 
 
-def _get_step(args, model, optimizer, spec, image, pipeline=None):
+def _audio_pipeline_of(dataloader):
+    """The dataset's device-side audio pipeline (datapipe.AudioPipeline): items then carry {clip, start} instead of
+    the spectrogram."""
+    return getattr(getattr(dataloader, "dataset", None), "device_audio_pipeline", None)
+
+
+def _get_step(args, model, optimizer, spec, image, pipeline=None, audio_pipeline=None):
     inner = getattr(model, "module", model)
     B = spec.shape[0]
     thw = (pipeline.T, pipeline.S, pipeline.S) if pipeline is not None else tuple(image.shape[2:])
-    key = (B, tuple(spec.shape[1:]), thw)
+    spec_hw = (audio_pipeline.F, audio_pipeline.frames) if audio_pipeline is not None else tuple(spec.shape[1:])
+    key = (B, spec_hw, thw)
     st = getattr(inner, "_gdl_step", None)
     if st is not None and getattr(inner, "_gdl_step_key", None) == key:
         return st
     g = optimizer.param_groups[0]
     world = torch.distributed.get_world_size() if torch.distributed.is_available() and \
         torch.distributed.is_initialized() else 1
-    st = DGLStep(inner, B, tuple(spec.shape[1:]), thw, alpha=args.alpha, lr=g['lr'],
+    st = DGLStep(inner, B, spec_hw, thw, alpha=args.alpha, lr=g['lr'],
                  momentum=g.get('momentum', 0.9), weight_decay=g.get('weight_decay', 1e-4), max_norm=40.0,
                  world_size=world, process_group=torch.distributed.group.WORLD if world > 1 else None)
     adopt_momentum(st.arena, optimizer, st)
@@ -90,18 +97,18 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler, wr
         del pending[:]
 
     # one batch of look-ahead: the H2D copy of batch k+1 (copy stream) overlaps the kernels of step k
-    pipe = _pipeline_of(dataloader)
+    pipe, apipe = _pipeline_of(dataloader), _audio_pipeline_of(dataloader)
 
     def prefetch(step, batch):
         if pipe is None:
             step.prefetch(*batch)
-        else:  # batch[1] is the int32 [B, T, 6] table of host-drawn crop boxes
-            step.prefetch(batch[0], batch[1].reshape(-1, 6), batch[2], pipeline=pipe)
+        else:  # batch[1] is the int32 [B, T, 6] table of host-drawn crop boxes, batch[0] {clip, start} with apipe
+            step.prefetch(batch[0], batch[1].reshape(-1, 6), batch[2], pipeline=pipe, audio_pipeline=apipe)
     it = iter(dataloader)
     nxt = next(it, None)
     st = None
     if nxt is not None:
-        st = _get_step(args, model, optimizer, nxt[0], nxt[1], pipe)
+        st = _get_step(args, model, optimizer, nxt[0], nxt[1], pipe, apipe)
         prefetch(st, nxt)
     step_i = -1
     while nxt is not None:
@@ -112,7 +119,7 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler, wr
         stats = st.step(lr=optimizer.param_groups[0]['lr'])
         nxt = next(it, None)
         if nxt is not None:
-            st2 = _get_step(args, model, optimizer, nxt[0], nxt[1], pipe)
+            st2 = _get_step(args, model, optimizer, nxt[0], nxt[1], pipe, apipe)
             if st2 is not st:  # geometry changed (last partial batch without drop_last): new engine
                 st = st2
             prefetch(st, nxt)
@@ -142,11 +149,13 @@ def valid(args, model, device, dataloader):
     with torch.no_grad():
         model.eval()
         print(inner.args.drop)
-        pipe = _pipeline_of(dataloader)
+        pipe, apipe = _pipeline_of(dataloader), _audio_pipeline_of(dataloader)
         for spec, image, label in dataloader:
             spec, image, label = spec.to(device), image.to(device), label.to(device)
             if pipe is not None:
                 image = pipe(image.reshape(-1, 6))
+            if apipe is not None:
+                spec = apipe(spec)
             out, out_a, out_v = model(spec.unsqueeze(1).float(), image.float())
             for i, o in enumerate((out, out_a, out_v)):  # softmax is monotone: arg-max of the logits
                 correct[i] += (o.argmax(1) == label).sum()

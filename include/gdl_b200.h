@@ -12,7 +12,14 @@
  *   - all kernels are sm_100a only (tcgen05/TMEM for the convolutions); there is no
  *     CPU, cuDNN, cuBLAS or Triton fallback;
  *   - activations are NHWC bf16; parameters/gradients/optimizer state are fp32;
- *     reductions are deterministic (fixed-order partials, no float atomics).
+ *     reductions are deterministic (fixed-order partials, no float atomics);
+ *   - threading / context model: the library keeps NO per-call or per-stream state, so there is no gdl_ctx object —
+ *     every entry point takes all of its operands, workspaces and the stream as arguments and is re-entrant.  The
+ *     only shared state is (a) the tensor-map cache (keyed by pointer + geometry, mutex-guarded) and (b) the
+ *     per-kernel cudaFuncSetAttribute calls made once per process, which is why ONE process drives ONE device
+ *     (torch.distributed's process-per-GPU model; gdl_init(device) checks the device).  The two scheduling hints
+ *     (gdl_set_sweep, gdl_set_fused_stats_min_k) are thread-local: host threads that enqueue on different streams do
+ *     not see each other's settings.
  */
 #ifndef GDL_B200_H_
 #define GDL_B200_H_
@@ -89,7 +96,7 @@ int gdl_conv_fwd_bias_act(const gdl_conv_desc* d, const void* x, const void* w_p
 int gdl_conv_fwd_stats(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
                        float* bn_partial, int* bn_partial_rows, gdl_stream_t s);
 /* Fused statistics are used for convolutions with R*S*Ci >= k (default: never — on the bench geometry the
- * epilogue cost equals what the separate kernel costs); k < 0 restores the default.  Returns the old value. */
+ * epilogue cost equals what the separate kernel costs); k < 0 restores the default.  Thread-local.  Returns the old value. */
 int gdl_set_fused_stats_min_k(int k);
 /* Scheduling hint for the calling thread (no reference counterpart: the reference's kernels are cuDNN's):
  * reverse != 0 makes the following gdl_conv_fwd / gdl_conv_dgrad (flat kernels), gdl_bn_stats, gdl_bn_apply,

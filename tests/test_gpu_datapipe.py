@@ -227,3 +227,23 @@ def test_step_fed_by_the_device_audio_pipeline():
         res.append(step.read_stats())
     for a, b in zip(res[0][:4], res[1][:4]):
         assert abs(a - b) <= 1e-3 * abs(a), (res[0], res[1])
+
+
+def test_device_dataset_delivers_audio_params_and_matches_the_host_dataset():
+    """SyntheticCramedDevice with the audio pipeline attached: items carry {clip, start}; the spectrograms computed
+    on the device equal the ones SyntheticCramed (the reference's sample contract, CramedDataset.py:57-110) computes
+    on the host, and train_epoch / valid consume them through DGLStep.prefetch(audio_pipeline=...)."""
+    import argparse
+    from gdl_b200.synthetic import SyntheticCramed, SyntheticCramedDevice
+    args = argparse.Namespace(dataset="CREMAD", fps=2, use_video_frames=3)
+    host = SyntheticCramed(args, "test", 4)
+    dev = SyntheticCramedDevice(args, "test", 4)
+    dev.attach_pipeline(torch.device("cuda"))
+    assert dev.device_audio_pipeline is not None
+    params = torch.stack([dev[i][0] for i in range(4)]).cuda()
+    assert params.dtype == torch.int32 and tuple(params.shape) == (4, 2)
+    spec = dev.device_audio_pipeline(params).cpu()
+    assert tuple(spec.shape) == (4, 257, 188)
+    for i in range(4):
+        ref = torch.as_tensor(host[i][0])
+        assert (spec[i] - ref).abs().max().item() <= 2e-4   # the host stand-in multiplies the window in float32
