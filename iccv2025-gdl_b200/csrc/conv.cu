@@ -470,6 +470,42 @@ __global__ void pack_weights_multi_kernel(const gdl_pack_entry* __restrict__ tab
   }
 }
 
+// Tiled variant for the block convolutions (Ci % 64 == 0, Co % 32 == 0, no channel padding): the element-wise kernel
+// above reads the OIHW master with a 36-byte stride per lane and scatters the transposed shadow in 2-byte pieces
+// (0.15 ms per encoder for 11 M weights).  Here one CTA moves a [32 co][64 ci][R*S] tile through shared memory:
+// coalesced fp32 reads (64*R*S contiguous floats per co), 128-byte runs into wp[co][tap][ci], 64-byte runs into
+// wT[ci][tap][co].  blockIdx.y = table entry, blockIdx.x = tile (CTAs beyond the entry's tile count exit).
+__global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const gdl_pack_entry* __restrict__ tab) {
+  extern __shared__ bf16 s_tile[];  // [32 co][RS][64 ci + 2 pad] (row stride 33 words: the transposed read is conflict-free)
+  constexpr int LD = 66;
+  const gdl_pack_entry e = tab[blockIdx.y];
+  const int RS = e.R * e.S;
+  const int ci_tiles = e.Ci >> 6, tiles = (e.Co >> 5) * ci_tiles;
+  if ((int)blockIdx.x >= tiles) return;
+  const int co0 = (blockIdx.x / ci_tiles) << 5, ci0 = (blockIdx.x % ci_tiles) << 6;
+  const int run = 64 * RS;  // contiguous floats per output channel in the OIHW master
+  for (int i = threadIdx.x; i < 32 * run; i += 256) {
+    const int co = i / run, r = i - co * run;
+    const int ci = r / RS, tap = r - ci * RS;
+    float v = e.w[((size_t)(co0 + co) * e.Ci + ci0) * RS + r];
+    if (e.scale != nullptr) v *= e.scale[co0 + co];
+    s_tile[(co * RS + tap) * LD + ci] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  bf16* wp = reinterpret_cast<bf16*>(e.wp);
+  for (int i = threadIdx.x; i < 32 * run; i += 256) {  // wp[co][tap*Ci + ci]: 64 consecutive ci per (co, tap)
+    const int ci = i & 63, ct = i >> 6, co = ct / RS, tap = ct - co * RS;
+    wp[(size_t)(co0 + co) * e.Kp + (size_t)tap * e.Ci + ci0 + ci] = s_tile[ct * LD + ci];
+  }
+  if (e.wT != nullptr) {
+    bf16* wT = reinterpret_cast<bf16*>(e.wT);
+    for (int i = threadIdx.x; i < 32 * run; i += 256) {  // wT[ci][tap*Co + co]: 32 consecutive co per (ci, tap)
+      const int co = i & 31, ct = i >> 5, tap = ct % RS, ci = ct / RS;
+      wT[(size_t)(ci0 + ci) * (RS * e.Co) + (size_t)tap * e.Co + co0 + co] = s_tile[(co * RS + tap) * LD + ci];
+    }
+  }
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                     int splits, int Kp, int Cd, int Ci, int ci_real, int R, int S) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (k, co), co fastest
@@ -761,6 +797,15 @@ static int conv_fwd_impl(const gdl_conv_desc* d, const void* x, const void* w_pa
   p.K = packed_k(d);
   p.KB = p.K / 64;
   return run_igemm(p, (cudaStream_t)s);
+}
+
+extern "C" int gdl_conv_pack_weights_tiled(const gdl_pack_entry* table_dev, int n, int max_tiles, int max_rs,
+                                           gdl_stream_t s) {
+  GDL_REQUIRE(table_dev && n > 0 && max_tiles > 0 && max_rs > 0 && max_rs <= 9, "gdl_conv_pack_weights_tiled: bad arguments");
+  const size_t smem = (size_t)32 * max_rs * 66 * sizeof(bf16);
+  pack_weights_tiled_kernel<<<dim3(max_tiles, n), 256, smem, (cudaStream_t)s>>>(table_dev);
+  GDL_CHECK_LAUNCH("pack_weights_tiled_kernel");
+  return GDL_OK;
 }
 
 extern "C" int gdl_conv_pack_weights_multi(const gdl_pack_entry* table_dev, int n, int64_t total, gdl_stream_t s) {

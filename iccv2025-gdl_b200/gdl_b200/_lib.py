@@ -57,6 +57,7 @@ SIGNATURES = {
     "gdl_bn_partial_floats": (_l, [_l, _i]),
     "gdl_bn_stats": (_i, [_p, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "gdl_conv_pack_weights_multi": (_i, [_p, _i, _l, _p]),
+    "gdl_conv_pack_weights_tiled": (_i, [_p, _i, _i, _i, _p]),
     "gdl_set_fused_stats_min_k": (_i, [_i]),
     "gdl_set_sweep": (_i, [_i]),
     "gdl_conv_fwd_stats": (_i, [_p, _p, _p, _p, _p, _p, _p]),

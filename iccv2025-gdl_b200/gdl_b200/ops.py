@@ -114,12 +114,23 @@ def make_pack_table(entries, device):
         e.Co, e.Ci, e.ci_real, e.R, e.S, e.Kp, e.start = Co, Ci, ci_real, R, S, Kp, start
         start += Co * Kp
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-    return host.to(device), len(entries), start
+    # tiled kernel (coalesced through shared memory) when every entry is an unpadded block convolution
+    tiled = all(e[4] == e[5] and e[4] % 64 == 0 and e[3] % 32 == 0 and e[8] == e[6] * e[7] * e[4] and e[6] * e[7] <= 9
+                for e in entries)
+    info = None
+    if tiled:
+        info = (max((e[3] // 32) * (e[4] // 64) for e in entries), max(e[6] * e[7] for e in entries))
+    return host.to(device), len(entries), start, info
 
 
 @_op("pack_weights", 1)
-def conv_pack_weights_multi(table, n, total):
-    check(_lib.load().gdl_conv_pack_weights_multi(_ptr(table), n, total, _stream()), "gdl_conv_pack_weights_multi")
+def conv_pack_weights_multi(table, n, total, tiled=None):
+    """tiled = (max_tiles, max_rs) from make_pack_table selects the shared-memory tiled kernel."""
+    if tiled is not None:
+        check(_lib.load().gdl_conv_pack_weights_tiled(_ptr(table), n, tiled[0], tiled[1], _stream()),
+              "gdl_conv_pack_weights_tiled")
+    else:
+        check(_lib.load().gdl_conv_pack_weights_multi(_ptr(table), n, total, _stream()), "gdl_conv_pack_weights_multi")
 
 
 @_op("conv_fwd", 1, lambda d, x, w, y, ci_real=None: ("flops", conv_flops(d, ci_real), _dstr(d)))

@@ -79,6 +79,10 @@ typedef struct {
                          BatchNorm running-statistics scale gamma/sqrt(var+eps) folded into the weights) */
 } gdl_pack_entry;
 int gdl_conv_pack_weights_multi(const gdl_pack_entry* table_dev, int n, int64_t total, gdl_stream_t s);
+/* The same through shared-memory tiles (coalesced reads and writes), for tables whose entries ALL have
+ * Ci == ci_real, Ci % 64 == 0, Co % 32 == 0 and Kp == R*S*Ci (the 19 block convolutions of a ResNet-18 encoder):
+ * max_tiles = max over entries of (Co/32)*(Ci/64), max_rs = max R*S (<= 9). */
+int gdl_conv_pack_weights_tiled(const gdl_pack_entry* table_dev, int n, int max_tiles, int max_rs, gdl_stream_t s);
 /* y[N,Ho,Wo,Co] = conv(x[N,Hi,Wi,Ci], w).  Implicit GEMM, tcgen05 + TMEM accumulators. */
 int gdl_conv_fwd(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
                  gdl_stream_t s);
