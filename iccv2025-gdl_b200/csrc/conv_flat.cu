@@ -71,6 +71,161 @@ __device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
   return (a - q * b < 0) ? q - 1 : q;
 }
 
+// ------------------------------------------------------------------------------------------
+// BatchNorm statistics in the epilogue (reference backbone.py:45,48 train-mode BN over the conv output).
+// An epilogue thread owns one pixel row of the tile, the statistics are per channel column: each warp transposes
+// its 32 x 32 block of bf16-ROUNDED outputs (what BatchNorm will read; zero for pad rows) through a private
+// 2.6 KB shared-memory scratch — lane l writes its row as four 16-byte vectors, then lane (hh, wd) reads the
+// packed channel pair wd of rows hh*16 .. hh*16+15 — and accumulates sum / sum of squares in registers over all
+// the CTA's tiles of one channel tile.  ~120 instructions per 32-column chunk (the shuffle butterfly this replaces
+// needed ~350) and 4 KB of shared-memory traffic per chunk.  Row pitch 20 words, upper 16 rows displaced by 16
+// words: row writes (8 lanes x 16 B per wavefront) and column reads (2 x 16 lanes x 4 B) are bank-conflict free.
+// The order of every addition is fixed, so the statistics are deterministic.
+constexpr int kStatRowBytes = 80;
+constexpr int kStatWarpBytes = 32 * kStatRowBytes + 64;
+constexpr int kStatScratchBytes = 4 * kStatWarpBytes;
+
+template <int BN>
+struct StatAcc {
+  float s[BN / 32][2], q[BN / 32][2];
+  int nt;
+};
+
+__device__ __forceinline__ void stat_chunk(uint32_t scratch, int lane, const uint4 (&o)[4], float (&s)[2],
+                                           float (&q)[2]) {
+  __syncwarp();  // the previous chunk's column reads are complete
+  const uint32_t wrow = scratch + lane * kStatRowBytes + (lane >> 4) * 64;
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + v * 16), "r"(o[v].x), "r"(o[v].y), "r"(o[v].z),
+                 "r"(o[v].w)
+                 : "memory");
+  __syncwarp();
+  const uint32_t rcol = scratch + (lane >> 4) * (16 * kStatRowBytes + 64) + (lane & 15) * 4;
+#pragma unroll
+  for (int rr = 0; rr < 16; ++rr) {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rcol + rr * kStatRowBytes) : "memory");
+    const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+    s[0] += lo;
+    q[0] = fmaf(lo, lo, q[0]);
+    s[1] += hi;
+    q[1] = fmaf(hi, hi, q[1]);
+  }
+}
+
+// Adds the warp's register sums of channel tile sa.nt into its private partial row [2][Cd] and clears them.
+template <int BN>
+__device__ __forceinline__ void stat_flush(StatAcc<BN>& sa, float* slot, int Cd, int lane) {
+  if (slot == nullptr || sa.nt < 0) return;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < BN / 32; ++c)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float s = sa.s[c][e] + __shfl_xor_sync(0xffffffffu, sa.s[c][e], 16);
+      const float q = sa.q[c][e] + __shfl_xor_sync(0xffffffffu, sa.q[c][e], 16);
+      if (lane < 16) {
+        const int ch = sa.nt * BN + c * 32 + 2 * lane + e;
+        slot[ch] += s;
+        slot[Cd + ch] += q;
+      }
+      sa.s[c][e] = sa.q[c][e] = 0.f;
+    }
+}
+
+// One item of the epilogue warps (shared by the single-CTA and the CTA-pair kernel): output addresses of this
+// thread's MT pixel rows, residual prefetch, wait for the accumulator, TMEM -> registers -> bf16 NHWC.
+// The residual rows (dgrad: gradient of the skip connection) are fetched into registers BEFORE the wait
+// on the accumulator, one tile ahead, so their DRAM latency hides behind the MMAs instead of stalling the
+// TMEM drain (measured: 0.45 -> 0.25 ms on the 56x56 C64 dgrads).
+template <int BN, int MT, bool STATS>
+__device__ __forceinline__ void flat_epilogue_item(const FlatParams& p, int cls, int n0, int q0, int tid, int lane,
+                                                   uint64_t* full_bar, uint32_t full_parity, uint32_t trow,
+                                                   uint32_t scratch, bool do_stats, StatAcc<BN>& sa) {
+  constexpr int NV = BN / 8;  // 16-byte vectors per output row
+  bf16* outp[MT];
+  const bf16* addp[MT];
+  bool validj[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j) {
+    const int q = q0 + j * 128 + tid;
+    const int n = q / p.IS;
+    const int r2 = q - n * p.IS;
+    const int h = r2 / p.P, w = r2 - h * p.P;
+    const int hd = h * p.dscale + p.ph[cls], wd = w * p.dscale + p.pw[cls];
+    validj[j] = n < p.N && h < p.Hs && w < p.Ws && hd < p.Hd && wd < p.Wd;
+    const size_t off = ((size_t)((size_t)n * p.Hd + hd) * p.Wd + wd) * p.Cd + n0;
+    outp[j] = p.dst + off;
+    addp[j] = nullptr;
+    if (validj[j] && p.add_mode == 1)
+      addp[j] = p.add_src + off;
+    else if (validj[j] && p.add_mode == 2 && (p.ph[cls] | p.pw[cls]) == 0)
+      addp[j] = p.add_src + ((size_t)((size_t)n * p.Hs + h) * p.Ws + w) * p.Cd + n0;
+  }
+  U32B res[NV / 2];
+  const U32B zero32 = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+  if (p.add_mode != 0) {
+#pragma unroll
+    for (int v = 0; v < NV / 2; ++v) res[v] = addp[0] ? ld_stream32(addp[0] + v * 16) : zero32;
+  }
+  mbar_wait(full_bar, full_parity);
+  tc_fence_after();
+#pragma unroll
+  for (int j = 0; j < MT; ++j) {
+    U32B nres[NV / 2];
+    if (p.add_mode != 0 && j + 1 < MT) {  // next tile's residual row while this one drains
+#pragma unroll
+      for (int v = 0; v < NV / 2; ++v) nres[v] = addp[j + 1] ? ld_stream32(addp[j + 1] + v * 16) : zero32;
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(trow + j * BN + c0, r);
+      tmem_ld_wait();
+      uint4 o[4];
+      if (validj[j] || STATS) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[g * 8 + i]);
+          if (p.add_mode != 0) {
+            float a[8];
+            const U32B& rv = res[(c0 / 8 + g) / 2];
+            unpack8((g & 1) == 0 ? rv.lo : rv.hi, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += a[i];
+          }
+          if (p.bias != nullptr) {  // eval mode: folded BatchNorm shift (same 8 floats for every lane: L1 broadcast)
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g * 8 + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          o[g] = pack8(f);
+        }
+      }
+      if (validj[j]) {  // 16 channels = one 32-byte store (a full sector per lane)
+        st_global32(outp[j] + c0, o[0], o[1]);
+        st_global32(outp[j] + c0 + 16, o[2], o[3]);
+      }
+      if (STATS && do_stats) {
+        if (!validj[j]) o[0] = o[1] = o[2] = o[3] = make_uint4(0, 0, 0, 0);
+        stat_chunk(scratch, lane, o, sa.s[c0 / 32], sa.q[c0 / 32]);
+      }
+    }
+    if (p.add_mode != 0 && j + 1 < MT) {
+#pragma unroll
+      for (int v = 0; v < NV / 2; ++v) res[v] = nres[v];
+    }
+  }
+}
+
 // RES: the whole packed weight matrix of the layer (taps x slabs tiles of BN x 64) is loaded ONCE per CTA and stays in
 // shared memory (64 -> 64 channel 3x3 layers: 9 tiles = 72 KB), instead of being streamed from L2 for every 256-pixel
 // item: the weight ring is 2/3 of the L2 -> SM traffic of those layers.  One class, one channel tile.
@@ -245,34 +400,16 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
     }
   } else if (warp < 4) {
     // ------------------------------ epilogue ------------------------------
-    // The residual rows (dgrad: gradient of the skip connection) are fetched into registers BEFORE the wait
-    // on the accumulator, one tile ahead, so their DRAM latency hides behind the MMAs instead of stalling the
-    // TMEM drain (measured: 0.45 -> 0.25 ms on the 56x56 C64 dgrads).
-    constexpr int NV = BN / 8;  // 16-byte vectors per output row
-    // Optional BatchNorm statistics of the output (reference backbone.py:45,48 train-mode BN): per 32-column
-    // chunk the 32 rows of a warp are reduced with a transposing shuffle butterfly (31 shuffles per statistic)
-    // so that lane l ends up with the column sum of channel c0+l; the per-warp sums accumulate in registers
-    // over the CTA's tiles and are flushed to the warp's private slot when the channel tile changes.
-    constexpr int NCH = BN / 32;
     const int lane = tid & 31;
-    float st_sum[NCH], st_sq[NCH];
+    StatAcc<BN> sa;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) st_sum[c] = st_sq[c] = 0.f;
+    for (int c = 0; c < BN / 32; ++c) sa.s[c][0] = sa.s[c][1] = sa.q[c][0] = sa.q[c][1] = 0.f;
+    sa.nt = -1;
+    // one partial row [2][Cd] per epilogue warp of every CTA
     float* st_slot = (STATS && p.stats) ? p.stats + (size_t)(blockIdx.x * 4 + warp) * 2 * p.Cd : nullptr;
     if (st_slot != nullptr)
       for (int c = lane; c < 2 * p.Cd; c += 32) st_slot[c] = 0.f;
-    int st_nt = -1;
-    auto st_flush = [&]() {
-      if (st_slot == nullptr || st_nt < 0) return;
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int ch = st_nt * BN + c * 32 + lane;
-        st_slot[ch] += st_sum[c];
-        st_slot[p.Cd + ch] += st_sq[c];
-        st_sum[c] = st_sq[c] = 0.f;
-      }
-    };
+    const uint32_t scratch = smem_base + bar_off + 512 + warp * kStatWarpBytes;
     int it = 0;
     for (int item = item_first; item < items_total; item += item_stride, ++it) {
       const int cls = item / per_class;
@@ -280,116 +417,18 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int nt = rem / mt_count;
       const int mt_i = rem - nt * mt_count;
       const int q0 = (p.rev ? mt_max - 1 - mt_i : mt_i) * TM;
-      const int n0 = nt * BN;
       const int acc = it & 1;
-      if (STATS && nt != st_nt) {
-        st_flush();
-        st_nt = nt;
+      if (STATS && nt != sa.nt) {
+        stat_flush<BN>(sa, st_slot, p.Cd, lane);
+        sa.nt = nt;
       }
-      bf16* outp[MT];
-      const bf16* addp[MT];
-      bool validj[MT];
-#pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        const int q = q0 + j * 128 + tid;
-        const int n = q / p.IS;
-        const int r2 = q - n * p.IS;
-        const int h = r2 / p.P, w = r2 - h * p.P;
-        const int hd = h * p.dscale + p.ph[cls], wd = w * p.dscale + p.pw[cls];
-        validj[j] = n < p.N && h < p.Hs && w < p.Ws && hd < p.Hd && wd < p.Wd;
-        const size_t off = ((size_t)((size_t)n * p.Hd + hd) * p.Wd + wd) * p.Cd + n0;
-        outp[j] = p.dst + off;
-        addp[j] = nullptr;
-        if (validj[j] && p.add_mode == 1)
-          addp[j] = p.add_src + off;
-        else if (validj[j] && p.add_mode == 2 && (p.ph[cls] | p.pw[cls]) == 0)
-          addp[j] = p.add_src + ((size_t)((size_t)n * p.Hs + h) * p.Ws + w) * p.Cd + n0;
-      }
-      U32B res[NV / 2];
-      const U32B zero32 = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      if (p.add_mode != 0) {
-#pragma unroll
-        for (int v = 0; v < NV / 2; ++v) res[v] = addp[0] ? ld_stream32(addp[0] + v * 16) : zero32;
-      }
-      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-      tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16) + acc * (MT * BN);
-#pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        U32B nres[NV / 2];
-        if (p.add_mode != 0 && j + 1 < MT) {  // next tile's residual row while this one drains
-#pragma unroll
-          for (int v = 0; v < NV / 2; ++v) nres[v] = addp[j + 1] ? ld_stream32(addp[j + 1] + v * 16) : zero32;
-        }
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(trow + j * BN + c0, r);
-          tmem_ld_wait();
-          if (validj[j]) {
-#pragma unroll
-            for (int g = 0; g < 4; g += 2) {  // 16 channels = one 32-byte store (a full sector per lane)
-              uint4 o[2];
-#pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[(g + h2) * 8 + i]);
-                if (p.add_mode != 0) {
-                  float a[8];
-                  const U32B& rv = res[(c0 / 8 + g) / 2];
-                  unpack8(h2 == 0 ? rv.lo : rv.hi, a);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] += a[i];
-                }
-                if (p.bias != nullptr) {  // eval mode: folded BatchNorm shift (same 8 floats for every lane: L1 broadcast)
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (g + h2) * 8));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (g + h2) * 8 + 4));
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (p.relu) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-                }
-                o[h2] = pack8(f);
-              }
-              st_global32(outp[j] + c0 + g * 8, o[0], o[1]);
-            }
-          }
-          if (STATS && st_slot != nullptr) {
-            // statistics of what BatchNorm will read: the bf16-rounded outputs (zero for pad rows)
-            float xs[32], xq[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float v = validj[j] ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[i]))) : 0.f;
-              xs[i] = v;
-              xq[i] = v * v;
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-              const bool upper = (lane & off) != 0;
-#pragma unroll
-              for (int i = 0; i < off; ++i) {
-                const float ss = upper ? xs[i] : xs[i + off], ks = upper ? xs[i + off] : xs[i];
-                const float sq = upper ? xq[i] : xq[i + off], kq = upper ? xq[i + off] : xq[i];
-                xs[i] = ks + __shfl_xor_sync(0xffffffffu, ss, off);
-                xq[i] = kq + __shfl_xor_sync(0xffffffffu, sq, off);
-              }
-            }
-            st_sum[c0 / 32] += xs[0];
-            st_sq[c0 / 32] += xq[0];
-          }
-        }
-        if (p.add_mode != 0 && j + 1 < MT) {
-#pragma unroll
-          for (int v = 0; v < NV / 2; ++v) res[v] = nres[v];
-        }
-      }
+      flat_epilogue_item<BN, MT, STATS>(p, cls, nt * BN, q0, tid, lane, &tmem_full[acc], (it >> 1) & 1, trow, scratch,
+                                        st_slot != nullptr, sa);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
-    if (STATS) st_flush();
+    if (STATS) stat_flush<BN>(sa, st_slot, p.Cd, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -412,7 +451,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
 //   empty barriers (window / weights / accumulator-ready): one per CTA, released by tcgen05.commit.cta_group::2
 //                  multicast to both
 //   tmem_empty     : in the leader, 8 arrivals (one per epilogue warp of both CTAs, remote arrive from the peer)
-template <int BN, int MT, int WST>
+template <int BN, int MT, int WST, bool STATS>
 __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __grid_constant__ FlatParams p) {
   constexpr int HB = BN / 2;
   constexpr int W_BYTES = HB * 128;
@@ -567,96 +606,33 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
     }
   } else if (warp < 4) {
     // ------------------------------ epilogue (both CTAs: own 128 rows x MT) ------------------------------
-    constexpr int NV = BN / 8;
     const int lane = tid & 31;
     const uint32_t empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0), empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    StatAcc<BN> sa;
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) sa.s[c][0] = sa.s[c][1] = sa.q[c][0] = sa.q[c][1] = 0.f;
+    sa.nt = -1;
+    float* st_slot = (STATS && p.stats) ? p.stats + (size_t)(blockIdx.x * 4 + warp) * 2 * p.Cd : nullptr;
+    if (st_slot != nullptr)
+      for (int c = lane; c < 2 * p.Cd; c += 32) st_slot[c] = 0.f;
+    const uint32_t scratch = smem_base + bar_off + 512 + warp * kStatWarpBytes;
     int it = 0;
     for (int item = item_first; item < items_total; item += item_stride, ++it) {
       int cls, nt, q0;
       tile_of(item, cls, nt, q0);
-      const int n0 = nt * BN;
       const int acc = it & 1;
-      bf16* outp[MT];
-      const bf16* addp[MT];
-      bool validj[MT];
-#pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        const int q = q0 + j * 128 + tid;
-        const int n = q / p.IS;
-        const int r2 = q - n * p.IS;
-        const int h = r2 / p.P, w = r2 - h * p.P;
-        const int hd = h * p.dscale + p.ph[cls], wd = w * p.dscale + p.pw[cls];
-        validj[j] = n < p.N && h < p.Hs && w < p.Ws && hd < p.Hd && wd < p.Wd;
-        const size_t off = ((size_t)((size_t)n * p.Hd + hd) * p.Wd + wd) * p.Cd + n0;
-        outp[j] = p.dst + off;
-        addp[j] = nullptr;
-        if (validj[j] && p.add_mode == 1)
-          addp[j] = p.add_src + off;
-        else if (validj[j] && p.add_mode == 2 && (p.ph[cls] | p.pw[cls]) == 0)
-          addp[j] = p.add_src + ((size_t)((size_t)n * p.Hs + h) * p.Ws + w) * p.Cd + n0;
+      if (STATS && nt != sa.nt) {
+        stat_flush<BN>(sa, st_slot, p.Cd, lane);
+        sa.nt = nt;
       }
-      U32B res[NV / 2];
-      const U32B zero32 = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      if (p.add_mode != 0) {
-#pragma unroll
-        for (int v = 0; v < NV / 2; ++v) res[v] = addp[0] ? ld_stream32(addp[0] + v * 16) : zero32;
-      }
-      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-      tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16) + acc * (MT * BN);
-#pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        U32B nres[NV / 2];
-        if (p.add_mode != 0 && j + 1 < MT) {
-#pragma unroll
-          for (int v = 0; v < NV / 2; ++v) nres[v] = addp[j + 1] ? ld_stream32(addp[j + 1] + v * 16) : zero32;
-        }
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(trow + j * BN + c0, r);
-          tmem_ld_wait();
-          if (validj[j]) {
-#pragma unroll
-            for (int g = 0; g < 4; g += 2) {
-              uint4 o[2];
-#pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[(g + h2) * 8 + i]);
-                if (p.add_mode != 0) {
-                  float a[8];
-                  const U32B& rv = res[(c0 / 8 + g) / 2];
-                  unpack8(h2 == 0 ? rv.lo : rv.hi, a);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] += a[i];
-                }
-                if (p.bias != nullptr) {  // eval mode: folded BatchNorm shift (same 8 floats for every lane: L1 broadcast)
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (g + h2) * 8));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + (g + h2) * 8 + 4));
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (p.relu) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-                }
-                o[h2] = pack8(f);
-              }
-              st_global32(outp[j] + c0 + g * 8, o[0], o[1]);
-            }
-          }
-        }
-        if (p.add_mode != 0 && j + 1 < MT) {
-#pragma unroll
-          for (int v = 0; v < NV / 2; ++v) res[v] = nres[v];
-        }
-      }
+      flat_epilogue_item<BN, MT, STATS>(p, cls, nt * BN, q0, tid, lane, &tmem_full[acc], (it >> 1) & 1, trow, scratch,
+                                        st_slot != nullptr, sa);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc ? empty1 : empty0);
     }
+    if (STATS) stat_flush<BN>(sa, st_slot, p.Cd, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -667,16 +643,19 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+thread_local int g_flat_last_grid = 0;  // grid of the last flat launch of this thread (partial statistics rows = 4 x grid)
+
 template <int BN, int MT, int WST, bool RES = false>
 static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   constexpr int TM = MT * 128;
   const int nrows_max = (TM + p.smax - p.smin - 1 + p.P - 1) / p.P + 1;
   p.win_stage_bytes = (nrows_max * p.P * 128 + 1023) / 1024 * 1024;
   if (RES) {
-    if (p.nclass != 1 || p.Cd != BN || p.ngroups[0] != 1 || p.stats != nullptr) return 0;
+    if (p.nclass != 1 || p.Cd != BN || p.ngroups[0] != 1) return 0;
     p.res_tiles = p.ntaps[0] * (p.Cs / 64);
   }
-  const int fixed = (RES ? p.res_tiles : WST) * BN * 128 + 512;
+  const bool st = p.stats != nullptr;
+  const int fixed = (RES ? p.res_tiles : WST) * BN * 128 + 512 + (st ? kStatScratchBytes : 0);
   int ws = (kFlatSmemBudget - fixed) / p.win_stage_bytes;
   if (ws > 4) ws = 4;
   if (ws < 2) return 0;  // window does not fit twice: not eligible
@@ -695,22 +674,18 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, false, RES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess && !RES)
-      e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_flat_kernel<BN, MT, WST, true, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_flat)");
     attr_set = true;
   }
   int grid = p.items_total < kNumSMs ? p.items_total : kNumSMs;
-  if (RES) {
-    conv_flat_kernel<BN, MT, WST, false, true><<<grid, kFlatThreads, total, s>>>(p);
-    GDL_CHECK_LAUNCH("conv_flat_kernel(resident weights)");
-    return 1;
-  }
-  if (p.stats != nullptr)
-    conv_flat_kernel<BN, MT, WST, true><<<grid, kFlatThreads, total, s>>>(p);
+  g_flat_last_grid = grid;
+  if (st)
+    conv_flat_kernel<BN, MT, WST, true, RES><<<grid, kFlatThreads, total, s>>>(p);
   else
-    conv_flat_kernel<BN, MT, WST, false><<<grid, kFlatThreads, total, s>>>(p);
+    conv_flat_kernel<BN, MT, WST, false, RES><<<grid, kFlatThreads, total, s>>>(p);
   GDL_CHECK_LAUNCH("conv_flat_kernel");
   return 1;
 }
@@ -719,11 +694,11 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
 template <int BN, int MT, int WST>
 static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   constexpr int TM = MT * 128;
-  if (p.stats != nullptr) return 0;
   const int nrows_max = (TM + p.smax - p.smin - 1 + p.P - 1) / p.P + 1;
   // + P-1 pixel rows: both CTAs of a pair start their window at the same offset whatever its phase in the padded row
   p.win_stage_bytes = ((nrows_max * p.P + p.P - 1) * 128 + 1023) / 1024 * 1024;
-  const int fixed = WST * (BN / 2) * 128 + 512;
+  const bool st = p.stats != nullptr;
+  const int fixed = WST * (BN / 2) * 128 + 512 + (st ? kStatScratchBytes : 0);
   int ws = (kFlatSmemBudget - fixed) / p.win_stage_bytes;
   if (ws > 4) ws = 4;
   if (ws < 2) return 0;
@@ -735,8 +710,11 @@ static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   if (total < kFlatSmemFloor) total = kFlatSmemFloor;  // sole TMEM user of its SM (see launch_flat)
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(conv_flat2_kernel<BN, MT, WST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_flat2_kernel<BN, MT, WST, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_flat2_kernel<BN, MT, WST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_flat2)");
     attr_set = true;
   }
@@ -755,12 +733,14 @@ static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST>, p);
+  g_flat_last_grid = grid2;
+  cudaError_t e = st ? cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST, true>, p)
+                     : cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST, false>, p);
   if (e != cudaSuccess) return cuda_fail(e, "conv_flat2_kernel");
   return 1;
 }
 
-thread_local int g_fused_stats_min_k = 1 << 30;  // per calling thread, like gdl_set_sweep
+thread_local int g_fused_stats_min_k = -1;  // per calling thread, like gdl_set_sweep; -1: GDL_FUSED_STATS_MIN_K or the default
 
 static int env_int3(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -791,11 +771,11 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   p.bias = bias;
   p.relu = relu;
   p.rev = g_sweep_rev;
-  // The statistics butterfly costs ~1.3k instructions per 128x128 tile in the epilogue warps: it hides behind the
-  // MMAs only when the reduction is long (measured: +2-8 % kernel time for K >= 1152, +30 % at K = 576, 2.4x for
-  // 1x1); against the separate statistics kernel it came out even on the whole step, so it is off by default
-  // (gdl_set_fused_stats_min_k(K) enables it for convolutions with K >= that value; tests/ cover both paths).
-  if (stats != nullptr && wt_k < g_fused_stats_min_k) stats = nullptr;
+  // BatchNorm statistics in the epilogue (stat_chunk above) for convolutions with K >= the threshold: default every
+  // convolution this kernel runs (GDL_FUSED_STATS_MIN_K / gdl_set_fused_stats_min_k(K) raise it; tests/ cover both paths).
+  static const int stats_min_k_env = env_int3("GDL_FUSED_STATS_MIN_K", 0);
+  const int stats_min_k = g_fused_stats_min_k >= 0 ? g_fused_stats_min_k : stats_min_k_env;
+  if (stats != nullptr && wt_k < stats_min_k) stats = nullptr;
   p.stats = stats;
   p.N = N; p.Hs = Hs; p.Ws = Ws; p.Cs = Cs;
   p.Hd = Hd; p.Wd = Wd; p.Cd = Cd;
@@ -906,7 +886,7 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
   // GDL_FLAT_PAIR (default 1): CTA-pair kernel (cta_group::2) where the wave-count model above prefers it
   static const int pair = env_int3("GDL_FLAT_PAIR", 1);
   if (BN == 128) {
-    if (pair && pair_wins && !mt_force && stats == nullptr) {
+    if (pair && pair_wins && !mt_force) {
       const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
       if (!th) return GDL_ECUDA;
       p.tm_w_half = *th;
@@ -922,8 +902,8 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
     // SM, 5 KB as a pair).  1 = wherever eligible (instead of the resident-weights kernel too), 2 = only where the
     // resident-weights kernel does not apply (e.g. the 128 -> 64 channel stride-2 data gradients), 0 = off.
     static const int pair64 = env_int3("GDL_FLAT_PAIR64", 2);
-    const bool res_ok = resident && mt == 2 && Cs == 64 && Cd == 64 && (kind == 0 || kind == 1) && stats == nullptr;
-    if (pair && pair64 && pair_wins && !mt_force && stats == nullptr && !(pair64 == 2 && res_ok)) {
+    const bool res_ok = resident && mt == 2 && Cs == 64 && Cd == 64 && (kind == 0 || kind == 1);
+    if (pair && pair64 && pair_wins && !mt_force && !(pair64 == 2 && res_ok)) {
       const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
       if (!th) return GDL_ECUDA;
       p.tm_w_half = *th;
@@ -933,11 +913,8 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
     if (rc == 0 && mt == 2) rc = launch_flat<64, 2, 6>(p, Q, s);
     if (rc == 0) rc = launch_flat<64, 1, 6>(p, Q, s);
   }
-  if (rc > 0 && stats_rows != nullptr && stats != nullptr) {
-    // one partial row per epilogue warp of every CTA (launch_flat's grid)
-    const int grid = p.items_total < kNumSMs ? p.items_total : kNumSMs;
-    *stats_rows = grid * 4;
-  }
+  // one partial row per epilogue warp of every CTA of the grid that ran
+  if (rc > 0 && stats_rows != nullptr && stats != nullptr) *stats_rows = g_flat_last_grid * 4;
   return rc;
 }
 
@@ -945,6 +922,6 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
 
 extern "C" int gdl_set_fused_stats_min_k(int k) {
   int old = gdl::g_fused_stats_min_k;
-  gdl::g_fused_stats_min_k = k < 0 ? (1 << 30) : k;
+  gdl::g_fused_stats_min_k = k < 0 ? -1 : k;
   return old;
 }

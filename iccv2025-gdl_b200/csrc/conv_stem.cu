@@ -93,6 +93,7 @@ struct StemParams {
   CUtensorMap tm_x;    // X {16, Wp, Hp, N}, box {16, 11, 19, 1}, 32B swizzle
   CUtensorMap tm_w;    // packed weights {256, 64}, box {16, 64}, 32B swizzle
   CUtensorMap tm_out;  // y {64, Wo, Ho, N}, box {64, 8, 16, 1}, 128B swizzle
+  float* stats;        // optional [gridDim.x][2][64]: per-CTA sum / sum of squares of the bf16 outputs (BatchNorm statistics)
   int N, Ho, Wo, tiles_h, tiles_w, tiles_total;
 };
 
@@ -102,7 +103,8 @@ struct StemFwdSmem {
   static constexpr int HALO_OFF = kSWBytes;
   static constexpr int OUT_OFF = (HALO_OFF + kSFwdHaloStages * kSHaloBytes + 1023) / 1024 * 1024;
   static constexpr int BAR_OFF = OUT_OFF + 128 * 128;
-  static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+  static constexpr int STAT_OFF = BAR_OFF + 512;  // [4 warps][2][64] floats
+  static constexpr int TOTAL = STAT_OFF + 2048 + 1024;
 };
 
 template <int ROLES>  // bit 0: elect.sync for the MMA issuer, bit 1: for the TMA producer (else lane 0 by thread id)
@@ -192,14 +194,25 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_fwd_kernel(const __grid_con
     }
   } else if (warp < 4) {
     // ---------------- epilogue: TMEM -> bf16 -> swizzled smem -> TMA store ----------------
-    const int row = tid, sw = row & 7;
+    // BatchNorm statistics (reference backbone.py:104 bn1, train mode) come out of the staged tile: each warp re-reads
+    // the 32 rows it wrote by columns (lane = channel pair, conflict-free: one 128-byte row per load) and keeps the
+    // sum / sum of squares of the bf16-rounded outputs in registers over all of the CTA's tiles; rows outside the
+    // image are staged as zeros (the TMA store clips them anyway).  Fixed order of additions: deterministic.
+    const int row = tid, sw = row & 7, lane = tid & 31;
     const uint32_t out_row = smem_base + L::OUT_OFF + row * 128;
+    const bool want_stats = p.stats != nullptr;
+    float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};
+    uint32_t col_off[8];  // byte offset of this lane's channel pair inside a staged row, per swizzle phase
+#pragma unroll
+    for (int k = 0; k < 8; ++k) col_off[k] = ((uint32_t)((lane >> 2) ^ k) << 4) + (lane & 3) * 4;
+    const uint32_t warp_rows = smem_base + L::OUT_OFF + warp * 32 * 128;
     int it = 0;
     for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
       const int n = t / tiles_img;
       const int rem = t - n * tiles_img;
       const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
       const int acc = it & 1;
+      const bool inside = (th * kSTileH + (row >> 3) < p.Ho) && (tw * kSTileW + (row & 7) < p.Wo);
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       if (tid == 0) tma_store_wait_read();
@@ -216,6 +229,7 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_fwd_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[q * 8 + i]);
           uint4 o = pack8(f);
+          if (want_stats && !inside) o = make_uint4(0, 0, 0, 0);
           const int chunk = (c0 >> 3) + q;
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(out_row + ((chunk ^ sw) << 4)), "r"(o.x),
                        "r"(o.y), "r"(o.z), "r"(o.w)
@@ -224,6 +238,19 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_fwd_kernel(const __grid_con
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
+      if (want_stats) {
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          uint32_t w;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(warp_rows + rr * 128 + col_off[rr & 7]) : "memory");
+          const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+          ssum[0] += lo;
+          ssq[0] = fmaf(lo, lo, ssq[0]);
+          ssum[1] += hi;
+          ssq[1] = fmaf(hi, hi, ssq[1]);
+        }
+      }
       fence_proxy_async();
       named_bar_sync(1, 128);
       if (tid == 0) {
@@ -232,6 +259,15 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_fwd_kernel(const __grid_con
       }
     }
     if (tid == 0) tma_store_wait_all();
+    if (want_stats) {  // combine the four warps in a fixed order: one partial row [2][64] per CTA
+      float* sred = reinterpret_cast<float*>(smem + L::STAT_OFF);
+      sred[warp * 128 + 2 * lane] = ssum[0];
+      sred[warp * 128 + 2 * lane + 1] = ssum[1];
+      sred[warp * 128 + 64 + 2 * lane] = ssq[0];
+      sred[warp * 128 + 64 + 2 * lane + 1] = ssq[1];
+      named_bar_sync(1, 128);
+      p.stats[(size_t)blockIdx.x * 128 + tid] = (sred[tid] + sred[128 + tid]) + (sred[256 + tid] + sred[384 + tid]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -418,7 +454,8 @@ extern "C" int gdl_stem_pack_weights_scaled(const float* w_oihw, const float* sc
   return GDL_OK;
 }
 
-extern "C" int gdl_stem_fwd(const void* x16, const void* w_packed, void* y, int N, int H, int W, gdl_stream_t s) {
+static int stem_fwd_impl(const void* x16, const void* w_packed, void* y, int N, int H, int W, float* stats, int* stats_rows,
+                         gdl_stream_t s) {
   GDL_REQUIRE(x16 && w_packed && y && N > 0, "gdl_stem_fwd: bad arguments");
   int Ho, Wo, Hp, Wp;
   GDL_REQUIRE(gdl_stem_geometry(H, W, &Ho, &Wo, &Hp, &Wp) == GDL_OK, "gdl_stem_fwd: bad shape");
@@ -428,6 +465,7 @@ extern "C" int gdl_stem_fwd(const void* x16, const void* w_packed, void* y, int 
   if (!tx || !tw || !to) return GDL_ECUDA;
   StemParams p;
   p.tm_x = *tx; p.tm_w = *tw; p.tm_out = *to;
+  p.stats = stats;
   p.N = N; p.Ho = Ho; p.Wo = Wo;
   p.tiles_h = (Ho + kSTileH - 1) / kSTileH;
   p.tiles_w = (Wo + kSTileW - 1) / kSTileW;
@@ -454,7 +492,18 @@ extern "C" int gdl_stem_fwd(const void* x16, const void* w_packed, void* y, int 
     default: stem_fwd_kernel<3><<<grid, kSThreads, StemFwdSmem::TOTAL, (cudaStream_t)s>>>(p); break;
   }
   GDL_CHECK_LAUNCH("stem_fwd_kernel");
+  if (stats_rows) *stats_rows = grid;
   return GDL_OK;
+}
+
+extern "C" int gdl_stem_fwd(const void* x16, const void* w_packed, void* y, int N, int H, int W, gdl_stream_t s) {
+  return stem_fwd_impl(x16, w_packed, y, N, H, W, nullptr, nullptr, s);
+}
+
+extern "C" int gdl_stem_fwd_stats(const void* x16, const void* w_packed, void* y, int N, int H, int W, float* bn_partial,
+                                  int* bn_partial_rows, gdl_stream_t s) {
+  GDL_REQUIRE(bn_partial && bn_partial_rows, "gdl_stem_fwd_stats: null pointer");
+  return stem_fwd_impl(x16, w_packed, y, N, H, W, bn_partial, bn_partial_rows, s);
 }
 
 extern "C" int64_t gdl_stem_wgrad_workspace_bytes(int N, int H, int W) {

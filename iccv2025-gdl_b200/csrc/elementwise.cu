@@ -620,7 +620,7 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(float hi, float lo) {
 __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd2_kernel(
     const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
     bf16* __restrict__ y, uint8_t* __restrict__ amax, bf16* __restrict__ xmax, int N, int H, int W, int C, int Ho,
-    int Wo) {
+    int Wo, int rev) {
   __shared__ float s_scale[512], s_shift[512];
   __shared__ int s_tapoff[16];  // element offset of tap (r,s) from the window's top-left pixel
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -633,7 +633,8 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd2_kernel(
   const int HB = (Ho + 1) / 2, WB = (Wo + 1) / 2;
   // 32-bit index arithmetic: the launcher checks that every element index of x fits in an int
   const int total = N * HB * WB * groups;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += gridDim.x * blockDim.x) {
+    const int i = rev ? total - 1 - i0 : i0;  // gdl_set_sweep: start on the producer's tail that is still in L2
     const int cg = i % groups;
     int t = i / groups;
     const int wb = t % WB;
@@ -1057,7 +1058,7 @@ extern "C" int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const 
     int64_t total2 = (int64_t)N * ((Ho + 1) / 2) * ((Wo + 1) / 2) * (C / 8);
     bn_relu_maxpool_fwd2_kernel<<<ew_grid(total2, 256, GDL_RESIDENT(bn_relu_maxpool_fwd2_kernel, 256)), 256, 0,
                                   (cudaStream_t)s>>>((const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H,
-                                                     W, C, Ho, Wo);
+                                                     W, C, Ho, Wo, g_sweep_rev);
     GDL_CHECK_LAUNCH("bn_relu_maxpool_fwd2_kernel");
     return GDL_OK;
   }

@@ -51,6 +51,7 @@ SIGNATURES = {
     "gdl_stem_layout": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "gdl_stem_pack_weights": (_i, [_p, _p, _i, _p]),
     "gdl_stem_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "gdl_stem_fwd_stats": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "gdl_stem_wgrad_workspace_bytes": (_l, [_i, _i, _i]),
     "gdl_stem_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _l, _p]),
     "gdl_layout_ncthw_to_nhwc8": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),

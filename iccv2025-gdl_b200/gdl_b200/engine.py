@@ -32,6 +32,7 @@ USE_WGRAD_STREAM = os.environ.get("GDL_WGRAD_STREAM", "0") != "0"
 #      reduce descending after the (ascending) dgrad, apply ascending
 #   2  the convolutions alternate as well (conv1 of a block descending, conv2 ascending, BN passes in between)
 SWEEP = int(os.environ.get("GDL_SWEEP", "1"))
+STEM_STATS = int(os.environ.get("GDL_STEM_STATS", "1"))  # BatchNorm statistics of the stem from its epilogue
 
 
 class _Pool:
@@ -129,12 +130,19 @@ class _StemBN(_ConvBN):
         ops.stem_pack_weights(self.conv.weight.data, self.wp, self.ci_real)
 
     def forward(self, eng, x16, res=None):
-        ops.stem_fwd(x16, self.wp, self.x, self.N, self.H, self.W, self.ci_real)
         bn = self.bn
-        ops.sweep(1 if SWEEP else 0)
-        ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
-                     bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
-                     self.scale, self.shift)
+        if STEM_STATS:  # batch statistics out of the stem's epilogue: no separate pass over the largest activation
+            rows = ops.stem_fwd_stats(x16, self.wp, self.x, self.N, self.H, self.W, self.ci_real, eng.bn_partial)
+            ops.bn_stats_finalize(eng.bn_partial, rows, self.P, self.C, bn.weight.data, bn.bias.data, bn.eps,
+                                  bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                                  self.scale, self.shift)
+            ops.sweep(1 if SWEEP else 0)
+        else:
+            ops.stem_fwd(x16, self.wp, self.x, self.N, self.H, self.W, self.ci_real)
+            ops.sweep(1 if SWEEP else 0)
+            ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
+                         bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
+                         self.scale, self.shift)
         # BN-apply + ReLU + MaxPool(3,2,1) in one pass (reference backbone.py:104-106)
         ops.bn_relu_maxpool_fwd(self.x, self.scale, self.shift, eng.pool_y, eng.pool_idx, eng.pool_xmax,
                                 self.N, self.Ho, self.Wo, 64, eng.Hp, eng.Wp)

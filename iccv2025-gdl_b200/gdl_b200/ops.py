@@ -171,7 +171,8 @@ def sweep(reverse):
 
 
 def set_fused_stats_min_k(k):
-    """Enable the conv-epilogue BN statistics for convolutions with R*S*Ci >= k (k < 0: library default = off)."""
+    """Enable the conv-epilogue BN statistics for convolutions with R*S*Ci >= k (k < 0: library default = every
+    flat-window convolution, or GDL_FUSED_STATS_MIN_K).  Returns the previous setting."""
     return int(_lib.load().gdl_set_fused_stats_min_k(int(k)))
 
 
@@ -228,6 +229,15 @@ def stem_pack_weights_scaled(w_oihw, scale64, w_packed, Cc):
 @_op("conv_fwd", 1, lambda x16, w, y, N, H, W, Cc: ("flops", _stem_flops(N, H, W, Cc), "N%d %dx%d stem C%d s2d" % (N, H, W, Cc)))
 def stem_fwd(x16, w_packed, y, N, H, W, Cc):
     check(_lib.load().gdl_stem_fwd(_ptr(x16), _ptr(w_packed), _ptr(y), N, H, W, _stream()), "gdl_stem_fwd")
+
+
+@_op("conv_fwd", 1, lambda x16, w, y, N, H, W, Cc, partial: ("flops", _stem_flops(N, H, W, Cc), "N%d %dx%d stem C%d s2d" % (N, H, W, Cc)))
+def stem_fwd_stats(x16, w_packed, y, N, H, W, Cc, bn_partial):
+    """Stem forward with the BatchNorm partial sums of y formed in the epilogue; returns the number of partial rows."""
+    rows = C.c_int(0)
+    check(_lib.load().gdl_stem_fwd_stats(_ptr(x16), _ptr(w_packed), _ptr(y), N, H, W, _ptr(bn_partial), C.byref(rows),
+                                         _stream()), "gdl_stem_fwd_stats")
+    return rows.value
 
 
 def stem_wgrad_workspace_bytes(N, H, W):

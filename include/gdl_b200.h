@@ -99,8 +99,10 @@ int gdl_conv_fwd_bias_act(const gdl_conv_desc* d, const void* x, const void* w_p
  * a path without the fused statistics (call gdl_bn_stats on y instead).  bn_partial: gdl_bn_partial_floats(). */
 int gdl_conv_fwd_stats(const gdl_conv_desc* d, const void* x, const void* w_packed, void* y,
                        float* bn_partial, int* bn_partial_rows, gdl_stream_t s);
-/* Fused statistics are used for convolutions with R*S*Ci >= k (default: never — on the bench geometry the
- * epilogue cost equals what the separate kernel costs); k < 0 restores the default.  Thread-local.  Returns the old value. */
+/* Fused statistics are used for convolutions with R*S*Ci >= k.  Default (k < 0): the environment variable
+ * GDL_FUSED_STATS_MIN_K, else 0 = every convolution the flat-window kernels run (the per-warp shared-memory
+ * transpose costs less than the separate statistics pass on every layer of the bench geometry).  Thread-local.
+ * Returns the old value (negative: the default was in force). */
 int gdl_set_fused_stats_min_k(int k);
 /* Scheduling hint for the calling thread (no reference counterpart: the reference's kernels are cuDNN's):
  * reverse != 0 makes the following gdl_conv_fwd / gdl_conv_dgrad (flat kernels), gdl_bn_stats, gdl_bn_apply,
@@ -130,6 +132,11 @@ int gdl_stem_pack_weights(const float* w_oihw, void* w_packed, int C, gdl_stream
 int gdl_stem_pack_weights_scaled(const float* w_oihw, const float* scale64, void* w_packed, int C, gdl_stream_t s);
 /* y bf16 [N,Ho,Wo,64]. */
 int gdl_stem_fwd(const void* x16, const void* w_packed, void* y, int N, int H, int W, gdl_stream_t s);
+/* Same, and the statistics of the following train-mode BatchNorm (reference backbone.py:104 bn1) from the epilogue:
+ * bn_partial receives *bn_partial_rows rows of [2][64] floats (sum, sum of squares of the bf16-rounded outputs) for
+ * gdl_bn_stats_finalize — no separate pass over the largest activation of the step. */
+int gdl_stem_fwd_stats(const void* x16, const void* w_packed, void* y, int N, int H, int W, float* bn_partial,
+                       int* bn_partial_rows, gdl_stream_t s);
 int64_t gdl_stem_wgrad_workspace_bytes(int N, int H, int W);
 /* dw fp32 OIHW [64][C][7][7] from x16 and dy bf16 [N,Ho,Wo,64]; deterministic split-K. */
 int gdl_stem_wgrad(const void* x16, const void* dy, float* dw_oihw, int C, int N, int H, int W,

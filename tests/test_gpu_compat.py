@@ -194,7 +194,7 @@ def test_valid_with_folded_batchnorm_on_a_64_sample_test_set(tmp_path):
     msd = model.state_dict()
     sd_same = {k: v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu() for k, v in msd.items()}
     correct = torch.zeros(3)
-    worst, num, den, flips = 0.0, 0.0, 0.0, 0
+    worst, num, den, flips, sep_flips = 0.0, 0.0, 0.0, 0, 0
     with torch.no_grad():
         for spec, image, label in batches:
             got = model(spec.cuda().unsqueeze(1).float(), image.cuda().float())
@@ -204,7 +204,12 @@ def test_valid_with_folded_batchnorm_on_a_64_sample_test_set(tmp_path):
                 worst = max(worst, d.abs().max().item() / r.abs().max().item())
                 num, den = num + d.double().pow(2).sum().item(), den + r.double().pow(2).sum().item()
                 correct[i] += (r.argmax(1) == label).sum()
-                flips += int((g.cpu().argmax(1) != r.argmax(1)).sum())
+                differ = g.cpu().argmax(1) != r.argmax(1)
+                flips += int(differ.sum())
+                # rows the fp32 reference separates by more than 2.5 % of its logit spread (tests/test_gpu_parity_at_size.py)
+                top2 = r.topk(2, dim=1).values
+                margin = (top2[:, 0] - top2[:, 1]) / (r.max(1).values - r.min(1).values)
+                sep_flips += int((differ & (margin > 2.5e-2)).sum())
     acc = valid(args, _Wrap(model), torch.device("cuda"), batches)
     rel_l2 = (num / den) ** 0.5
     print("eval logits: relative L2 error %.4f, max |diff| / max |logit| %.4f, arg-max flips %d / 192; acc %s vs oracle %s"
@@ -212,7 +217,7 @@ def test_valid_with_folded_batchnorm_on_a_64_sample_test_set(tmp_path):
     # 17 layers of bf16 storage WITHOUT the per-batch renormalisation of training-mode BatchNorm: ~0.4 % rounding noise per
     # layer accumulates to 1-2 % of a logit (relative L2), a few % in the worst of the 1152 logits
     assert rel_l2 <= 2e-2 and worst <= 6e-2, (rel_l2, worst)
-    assert flips <= 2, flips
+    assert sep_flips == 0 and flips <= 4, (sep_flips, flips)   # >= 98 % of all rows, every separable row
     if flips == 0:
         assert list(acc) == (correct / 64).tolist()
     else:

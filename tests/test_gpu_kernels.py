@@ -215,6 +215,25 @@ def test_stem_space_to_depth(ci_real, T, H, W):
     ref = F.conv2d(x, w, stride=2, padding=3)
     assert torch.isfinite(x16.float()).all() and torch.isfinite(y.float()).all()
     assert rel_err(nchw(y), ref) < 6e-3, rel_err(nchw(y), ref)
+    # BatchNorm statistics from the stem's epilogue == a separate pass over the stored output (and the same output)
+    P = N * Ho * Wo
+    partial = torch.full((ops.bn_partial_floats(P, Co),), float("nan"), device="cuda")
+    y2 = torch.full_like(y, float("nan"))
+    rows = ops.stem_fwd_stats(x16, wp, y2, N, H, W, ci_real, partial)
+    assert rows > 0 and torch.equal(y, y2)
+    gamma, beta = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    outs = []
+    for fused in (True, False):
+        rm, rv = torch.zeros(Co, device="cuda"), torch.ones(Co, device="cuda")
+        mean, invstd, scale, shift = (torch.empty(Co, device="cuda") for _ in range(4))
+        if fused:
+            ops.bn_stats_finalize(partial, rows, P, Co, gamma, beta, 1e-5, 0.1, rm, rv, mean, invstd, scale, shift)
+        else:
+            ops.bn_stats(y, P, Co, torch.empty_like(partial), gamma, beta, 1e-5, 0.1, rm, rv, mean, invstd, scale, shift)
+        outs.append((mean, invstd, scale, shift, rm, rv))
+    torch.cuda.synchronize()
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (a - b).abs().max()
     dy = torch.randn(N, Co, Ho, Wo, device="cuda", generator=g).to(torch.bfloat16).float()
     ws = torch.empty(ops.stem_wgrad_workspace_bytes(N, H, W) // 4, device="cuda")
     dw = torch.full((Co, ci_real, 7, 7), float("nan"), device="cuda")
