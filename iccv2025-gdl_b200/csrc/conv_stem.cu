@@ -31,30 +31,34 @@ constexpr int kSThreads = 192;
 // ------------------------------------------------------------------------------------------
 // layout: f32 [B,C,T,H,W] -> bf16 space-to-depth [B*T, Hp, Wp, 16]
 // ------------------------------------------------------------------------------------------
-__global__ void stem_layout_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int C,
-                                   int T, int H, int W, int Hp, int Wp) {
-  const int64_t total = (int64_t)B * T * Hp * Wp;
+// One CTA per output row (image bt, s2d row pp), one thread per s2d pixel: consecutive threads read consecutive pairs
+// of source pixels of the two source rows 2pp-3, 2pp-2 of every channel (a warp covers 256 contiguous bytes per row) and
+// write consecutive 32-byte pixels.  C is a template parameter so the 16 staged values stay in registers, and the only
+// divisions are per CTA (the previous one-thread-per-pixel grid-stride version spent most of its issue slots on 64-bit
+// div/mod and a runtime-indexed local array: 50 % issue utilisation at 19-29 % of DRAM bandwidth).
+template <int C>
+__global__ void __launch_bounds__(128) stem_layout_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
+                                                          int T, int H, int W, int Hp, int Wp) {
+  const int row = blockIdx.x;
+  const int bt = row / Hp, pp = row - bt * Hp;
+  const int b = bt / T, t = bt - b * T;
   const int64_t HW = (int64_t)H * W;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int q = int(i % Wp);
-    int64_t t1 = i / Wp;
-    int pp = int(t1 % Hp);
-    int64_t bt = t1 / Hp;
-    int b = int(bt / T), t = int(bt - (int64_t)b * T);
+  const float* base = src + ((int64_t)b * C * T + t) * HW;  // channel c: + c*T*HW
+  const int h0 = 2 * pp - 3;
+  for (int q = threadIdx.x; q < Wp; q += blockDim.x) {
     float f[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) f[k] = 0.f;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-      int h = 2 * pp + dy - 3;
+      const int h = h0 + dy;
       if (h < 0 || h >= H) continue;
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        int w = 2 * q + dx - 3;
+        const int w = 2 * q + dx - 3;
         if (w < 0 || w >= W) continue;
-        for (int c = 0; c < C; ++c)
-          f[(dy * 2 + dx) * C + c] = src[(((int64_t)b * C + c) * T + t) * HW + (int64_t)h * W + w];
+#pragma unroll
+        for (int c = 0; c < C; ++c) f[(dy * 2 + dx) * C + c] = __ldg(base + (int64_t)c * T * HW + (int64_t)h * W + w);
       }
     }
     float lo[8], hi[8];
@@ -63,7 +67,7 @@ __global__ void stem_layout_kernel(const float* __restrict__ src, bf16* __restri
       lo[k] = f[k];
       hi[k] = f[8 + k];
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
+    uint4* o = reinterpret_cast<uint4*>(dst + ((int64_t)row * Wp + q) * 16);
     o[0] = pack8(lo);
     o[1] = pack8(hi);
   }
@@ -431,10 +435,15 @@ extern "C" int gdl_stem_layout(const float* src, void* dst, int B, int C, int T,
   GDL_REQUIRE(src && dst && B > 0 && C > 0 && C <= 4 && T > 0, "gdl_stem_layout: bad arguments");
   int Ho, Wo, Hp, Wp;
   GDL_REQUIRE(gdl_stem_geometry(H, W, &Ho, &Wo, &Hp, &Wp) == GDL_OK, "gdl_stem_layout: bad shape");
-  int64_t total = (int64_t)B * T * Hp * Wp;
-  int64_t blocks = ceil_div64(total, 256);
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  stem_layout_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(src, (bf16*)dst, B, C, T, H, W, Hp, Wp);
+  const int64_t rows = (int64_t)B * T * Hp;
+  GDL_REQUIRE(rows < ((int64_t)1 << 31), "gdl_stem_layout: too many rows");
+  const cudaStream_t st = (cudaStream_t)s;
+  switch (C) {
+    case 1: stem_layout_kernel<1><<<(unsigned)rows, 128, 0, st>>>(src, (bf16*)dst, T, H, W, Hp, Wp); break;
+    case 2: stem_layout_kernel<2><<<(unsigned)rows, 128, 0, st>>>(src, (bf16*)dst, T, H, W, Hp, Wp); break;
+    case 3: stem_layout_kernel<3><<<(unsigned)rows, 128, 0, st>>>(src, (bf16*)dst, T, H, W, Hp, Wp); break;
+    default: stem_layout_kernel<4><<<(unsigned)rows, 128, 0, st>>>(src, (bf16*)dst, T, H, W, Hp, Wp); break;
+  }
   GDL_CHECK_LAUNCH("stem_layout_kernel");
   return GDL_OK;
 }

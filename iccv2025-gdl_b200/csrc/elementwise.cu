@@ -187,30 +187,39 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
   shift[c] = beta[c] - rm[c] * sc;
 }
 
+// Per-channel coefficients of the element-wise passes live in REGISTERS: the grid stride (gridDim.x * blockDim.x) and the
+// vector count are multiples of C/8, so a thread meets the same 8-channel group in every iteration.  (Shared-memory
+// coefficient tables cost 2-5 LDS.128 per 16-byte vector, each 4-8 wavefronts because neighbouring lanes read different
+// groups: ncu showed the L1/shared pipe at 80-94 % and DRAM at 50-68 % in bn_bwd_apply / bn_bwd_nores_apply.)
+__device__ __forceinline__ int fixed_channel_group(int64_t first_vec, int64_t nvec, int groups, int rev) {
+  const int cg = int(first_vec % groups);
+  return rev ? groups - 1 - cg : cg;  // nvec % groups == 0: vector nvec-1-i belongs to group groups-1-(i % groups)
+}
+
 // y = [relu](x*scale + shift [+ res])
 __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x,
                                                        const bf16* __restrict__ res,
                                                        bf16* __restrict__ y, int64_t nvec, int C,
                                                        const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int relu, int rev) {
-  __shared__ float s_scale[512], s_shift[512];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    s_scale[c] = scale[c];
-    s_shift[c] = shift[c];
-  }
-  __syncthreads();
   const int groups = C / 8;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec;
-       i0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = sweep_idx(i0, nvec, rev);
-    const int cg = int(i % groups);
-    float f[8];
-    unpack8(ld_stream16(x + i * 8), f);
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = fixed_channel_group(first, nvec, groups, rev);
+  float sc[8], sh[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) f[c] = fmaf(f[c], s_scale[cg * 8 + c], s_shift[cg * 8 + c]);
+  for (int c = 0; c < 8; ++c) {
+    sc[c] = scale[cg * 8 + c];
+    sh[c] = shift[cg * 8 + c];
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto body = [&](int64_t i, const uint4& ux, const uint4& ur) {
+    float f[8];
+    unpack8(ux, f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = fmaf(f[c], sc[c], sh[c]);
     if (res != nullptr) {
       float r[8];
-      unpack8(ld_stream16(res + i * 8), r);
+      unpack8(ur, r);
 #pragma unroll
       for (int c = 0; c < 8; ++c) f[c] += r[c];
     }
@@ -219,23 +228,30 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
       for (int c = 0; c < 8; ++c) f[c] = fmaxf(f[c], 0.f);
     }
     *reinterpret_cast<uint4*>(y + i * 8) = pack8(f);
+  };
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  int64_t i0 = first;
+  for (; i0 + stride < nvec; i0 += 2 * stride) {  // two vectors (up to four loads) in flight per thread
+    const int64_t j0 = sweep_idx(i0, nvec, rev), j1 = sweep_idx(i0 + stride, nvec, rev);
+    const uint4 x0 = ld_stream16(x + j0 * 8), x1 = ld_stream16(x + j1 * 8);
+    const uint4 r0 = res ? ld_stream16(res + j0 * 8) : zero4, r1 = res ? ld_stream16(res + j1 * 8) : zero4;
+    body(j0, x0, r0);
+    body(j1, x1, r1);
+  }
+  for (; i0 < nvec; i0 += stride) {
+    const int64_t j = sweep_idx(i0, nvec, rev);
+    body(j, ld_stream16(x + j * 8), res ? ld_stream16(res + j * 8) : zero4);
   }
 }
 
-// backward pass 1: dz = dy * (y > 0); partial sums of dz and dz * xhat
+// backward pass 1: dz = dy * (y > 0); partial sums of dz and dz * x (bn_bwd_finalize_raw_kernel forms sum(dz * xhat))
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
-    const bf16* dy, const bf16* __restrict__ y, const bf16* __restrict__ x, bf16* dz, int64_t P, int C, const float* __restrict__ mean,
-    const float* __restrict__ invstd, float* __restrict__ partial, int relu, int rev) {
+    const bf16* dy, const bf16* __restrict__ y, const bf16* __restrict__ x, bf16* dz, int64_t P, int C,
+    float* __restrict__ partial, int relu, int rev) {
   const int groups = C / 8;
   const int lanes = kBnThreads / groups;
   const int cg = threadIdx.x % groups;
   const int lane = threadIdx.x / groups;
-  float mu[8], is[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    mu[c] = mean[cg * 8 + c];
-    is[c] = invstd[cg * 8 + c];
-  }
   float acc[2][8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[0][c] = acc[1][c] = 0.f;
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       acc[0][c] += g[c];
-      acc[1][c] = fmaf(g[c], (xv[c] - mu[c]) * is[c], acc[1][c]);
+      acc[1][c] = fmaf(g[c], xv[c], acc[1][c]);
     }
   };
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
@@ -299,29 +315,30 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const float* __restrict__ invstd, const float* __restrict__ dgamma,
     const float* __restrict__ dbeta, int rev) {
   // dx = a*dz + b*x + c  with  a = gamma*invstd,  b = -a*invstd*dgamma/P,
-  //                            c = -a*dbeta/P - b*mean
-  __shared__ float s_a[512], s_b[512], s_c[512];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = gamma[c] * invstd[c];
-    float b = -a * invstd[c] * dgamma[c] * invP;
-    s_a[c] = a;
-    s_b[c] = b;
-    s_c[c] = -a * dbeta[c] * invP - b * mean[c];
-  }
-  __syncthreads();
+  //                            c = -a*dbeta/P - b*mean          (per channel, in registers: see fixed_channel_group)
   const int groups = C / 8;
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = fixed_channel_group(first, nvec, groups, rev);
+  float ka[8], kb[8], kc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ch = cg * 8 + c;
+    const float a = gamma[ch] * invstd[ch];
+    const float b = -a * invstd[ch] * dgamma[ch] * invP;
+    ka[c] = a;
+    kb[c] = b;
+    kc[c] = -a * dbeta[ch] * invP - b * mean[ch];
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   auto body = [&](int64_t i, const uint4& ug, const uint4& ux) {
-    const int cg = int(i % groups);
     float g[8], xv[8];
     unpack8(ug, g);
     unpack8(ux, xv);
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      g[c] = fmaf(s_a[cg * 8 + c], g[c], fmaf(s_b[cg * 8 + c], xv[c], s_c[cg * 8 + c]));
+    for (int c = 0; c < 8; ++c) g[c] = fmaf(ka[c], g[c], fmaf(kb[c], xv[c], kc[c]));
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(g);
   };
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = first;
   for (; i + stride < nvec; i += 2 * stride) {
     const int64_t j0 = sweep_idx(i, nvec, rev), j1 = sweep_idx(i + stride, nvec, rev);
     const uint4 g0 = ld_stream16(dz + j0 * 8), x0 = ld_stream16(x + j0 * 8);
@@ -433,19 +450,19 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict
 // models/backbone.py:44-46): the ReLU mask is recomputed from x (y > 0  <=>  x*scale+shift > 0), so
 // neither y is read nor the masked gradient written: 10 B/element instead of 14.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
-    const bf16* __restrict__ dy, const bf16* __restrict__ x, int64_t P, int C, const float* __restrict__ mean,
-    const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
-    float* __restrict__ partial, int rev) {
+// The reduce pass accumulates sum(dz) and sum(dz * x); the finalize kernel turns the second into
+// sum(dz * xhat) = invstd * (sum(dz * x) - mean * sum(dz)) in double precision (5 instead of 8 instructions per
+// element and 16 registers fewer: three CTAs per SM instead of two — the kernel was latency bound at 25 % occupancy).
+__global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_nores_reduce_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, int64_t P, int C, const float* __restrict__ scale,
+    const float* __restrict__ shift, float* __restrict__ partial, int rev) {
   const int groups = C / 8;
   const int lanes = kBnThreads / groups;
   const int cg = threadIdx.x % groups;
   const int lane = threadIdx.x / groups;
-  float mu[8], is[8], sc[8], sh[8];
+  float sc[8], sh[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    mu[c] = mean[cg * 8 + c];
-    is[c] = invstd[cg * 8 + c];
     sc[c] = scale[cg * 8 + c];
     sh[c] = shift[cg * 8 + c];
   }
@@ -462,7 +479,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
     for (int c = 0; c < 8; ++c) {
       const float gz = fmaf(xv[c], sc[c], sh[c]) > 0.f ? g[c] : 0.f;
       acc[0][c] += gz;
-      acc[1][c] = fmaf(gz, (xv[c] - mu[c]) * is[c], acc[1][c]);
+      acc[1][c] = fmaf(gz, xv[c], acc[1][c]);
     }
   };
   for (; pix + 3 * stride < P; pix += 4 * stride) {  // four pixels (eight 16-byte loads) in flight per thread
@@ -483,48 +500,65 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_nores_reduce_kernel(
   block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
 }
 
+// partials hold (sum dz, sum dz*x): dbeta = s1, dgamma = invstd * (s2 - mean * s1)
+__global__ void bn_bwd_finalize_raw_kernel(const float* __restrict__ partial, int nblk, int C,
+                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    s1 += (double)partial[(size_t)b * 2 * C + c];
+    s2 += (double)partial[(size_t)b * 2 * C + C + c];
+  }
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if (lane == 0) {
+    dbeta[c] = (float)s1;
+    dgamma[c] = (float)((double)invstd[c] * (s2 - (double)mean[c] * s1));
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_nores_apply_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, int64_t nvec, int C,
     float invP, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int rev) {
-  __shared__ float s_a[512], s_b[512], s_c[512], s_sc[512], s_sh[512];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = gamma[c] * invstd[c];
-    float b = -a * invstd[c] * dgamma[c] * invP;
-    s_a[c] = a;
-    s_b[c] = b;
-    s_c[c] = -a * dbeta[c] * invP - b * mean[c];
-    s_sc[c] = scale[c];
-    s_sh[c] = shift[c];
-  }
-  __syncthreads();
   const int groups = C / 8;
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = fixed_channel_group(first, nvec, groups, rev);
+  float ka[8], kb[8], kc[8], sc[8], sh[8];  // per-channel coefficients in registers (see fixed_channel_group)
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ch = cg * 8 + c;
+    const float a = gamma[ch] * invstd[ch];
+    const float b = -a * invstd[ch] * dgamma[ch] * invP;
+    ka[c] = a;
+    kb[c] = b;
+    kc[c] = -a * dbeta[ch] * invP - b * mean[ch];
+    sc[c] = scale[ch];
+    sh[c] = shift[ch];
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   auto body = [&](int64_t i, const uint4& ug, const uint4& ux) {
-    const int cg = int(i % groups);
     float g[8], xv[8];
     unpack8(ug, g);
     unpack8(ux, xv);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const int ch = cg * 8 + c;
-      const float gz = fmaf(xv[c], s_sc[ch], s_sh[ch]) > 0.f ? g[c] : 0.f;
-      g[c] = fmaf(s_a[ch], gz, fmaf(s_b[ch], xv[c], s_c[ch]));
+      const float gz = fmaf(xv[c], sc[c], sh[c]) > 0.f ? g[c] : 0.f;
+      g[c] = fmaf(ka[c], gz, fmaf(kb[c], xv[c], kc[c]));
     }
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(g);
   };
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < nvec; i += 4 * stride) {  // four vectors (eight loads) in flight per thread
-    uint4 g[4], xx[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int64_t j = sweep_idx(i + k * stride, nvec, rev);
-      g[k] = ld_stream16(dy + j * 8);
-      xx[k] = ld_stream16(x + j * 8);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) body(sweep_idx(i + k * stride, nvec, rev), g[k], xx[k]);
+  int64_t i = first;
+  for (; i + stride < nvec; i += 2 * stride) {  // two vectors (four loads) in flight per thread
+    const int64_t j0 = sweep_idx(i, nvec, rev), j1 = sweep_idx(i + stride, nvec, rev);
+    const uint4 g0 = ld_stream16(dy + j0 * 8), x0 = ld_stream16(x + j0 * 8);
+    const uint4 g1 = ld_stream16(dy + j1 * 8), x1 = ld_stream16(x + j1 * 8);
+    body(j0, g0, x0);
+    body(j1, g1, x1);
   }
   for (; i < nvec; i += stride) {
     const int64_t j = sweep_idx(i, nvec, rev);
@@ -715,6 +749,131 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd2_kernel(
           *reinterpret_cast<uint4*>(xmax + off) = xv;
         }
       }
+    }
+  }
+}
+
+// v3: column sweep.  One thread per (image, segment of kTailSeg output rows, output column, 8-channel group) walks
+// down its column: every input row is loaded and BN+ReLU-evaluated ONCE per thread (3 pixels: 1.5 evaluations per
+// output-row pixel instead of 6.25 per 2x2 block), the max is separable — horizontal max of a row with the column tag
+// (2 - s) in the key's low bits, then vertical max with the row tag 3*(2 - r) added — and the bottom row of one window
+// is the top row of the next.  Key = bf16 bits of the activation << 16 | (8 - tap): one unsigned max per candidate gives
+// the value and the FIRST arg-max in scan order (ATen's rule).  ~330 instructions per output pixel and 8 channels
+// (v2: ~640), all six loads of an iteration issued before any is consumed.
+constexpr int kTailSeg = 14;
+
+__device__ __forceinline__ void tail_row_keys(const uint4& u, const float (&sc)[8], const float (&sh)[8], uint32_t tag,
+                                              uint32_t (&k)[8]) {
+  const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float f0 = __uint_as_float(wd[j] << 16), f1 = __uint_as_float(wd[j] & 0xffff0000u);
+    const uint32_t pk = relu_pack_bf16x2(fmaf(f1, sc[2 * j + 1], sh[2 * j + 1]), fmaf(f0, sc[2 * j], sh[2 * j]));
+    k[2 * j] = __byte_perm(pk, tag, 0x1054);      // (low half of pk) << 16 | tag
+    k[2 * j + 1] = __byte_perm(pk, tag, 0x3254);  // (high half of pk) << 16 | tag
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) bn_relu_maxpool_fwd3_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+    bf16* __restrict__ y, uint8_t* __restrict__ amax, bf16* __restrict__ xmax, int N, int H, int W, int C, int Ho,
+    int Wo, int nseg, int rev) {
+  __shared__ int s_tapoff[16];  // element offset of tap (r,s) from the window's top-left pixel
+  if (threadIdx.x < 9) s_tapoff[threadIdx.x] = ((threadIdx.x / 3) * W + threadIdx.x % 3) * C;
+  __syncthreads();
+  const int groups = C / 8;
+  const int total = N * nseg * Wo * groups;  // 32-bit index arithmetic: the launcher checks the element count of x
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += gridDim.x * blockDim.x) {
+    const int i = rev ? total - 1 - i0 : i0;
+    const int cg = i % groups;
+    int t = i / groups;
+    const int wo = t % Wo;
+    t /= Wo;
+    const int seg = t % nseg;
+    const int n = t / nseg;
+    float sc[8], sh[8];
+    {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
+      sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+      sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+    }
+    const bf16* xn = x + (int64_t)n * H * W * C + cg * 8;
+    const int w0 = 2 * wo - 1;
+    const bool lv = w0 >= 0, rv = w0 + 2 < W;
+    const int e0 = (lv ? w0 : 0) * C, e1 = (w0 + 1) * C, e2 = (rv ? w0 + 2 : w0 + 1) * C;  // clamped column offsets
+    const int rowe = W * C;
+    auto hmax = [&](const uint4& u0, const uint4& u1, const uint4& u2, uint32_t (&hm)[8]) {
+      tail_row_keys(u1, sc, sh, 1u, hm);
+      uint32_t k[8];
+      if (lv) {
+        tail_row_keys(u0, sc, sh, 2u, k);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) hm[c] = max(hm[c], k[c]);
+      }
+      if (rv) {
+        tail_row_keys(u2, sc, sh, 0u, k);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) hm[c] = max(hm[c], k[c]);
+      }
+    };
+    const int ho0 = seg * kTailSeg, ho1 = min(ho0 + kTailSeg, Ho);
+    uint32_t carry[8];
+    uint32_t carry_tag = 0u;  // 6 once the carried row exists (it is row r = 0 of the next window)
+    if (ho0 > 0) {
+      const bf16* xr = xn + (2 * ho0 - 1) * rowe;
+      const uint4 u0 = ld_keep16(xr + e0), u1 = ld_keep16(xr + e1), u2 = ld_keep16(xr + e2);
+      hmax(u0, u1, u2, carry);
+      carry_tag = 6u;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) carry[c] = 0u;
+    }
+    for (int ho = ho0; ho < ho1; ++ho) {
+      const bool dv = 2 * ho + 1 < H;
+      const bf16* xa = xn + (2 * ho) * rowe;
+      const bf16* xb = xa + (dv ? rowe : 0);
+      const uint4 a0 = ld_keep16(xa + e0), a1 = ld_keep16(xa + e1), a2 = ld_keep16(xa + e2);
+      const uint4 b0 = ld_keep16(xb + e0), b1 = ld_keep16(xb + e1), b2 = ld_keep16(xb + e2);
+      uint32_t mid[8], bot[8], key[8];
+      hmax(a0, a1, a2, mid);
+      if (dv) {
+        hmax(b0, b1, b2, bot);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bot[c] = 0u;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) key[c] = max(max(carry[c] + carry_tag, mid[c] + 3u), bot[c]);
+      const int64_t off = (int64_t)((n * Ho + ho) * Wo + wo) * C + cg * 8;
+      uint4 yv;
+      uint32_t* yw = reinterpret_cast<uint32_t*>(&yv);
+      uint32_t tap[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) tap[c] = 8u - (key[c] & 15u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) yw[j] = __byte_perm(key[2 * j], key[2 * j + 1], 0x7632);
+      *reinterpret_cast<uint4*>(y + off) = yv;
+      uint2 packed;
+      packed.x = tap[0] | (tap[1] << 8) | (tap[2] << 16) | (tap[3] << 24);
+      packed.y = tap[4] | (tap[5] << 8) | (tap[6] << 16) | (tap[7] << 24);
+      *reinterpret_cast<uint2*>(amax + off) = packed;
+      if (xmax != nullptr) {
+        // conv output at the arg-max: re-read (L1 hit) through the tap-offset table
+        const unsigned short* xw = reinterpret_cast<const unsigned short*>(xn) + ((2 * ho - 1) * W + w0) * C;
+        uint32_t xb16[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xb16[c] = xw[s_tapoff[tap[c]] + c];
+        uint4 xv;
+        xv.x = xb16[0] | (xb16[1] << 16);
+        xv.y = xb16[2] | (xb16[3] << 16);
+        xv.z = xb16[4] | (xb16[5] << 16);
+        xv.w = xb16[6] | (xb16[7] << 16);
+        *reinterpret_cast<uint4*>(xmax + off) = xv;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) carry[c] = bot[c];
+      carry_tag = 6u;
     }
   }
 }
@@ -1012,10 +1171,11 @@ extern "C" int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz
   GDL_REQUIRE(!relu || (y && dz), "gdl_bn_bwd: relu needs y and dz");
   int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_bwd_reduce_kernel, kBnThreads));
   bn_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
-      (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, mean, invstd, partial, relu, g_sweep_rev);
+      (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, partial, relu, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_reduce_kernel");
-  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
-  GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  bn_bwd_finalize_raw_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, mean, invstd, dgamma,
+                                                                               dbeta);
+  GDL_CHECK_LAUNCH("bn_bwd_finalize_raw_kernel");
   int64_t nvec = P * C / 8;
   const bf16* dzp = relu ? (const bf16*)dz : (const bf16*)dy;
   bn_bwd_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
@@ -1031,11 +1191,12 @@ extern "C" int gdl_bn_bwd_nores(const void* dy, const void* x, void* dx, int64_t
   GDL_REQUIRE(dy && x && dx && gamma && mean && invstd && scale && shift && partial && dgamma && dbeta,
               "gdl_bn_bwd_nores: null pointer");
   int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_bwd_nores_reduce_kernel, kBnThreads));
-  bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)dy, (const bf16*)x, P, C, mean,
-                                                                      invstd, scale, shift, partial, g_sweep_rev);
+  bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)dy, (const bf16*)x, P, C, scale,
+                                                                      shift, partial, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_nores_reduce_kernel");
-  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
-  GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  bn_bwd_finalize_raw_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, mean, invstd, dgamma,
+                                                                               dbeta);
+  GDL_CHECK_LAUNCH("bn_bwd_finalize_raw_kernel");
   int64_t nvec = P * C / 8;
   bn_bwd_nores_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_nores_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
       (const bf16*)dy, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, scale, shift, dgamma,
@@ -1049,11 +1210,21 @@ extern "C" int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const 
                                        gdl_stream_t s) {
   GDL_REQUIRE(x && scale && shift && y && argmax, "gdl_bn_relu_maxpool_fwd: null pointer");
   GDL_REQUIRE(chan_ok(C) && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "gdl_bn_relu_maxpool_fwd: bad shape");
-  // GDL_STEM_TAIL: 2 (default) = one thread per 2x2 output block with packed max/arg-max keys, 1 = one thread per output
+  // GDL_STEM_TAIL: 3 (default) = column sweep, 2 = one thread per 2x2 output block with packed max/arg-max keys,
+  // 1 = one thread per output
   static const int variant = []() {
     const char* e = getenv("GDL_STEM_TAIL");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 3;
   }();
+  if (variant >= 3 && (int64_t)N * H * W * C < ((int64_t)1 << 31)) {  // 32-bit indexing inside the kernel
+    const int nseg = (Ho + kTailSeg - 1) / kTailSeg;
+    int64_t total3 = (int64_t)N * nseg * Wo * (C / 8);
+    bn_relu_maxpool_fwd3_kernel<<<ew_grid(total3, 256, GDL_RESIDENT(bn_relu_maxpool_fwd3_kernel, 256)), 256, 0,
+                                  (cudaStream_t)s>>>((const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H,
+                                                     W, C, Ho, Wo, nseg, g_sweep_rev);
+    GDL_CHECK_LAUNCH("bn_relu_maxpool_fwd3_kernel");
+    return GDL_OK;
+  }
   if (variant >= 2 && (int64_t)N * H * W * C < ((int64_t)1 << 31)) {  // the v2 kernel indexes with 32-bit integers
     int64_t total2 = (int64_t)N * ((Ho + 1) / 2) * ((Wo + 1) / 2) * (C / 8);
     bn_relu_maxpool_fwd2_kernel<<<ew_grid(total2, 256, GDL_RESIDENT(bn_relu_maxpool_fwd2_kernel, 256)), 256, 0,
@@ -1085,14 +1256,17 @@ extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax,
     const int64_t Pp = (int64_t)N * Ho * Wo;
     nblk = bn_blocks_cap(Pp, C, GDL_RESIDENT(bn_bwd_nores_reduce_kernel, kBnThreads));
     bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)gpool, (const bf16*)xmax, Pp, C,
-                                                                        mean, invstd, scale, shift, partial, g_sweep_rev);
+                                                                        scale, shift, partial, g_sweep_rev);
+    GDL_CHECK_LAUNCH("bn_bwd_nores_reduce_kernel(stem tail)");
+    bn_bwd_finalize_raw_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, mean, invstd, dgamma,
+                                                                                 dbeta);
   } else {
     nblk = bn_blocks_cap((int64_t)N * Ho * Wo * 4, C, GDL_RESIDENT(bn_relu_maxpool_bwd_reduce_kernel, kBnThreads));
     bn_relu_maxpool_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
         (const bf16*)gpool, argmax, (const bf16*)x, N, H, W, C, Ho, Wo, mean, invstd, scale, shift, partial);
+    GDL_CHECK_LAUNCH("bn_relu_maxpool_bwd_reduce_kernel");
+    bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
   }
-  GDL_CHECK_LAUNCH("bn_relu_maxpool_bwd_reduce_kernel");
-  bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
   bn_relu_maxpool_bwd_apply_kernel<<<ew_grid(total, 256, GDL_RESIDENT(bn_relu_maxpool_bwd_apply_kernel, 256)), 256, 0,
