@@ -283,19 +283,29 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_fwd_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------
 struct StemWgradParams {
   CUtensorMap tm_x;   // X, box {16, 11, 19, 1}, 32B swizzle
-  CUtensorMap tm_dy;  // dY {64, Wo, Ho, N}, box {64, 8, 16, 1}, 128B swizzle
-  float* partial;     // [splits][4 b][64 co][64 (a,ch)]
+  CUtensorMap tm_dy;  // dY {64, Wo, Ho, N}, box {64, 8, 17, 1}, 128B swizzle (one row below the tile: the shifted M block)
+  float* partial;     // [splits][4 a][64 co][64 (b,ch)]
   int N, Ho, Wo, tiles_h, tiles_w, tiles_total, tiles_per_split;
 };
 constexpr int kSWgStages = 4;
+constexpr int kSWgDyRows = kSTileH + 1;
 struct StemWgSmem {
-  static constexpr int DY_BYTES = 128 * 128;
-  static constexpr int DY_OFF = 0;
-  static constexpr int HALO_OFF = kSWgStages * DY_BYTES;
+  // per dY stage: 2 KB that stay zero (two 8-pixel K groups in front of the tile: the K step "rows -2, -1") + 17 tile rows
+  static constexpr int DY_STAGE = 2048 + kSWgDyRows * 1024;
+  static constexpr int DY_BYTES = kSWgDyRows * 1024;
+  static constexpr int HALO_OFF = kSWgStages * DY_STAGE;
   static constexpr int BAR_OFF = (HALO_OFF + kSWgStages * kSHaloBytes + 1023) / 1024 * 1024;
   static constexpr int TOTAL = BAR_OFF + 512 + 1024;
 };
 
+// Every MMA uses all 128 rows of M and all of its operand bytes: M = {tap row a, tap row a-1} x 64 co — the second
+// 64-row block of the MN-major A operand is the SAME dY tile one image row further (LBO = 1024 B), and
+// sum_p dY[p + (1,0)] X[p + (a,b)] = sum_p' dY[p'] X[p' + (a-1,b)] — and N = 4 column taps b x 16 ch (LBO = 32 B: the next
+// halo pixel).  Two accumulators (a = 1 | 0 and a = 3 | 2) instead of four half-empty ones: half the MMAs and half the
+// shared-memory operand traffic, which bounded the kernel (ncu: L1/shared pipe 89 %, DRAM 36 %).  Shifted block coverage:
+// tile rows 1..16 (row 16 = the next tile's row 0, or TMA zero fill below the image), so only row 0 of the IMAGE is
+// missing for a-1: tiles of the first tile row run one more K step over "rows -2, -1", where block 0 reads the 2 KB of
+// zeros kept in front of the tile and block 1 reads (zeros, row 0).
 __global__ void __launch_bounds__(kSThreads, 1) stem_wgrad_kernel(const __grid_constant__ StemWgradParams p) {
   using L = StemWgSmem;
   constexpr int ST = kSWgStages;
@@ -310,6 +320,11 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_wgrad_kernel(const __grid_c
   const int t0 = blockIdx.x * p.tiles_per_split;
   const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
 
+  {  // zero every operand byte once: the zero K groups in front of each dY tile, and finite values wherever the extra
+     // K step's B descriptor points in front of a halo (0 x NaN would poison the accumulator)
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < (L::BAR_OFF >> 4); i += kSThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
   if (tid == 0) {
     for (int i = 0; i < ST; ++i) {
       mbar_init(&full[i], 1);
@@ -319,13 +334,14 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_wgrad_kernel(const __grid_c
     fence_mbar_init();
   }
   if (warp == 4) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
   if (tid == 5 * 32) {
     tma_prefetch_desc(&p.tm_x);
     tma_prefetch_desc(&p.tm_dy);
   }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -343,60 +359,62 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_wgrad_kernel(const __grid_c
       mbar_arrive_expect_tx(&full[st], kSHaloBox + L::DY_BYTES);
       tma_load_4d(smem_base + L::HALO_OFF + st * kSHaloBytes, &p.tm_x, &full[st], 0, tw * kSTileW, th * kSTileH, n);
       // pixels outside the image are zero-filled in dY, so they contribute nothing
-      tma_load_4d(smem_base + L::DY_OFF + st * L::DY_BYTES, &p.tm_dy, &full[st], 0, tw * kSTileW, th * kSTileH, n);
+      tma_load_4d(smem_base + st * L::DY_STAGE + 2048, &p.tm_dy, &full[st], 0, tw * kSTileW, th * kSTileH, n);
     }
   } else if (warp == 4 && elect_one()) {
-    // D_b[co 128 (upper 64 rows duplicate/garbage)][(a,ch) 64] += dY^T . X_shift(b)
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-    const uint32_t a_hi = desc_hi_sw128(1024);            // dY: MN-major, 128B rows, 8-pixel groups
-    const uint32_t b_hi = desc_hi_sw32(kSHaloW * 32);     // halo: 8-pixel groups one image row apart
-    const uint32_t a_lo0 = desc_lo_sw128(smem_base + L::DY_OFF, 16);
-    const uint32_t b_lo0 = desc_lo_sw128(smem_base + L::HALO_OFF, kSHaloW * 32);  // LBO: next a-tap
+    const uint32_t a_hi = desc_hi_sw128(1024);            // dY: MN-major, 128B rows, K groups of 8 pixels = tile rows
+    const uint32_t b_hi = desc_hi_sw32(kSHaloW * 32);     // halo: K groups of 8 pixels one image row apart
     int it = 0;
     for (int t = t0; t < t1; ++t, ++it) {
       const int st = it % ST;
+      const int rem = t % tiles_img;
+      const int jstart = rem < p.tiles_w ? -1 : 0;  // first tile row of an image: the extra K step (see above)
       mbar_wait(&full[st], (it / ST) & 1);
       tc_fence_after();
-      const uint32_t a_lo = a_lo0 + st * (L::DY_BYTES >> 4);
-      const uint32_t b_lo = b_lo0 + st * (kSHaloBytes >> 4);
+      const uint32_t dy0 = smem_base + st * L::DY_STAGE + 2048;
+      const uint32_t halo0 = smem_base + L::HALO_OFF + st * kSHaloBytes;
+      for (int j = jstart; j < 8; ++j) {  // 16 pixels = tile rows 2j, 2j+1 (block 1: 2j+1, 2j+2)
+        const uint32_t a_lo = desc_lo_sw128(dy0 + j * 2048, 1024);  // LBO: the second M block is one tile row further
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {  // 16 pixels = tile rows 2j, 2j+1
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          mma_bf16_ss(tmem_base + b * 64, desc_join(a_lo + j * (2048 >> 4), a_hi),
-                      desc_join(b_lo + (((2 * j * kSHaloW + b) * 32) >> 4), b_hi), idesc, (it | j) != 0 ? 1u : 0u);
+        for (int ai = 0; ai < 2; ++ai) {
+          const int a = 2 * ai + 1;
+          const uint32_t b_lo = desc_lo_sw128(halo0 + (2 * j + a) * (kSHaloW * 32), 32);  // LBO: next column tap b
+          mma_bf16_ss(tmem_base + ai * 64, desc_join(a_lo, a_hi), desc_join(b_lo, b_hi), idesc,
+                      (it != 0 || j != jstart) ? 1u : 0u);
+        }
       }
       mma_commit(&empty[st]);
     }
     mma_commit(tmem_full);
-  } else if (warp < 2) {
-    // rows 0..63 = co
+  } else if (warp < 4) {
+    // row = (block, co): block 0 holds tap row a = 2*ai + 1, block 1 tap row a - 1
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int co = tid;
+    const int blk = tid >> 6, co = tid & 63;
     const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16);
-    float* out = p.partial + (size_t)blockIdx.x * 4 * 64 * 64 + (size_t)co * 64;
-    for (int b = 0; b < 4; ++b) {
+    for (int ai = 0; ai < 2; ++ai) {
+      const int a = 2 * ai + 1 - blk;
+      float* out = p.partial + (size_t)blockIdx.x * 4 * 64 * 64 + ((size_t)a * 64 + co) * 64;
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(trow + b * 64 + c0, r);
+        tmem_ld32(trow + ai * 64 + c0, r);
         tmem_ld_wait();
         if (t1 > t0) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(out + (size_t)b * 64 * 64 + c0 + q * 4) =
-                make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+            *reinterpret_cast<uint4*>(out + c0 + q * 4) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 
-// partial [splits][b][co][a*16+ch] -> dw OIHW [64][C][7][7]
+// partial [splits][a][co][b*16+ch] -> dw OIHW [64][C][7][7]
 __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
                                          int C) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,7 +425,7 @@ __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, floa
   int co = idx / (49 * C);
   int a = r >> 1, dy = r & 1, b = s >> 1, dx = s & 1;
   int ch = (dy * 2 + dx) * C + c;
-  const size_t off = ((size_t)b * 64 + co) * 64 + a * 16 + ch;
+  const size_t off = ((size_t)a * 64 + co) * 64 + b * 16 + ch;
   float acc = 0.f;
   for (int sp = 0; sp < splits; ++sp) acc += partial[(size_t)sp * 4 * 64 * 64 + off];
   dw[idx] = acc;
@@ -529,7 +547,7 @@ extern "C" int gdl_stem_wgrad(const void* x16, const void* dy, float* dw_oihw, i
   GDL_REQUIRE(gdl_stem_geometry(H, W, &Ho, &Wo, &Hp, &Wp) == GDL_OK, "gdl_stem_wgrad: bad shape");
   StemWgradParams p;
   const CUtensorMap* tx = tmap_nhwc16(x16, N, Hp, Wp, kSHaloW, kSHaloH);
-  const CUtensorMap* td = tmap_nhwc(dy, N, Ho, Wo, 64, kSTileW, kSTileH);
+  const CUtensorMap* td = tmap_nhwc(dy, N, Ho, Wo, 64, kSTileW, kSWgDyRows);
   if (!tx || !td) return GDL_ECUDA;
   p.tm_x = *tx; p.tm_dy = *td;
   p.partial = (float*)workspace;

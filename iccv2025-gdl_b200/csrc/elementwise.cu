@@ -982,49 +982,52 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_maxpool_bwd_reduce_kernel(
   block_channel_reduce<2>(acc, C, partial + (size_t)blockIdx.x * 2 * C);
 }
 
-__global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_apply_kernel(
+__global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_apply_kernel(
     const bf16* __restrict__ gpool, const uint8_t* __restrict__ amax, const bf16* __restrict__ x,
     bf16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, float invP,
     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ dgamma,
     const float* __restrict__ dbeta) {
-  __shared__ float s_a[512], s_b[512], s_c[512], s_sc[512], s_sh[512];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = gamma[c] * invstd[c];
-    float b = -a * invstd[c] * dgamma[c] * invP;
-    s_a[c] = a;
-    s_b[c] = b;
-    s_c[c] = -a * dbeta[c] * invP - b * mean[c];
-    s_sc[c] = scale[c];
-    s_sh[c] = shift[c];
-  }
-  __syncthreads();
+  // per-channel coefficients in registers: the grid stride is a multiple of C/8, so a thread keeps its channel group
+  // (the shared-memory tables cost 40 LDS.128 per block); block indices are 32-bit (the launcher checks the range)
   const int groups = C / 8;
-  const int64_t total = (int64_t)N * Ho * Wo * groups;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = first % groups;
+  float ka[8], kb[8], kc[8], sc[8], sh[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ch = cg * 8 + c;
+    const float a = gamma[ch] * invstd[ch];
+    const float b = -a * invstd[ch] * dgamma[ch] * invP;
+    ka[c] = a;
+    kb[c] = b;
+    kc[c] = -a * dbeta[ch] * invP - b * mean[ch];
+    sc[c] = scale[ch];
+    sh[c] = shift[ch];
+  }
+  const int total = N * Ho * Wo * groups;
+  const int stride = gridDim.x * blockDim.x;
+  for (int idx = first; idx < total; idx += stride) {
     {  // L2 prefetch of the four stem pixels of this thread's NEXT iteration (ptxas sinks three of the four
        // x loads of load_block behind the stores; a full iteration of lead hides their DRAM latency)
-      const int64_t idx2 = idx + (int64_t)gridDim.x * blockDim.x;
+      const int idx2 = idx + stride;
       if (idx2 < total) {
-        const int64_t b2 = idx2 / groups;
-        const int cg2 = int(idx2 - b2 * groups);
-        const int j2 = int(b2 % Wo);
-        const int64_t t2 = b2 / Wo;
-        const int i2 = int(t2 % Ho);
-        const bf16* xb = x + (((t2 / Ho) * H + min(2 * i2, H - 1)) * W + min(2 * j2, W - 1)) * C + cg2 * 8;
-        const int64_t dw = 2 * j2 + 1 < W ? C : 0, dh = 2 * i2 + 1 < H ? (int64_t)W * C : 0;
+        const int b2 = idx2 / groups;
+        const int j2 = b2 % Wo;
+        const int t2 = b2 / Wo;
+        const int i2 = t2 % Ho;
+        const bf16* xb = x + (((int64_t)(t2 / Ho) * H + min(2 * i2, H - 1)) * W + min(2 * j2, W - 1)) * C + cg * 8;
+        const int dw = 2 * j2 + 1 < W ? C : 0, dh = 2 * i2 + 1 < H ? W * C : 0;
         prefetch_l2(xb);
         prefetch_l2(xb + dw);
         prefetch_l2(xb + dh);
         prefetch_l2(xb + dh + dw);
       }
     }
-    const int cg = int(idx % groups);
-    const int64_t b = idx / groups;
-    const int j = int(b % Wo);
-    const int64_t t = b / Wo;
-    const int i = int(t % Ho), n = int(t / Ho);
+    const int b = idx / groups;
+    const int j = b % Wo;
+    const int t = b / Wo;
+    const int i = t % Ho, n = t / Ho;
     PoolBlock blk;
     load_block(gpool, amax, x, n, i, j, cg, C, H, W, Ho, Wo, blk);
     float p[4][8];
@@ -1036,9 +1039,8 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_apply_kernel(
       unpack8(blk.xq[q], xv);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const int ch = cg * 8 + c;
-        const float gz = fmaf(xv[c], s_sc[ch], s_sh[ch]) > 0.f ? bf16_round(p[q][c]) : 0.f;
-        o[c] = fmaf(s_a[ch], gz, fmaf(s_b[ch], xv[c], s_c[ch]));
+        const float gz = fmaf(xv[c], sc[c], sh[c]) > 0.f ? bf16_round(p[q][c]) : 0.f;
+        o[c] = fmaf(ka[c], gz, fmaf(kb[c], xv[c], kc[c]));
       }
       if (blk.okq[q]) *reinterpret_cast<uint4*>(dx + off) = pack8(o);
     }
@@ -1269,6 +1271,7 @@ extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax,
   }
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  GDL_REQUIRE(total < ((int64_t)1 << 30), "gdl_bn_relu_maxpool_bwd: too many pooled pixels for 32-bit block indices");
   bn_relu_maxpool_bwd_apply_kernel<<<ew_grid(total, 256, GDL_RESIDENT(bn_relu_maxpool_bwd_apply_kernel, 256)), 256, 0,
                                      (cudaStream_t)s>>>(
       (const bf16*)gpool, argmax, (const bf16*)x, (bf16*)dx, N, H, W, C, Ho, Wo, 1.f / (float)P, gamma, mean, invstd,
