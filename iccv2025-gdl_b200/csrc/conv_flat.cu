@@ -39,6 +39,9 @@ struct FlatTap {
 
 struct FlatParams {
   CUtensorMap tm_x[4];  // {Cs, Ws, Hs, N} views of the source (one per parity plane), box {64, P, 1, 1}
+  CUtensorMap tm_x4[4];    // same views, box {64, P, 4, 1}: four padded rows of one image per TMA operation
+  CUtensorMap tm_ximg[4];  // same views, box {64, P, Hs+1, 1}: a whole padded image (small maps; see use_img)
+  int use_r4, use_img;
   CUtensorMap tm_w;  // {K, rows} packed weights, box {64, BN}
   CUtensorMap tm_w_half;  // CTA-pair kernel: box {64, BN/2} (each CTA of a pair holds one half of every weight tile)
   bf16* dst;
@@ -226,6 +229,46 @@ __device__ __forceinline__ void flat_epilogue_item(const FlatParams& p, int cls,
   }
 }
 
+// Window loader: padded rows [rho, rho + nrows) of the flat grid, row (n, h) at sdst + i * row_bytes.  The producer is
+// ONE thread and pays ~100 clocks per TMA operation, so one-row boxes (1 KB at 7x7) made it the bottleneck wherever a
+// window is many short rows — 7x7 / 9x6 maps, and every stride-2 convolution (four plane windows per slab: measured
+// 32 clocks of MMA per TMA operation there, 27-40 % of the stride-1 rate).  Rows are therefore fetched as whole padded
+// images (box {64, P, Hs+1, 1}: 7x7 .. 17x12 maps) or four-row bands wherever they fit inside one image, single rows
+// otherwise; (n, h) advance incrementally — no division per row.  Rows h == Hs, images n < 0 or n >= N are TMA
+// out-of-bounds zero fill exactly as with one-row boxes.
+template <bool PAIR>
+__device__ __forceinline__ void flat_load_rows(const FlatParams& p, int plane, uint32_t sdst, uint64_t* bar,
+                                               uint32_t bar_cluster, int c0, int n, int h, int nrows,
+                                               uint32_t row_bytes) {
+  const int rows_img = p.Hs + 1;
+  auto issue = [&](const CUtensorMap* m) {
+    if (PAIR)
+      tma2_load_4d(sdst, m, bar_cluster, c0, 0, h, n);
+    else
+      tma_load_4d(sdst, m, bar, c0, 0, h, n);
+  };
+  while (nrows > 0) {
+    int took;
+    if (p.use_img && h == 0 && nrows >= rows_img) {
+      issue(&p.tm_ximg[plane]);
+      took = rows_img;
+    } else if (p.use_r4 && nrows >= 4 && h + 4 <= rows_img) {
+      issue(&p.tm_x4[plane]);
+      took = 4;
+    } else {
+      issue(&p.tm_x[plane]);
+      took = 1;
+    }
+    sdst += took * row_bytes;
+    nrows -= took;
+    h += took;
+    if (h >= rows_img) {
+      h = 0;
+      ++n;
+    }
+  }
+}
+
 // RES: the whole packed weight matrix of the layer (taps x slabs tiles of BN x 64) is loaded ONCE per CTA and stays in
 // shared memory (64 -> 64 channel 3x3 layers: 9 tiles = 72 KB), instead of being streamed from L2 for every 256-pixel
 // item: the weight ring is 2/3 of the L2 -> SM traffic of those layers.  One class, one channel tile.
@@ -311,20 +354,15 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
       const int rho_a = floor_div(q0 + p.smin, p.P);
       const int rho_b = floor_div(q0 + TM + p.smax - 1, p.P);
       const int nrows = rho_b - rho_a + 1;
+      const int n_a = floor_div(rho_a, rows_img), h_a = rho_a - n_a * rows_img;
       const int ngrp = p.ngroups[cls];
       for (int slab = 0; slab < slabs; ++slab) {
         for (int g = 0; g < ngrp; ++g, ++wincount) {
           const int ws = wincount % WS;
           if (wincount >= WS) mbar_wait(&win_empty[ws], ((wincount / WS) - 1) & 1);
           mbar_arrive_expect_tx(&win_full[ws], (uint32_t)nrows * row_bytes);
-          const uint32_t sdst = smem_base + ws * p.win_stage_bytes;
-          const CUtensorMap* tmx = &p.tm_x[p.gplane[cls][g]];
-          for (int i = 0; i < nrows; ++i) {
-            const int rho = rho_a + i;
-            const int n = floor_div(rho, rows_img);
-            const int h = rho - n * rows_img;
-            tma_load_4d(sdst + i * row_bytes, tmx, &win_full[ws], slab * 64, 0, h, n);
-          }
+          flat_load_rows<false>(p, p.gplane[cls][g], smem_base + ws * p.win_stage_bytes, &win_full[ws], 0u, slab * 64,
+                                n_a, h_a, nrows, row_bytes);
           if (!RES)
             for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
               const int st = wcount % WST;
@@ -531,6 +569,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
       const int rho_b = floor_div(q0 + TM + p.smax - 1, p.P);
       const int nrows = rho_b - rho_a + 1;
       const int o = q0 + p.smin - rho_a * p.P;  // phase of the window's first pixel inside its first padded row
+      const int n_a = floor_div(rho_a, rows_img), h_a = rho_a - n_a * rows_img;
       const int ngrp = p.ngroups[cls];
       for (int slab = 0; slab < slabs; ++slab) {
         for (int g = 0; g < ngrp; ++g, ++wincount) {
@@ -539,13 +578,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
           const uint32_t full = mapa_u32(smem_u32(&win_full[ws]), 0);
           mbar_arrive_expect_tx_cluster(full, (uint32_t)nrows * row_bytes);
           const uint32_t sdst = smem_base + ws * p.win_stage_bytes + (uint32_t)(p.P - 1 - o) * 128u;
-          const CUtensorMap* tmx = &p.tm_x[p.gplane[cls][g]];
-          for (int i = 0; i < nrows; ++i) {
-            const int rho = rho_a + i;
-            const int n = floor_div(rho, rows_img);
-            const int h = rho - n * rows_img;
-            tma2_load_4d(sdst + i * row_bytes, tmx, full, slab * 64, 0, h, n);
-          }
+          flat_load_rows<true>(p, p.gplane[cls][g], sdst, nullptr, full, slab * 64, n_a, h_a, nrows, row_bytes);
           for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
             const int st = wcount % WST;
             if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
@@ -849,21 +882,35 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
       if (p.taps[c][t].shift > p.smax) p.smax = p.taps[c][t].shift;
     }
   const int BN = (Cd % 128 == 0) ? 128 : 64;
+  // GDL_FLAT_ROWBOX (default 3): bit 0 = four-row boxes, bit 1 = whole-image boxes for maps of at most 32 KB per slab
+  static const int rowbox = env_int3("GDL_FLAT_ROWBOX", 3);
+  const int rows_img = Hs + 1;
+  p.use_r4 = (rowbox & 1) && rows_img >= 4;
+  p.use_img = (rowbox & 2) && rows_img <= 256 && (int64_t)rows_img * P * 128 <= 32 * 1024;
+  auto views = [&](const void* base, int w, int h, int64_t vW, int64_t vH, int idx) -> bool {
+    const CUtensorMap* t = tmap_view4(base, Cs, w, h, N, vW, vH, sN, P);
+    if (!t) return false;
+    p.tm_x[idx] = *t;
+    if (p.use_r4) {
+      if (!(t = tmap_view4(base, Cs, w, h, N, vW, vH, sN, P, 4))) return false;
+      p.tm_x4[idx] = *t;
+    }
+    if (p.use_img) {
+      if (!(t = tmap_view4(base, Cs, w, h, N, vW, vH, sN, P, rows_img))) return false;
+      p.tm_ximg[idx] = *t;
+    }
+    return true;
+  };
   if (kind == 4) {
     const int Wi = int(sH / Cs), Hi = int(sN / sH);
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
         const int ph = (Hi - a + 1) / 2, pw = (Wi - b + 1) / 2;
         if (ph <= 0 || pw <= 0) return 0;
-        const CUtensorMap* t =
-            tmap_view4((const bf16*)src + ((int64_t)a * Wi + b) * Cs, Cs, pw, ph, N, 2 * (int64_t)Cs, 2 * sH, sN, P);
-        if (!t) return GDL_ECUDA;
-        p.tm_x[a * 2 + b] = *t;
+        if (!views((const bf16*)src + ((int64_t)a * Wi + b) * Cs, pw, ph, 2 * (int64_t)Cs, 2 * sH, a * 2 + b)) return GDL_ECUDA;
       }
   } else {
-    const CUtensorMap* tx = tmap_view4(src, Cs, Ws, Hs, N, sW, sH, sN, P);
-    if (!tx) return GDL_ECUDA;
-    p.tm_x[0] = *tx;
+    if (!views(src, Ws, Hs, sW, sH, 0)) return GDL_ECUDA;
   }
   const CUtensorMap* tw = tmap_rows(wt, wt_rows, wt_k, BN);
   if (!tw) return GDL_ECUDA;
