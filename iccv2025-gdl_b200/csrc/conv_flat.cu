@@ -489,7 +489,10 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
 //   empty barriers (window / weights / accumulator-ready): one per CTA, released by tcgen05.commit.cta_group::2
 //                  multicast to both
 //   tmem_empty     : in the leader, 8 arrivals (one per epilogue warp of both CTAs, remote arrive from the peer)
-template <int BN, int MT, int WST, bool STATS>
+//   RES: as in the single-CTA kernel, the layer's whole packed weight matrix stays in shared memory — each CTA of the
+//   pair keeps ITS HALF of every tile (64 -> 64 channel 3x3 layers: 9 x 4 KB) — so the N = 64 layers get both remedies
+//   for their shared-memory-bandwidth bound: no weight ring traffic and 5 KB instead of 6 KB of operands per MMA.
+template <int BN, int MT, int WST, bool STATS, bool RES = false>
 __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __grid_constant__ FlatParams p) {
   constexpr int HB = BN / 2;
   constexpr int W_BYTES = HB * 128;
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int w_off = p.win_stages * p.win_stage_bytes;
-  const int bar_off = w_off + WST * W_BYTES;
+  const int bar_off = w_off + (RES ? p.res_tiles : WST) * W_BYTES;
   uint64_t* win_full = reinterpret_cast<uint64_t*>(smem + bar_off);
   uint64_t* win_empty = win_full + kMaxWin;
   uint64_t* w_full = win_empty + kMaxWin;
@@ -561,6 +564,14 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
     const int rows_img = p.Hs + 1;
     const uint32_t row_bytes = (uint32_t)p.P * 128u;
     int wincount = 0, wcount = 0;
+    if (RES) {  // this CTA's half of tile (slab, tap) at index slab * ntaps + tap; one barrier (in the leader) for all
+      const uint32_t wfull = mapa_u32(smem_u32(&w_full[0]), 0);
+      mbar_arrive_expect_tx_cluster(wfull, (uint32_t)p.res_tiles * W_BYTES);
+      for (int slab = 0; slab < slabs; ++slab)
+        for (int t = 0; t < p.ntaps[0]; ++t)
+          tma2_load_2d(smem_base + w_off + (slab * p.ntaps[0] + t) * W_BYTES, &p.tm_w_half, wfull,
+                       p.taps[0][t].wk + slab * 64, rank * HB);
+    }
     for (int item = item_first; item < items_total; item += item_stride) {
       int cls, nt, q0;
       tile_of(item, cls, nt, q0);
@@ -579,6 +590,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
           mbar_arrive_expect_tx_cluster(full, (uint32_t)nrows * row_bytes);
           const uint32_t sdst = smem_base + ws * p.win_stage_bytes + (uint32_t)(p.P - 1 - o) * 128u;
           flat_load_rows<true>(p, p.gplane[cls][g], sdst, nullptr, full, slab * 64, n_a, h_a, nrows, row_bytes);
+          if (!RES)
           for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
             const int st = wcount % WST;
             if (wcount >= WST) mbar_wait(&w_empty[st], ((wcount / WST) - 1) & 1);
@@ -599,6 +611,10 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
     const uint32_t ab_hi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo_sw128(smem_base, 16), b_lo0 = desc_lo_sw128(smem_base + w_off, 16);
     int wincount = 0, wcount = 0, it = 0;
+    if (RES) {
+      mbar_wait(&w_full[0], 0);
+      tc_fence_after();
+    }
     for (int item = item_first; item < items_total; item += item_stride, ++it) {
       const int cls = item / per_class;
       const int acc = it & 1;
@@ -616,9 +632,11 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
           // pixel q0 + shift sits (P - 1 + shift - smin) pixel rows into the stage, in both CTAs
           const uint32_t a_win = a_lo0 + ((ws * p.win_stage_bytes) >> 4) + (p.P - 1 - p.smin) * 8;
           for (int t = p.gtap0[cls][g]; t < p.gtap0[cls][g + 1]; ++t, ++wcount) {
-            const int st = wcount % WST;
-            mbar_wait(&w_full[st], (wcount / WST) & 1);
-            tc_fence_after();
+            const int st = RES ? slab * p.ntaps[0] + t : wcount % WST;
+            if (!RES) {
+              mbar_wait(&w_full[st], (wcount / WST) & 1);
+              tc_fence_after();
+            }
             const uint32_t a_lo = a_win + p.taps[cls][t].shift * 8;
             const uint32_t b_lo = b_lo0 + st * (W_BYTES >> 4);
             const uint32_t first = (slab | t) != 0 ? 1u : 0u;
@@ -630,7 +648,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
                 mma2_bf16_acc(d_tmem + j * BN, desc_join(a_lo + j * 1024 + 2 * k, ab_hi),
                               desc_join(b_lo + 2 * k, ab_hi), idesc);
             }
-            mma2_commit_both(&w_empty[st]);
+            if (!RES) mma2_commit_both(&w_empty[st]);
           }
           mma2_commit_both(&win_empty[ws]);
         }
@@ -724,14 +742,18 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
 }
 
 // CTA-pair kernel: p.tm_w_half must hold the {64, BN/2} weight map.  Returns 0 when not eligible.
-template <int BN, int MT, int WST>
+template <int BN, int MT, int WST, bool RES = false>
 static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   constexpr int TM = MT * 128;
+  if (RES) {
+    if (p.nclass != 1 || p.Cd != BN || p.ngroups[0] != 1) return 0;
+    p.res_tiles = p.ntaps[0] * (p.Cs / 64);
+  }
   const int nrows_max = (TM + p.smax - p.smin - 1 + p.P - 1) / p.P + 1;
   // + P-1 pixel rows: both CTAs of a pair start their window at the same offset whatever its phase in the padded row
   p.win_stage_bytes = ((nrows_max * p.P + p.P - 1) * 128 + 1023) / 1024 * 1024;
   const bool st = p.stats != nullptr;
-  const int fixed = WST * (BN / 2) * 128 + 512 + (st ? kStatScratchBytes : 0);
+  const int fixed = (RES ? p.res_tiles : WST) * (BN / 2) * 128 + 512 + (st ? kStatScratchBytes : 0);
   int ws = (kFlatSmemBudget - fixed) / p.win_stage_bytes;
   if (ws > 4) ws = 4;
   if (ws < 2) return 0;
@@ -743,10 +765,10 @@ static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   if (total < kFlatSmemFloor) total = kFlatSmemFloor;  // sole TMEM user of its SM (see launch_flat)
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_flat2_kernel<BN, MT, WST, false>,
+    cudaError_t e = cudaFuncSetAttribute(conv_flat2_kernel<BN, MT, WST, false, RES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_flat2_kernel<BN, MT, WST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(conv_flat2_kernel<BN, MT, WST, true, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_flat2)");
     attr_set = true;
@@ -767,8 +789,8 @@ static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   g_flat_last_grid = grid2;
-  cudaError_t e = st ? cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST, true>, p)
-                     : cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST, false>, p);
+  cudaError_t e = st ? cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST, true, RES>, p)
+                     : cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST, false, RES>, p);
   if (e != cudaSuccess) return cuda_fail(e, "conv_flat2_kernel");
   return 1;
 }
@@ -950,7 +972,15 @@ int try_conv_flat(int kind, int N, int Hs, int Ws, int Cs, int64_t sW, int64_t s
     // resident-weights kernel does not apply (e.g. the 128 -> 64 channel stride-2 data gradients), 0 = off.
     static const int pair64 = env_int3("GDL_FLAT_PAIR64", 2);
     const bool res_ok = resident && mt == 2 && Cs == 64 && Cd == 64 && (kind == 0 || kind == 1);
-    if (pair && pair64 && pair_wins && !mt_force && !(pair64 == 2 && res_ok)) {
+    // GDL_FLAT_PAIR64RES (default 1): CTA pair AND resident weights for the 64 -> 64 channel 3x3 layers
+    static const int pair64res = env_int3("GDL_FLAT_PAIR64RES", 1);
+    if (pair && pair64res && pair_wins && !mt_force && res_ok) {
+      const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
+      if (!th) return GDL_ECUDA;
+      p.tm_w_half = *th;
+      rc = launch_flat2<64, 2, 8, true>(p, Q, s);
+    }
+    if (rc == 0 && pair && pair64 && pair_wins && !mt_force && !(pair64 == 2 && res_ok)) {
       const CUtensorMap* th = tmap_rows(wt, wt_rows, wt_k, BN / 2);
       if (!th) return GDL_ECUDA;
       p.tm_w_half = *th;
