@@ -29,10 +29,11 @@ constexpr int kGemmW = 128;  // the GEMM row index is folded into an (H, 128) "i
 
 // C[m][n] = sum over splits of partial[sp][m][n] (+ bias[n]); fixed order => deterministic
 __global__ void gemm_tn_reduce_kernel(const float* __restrict__ partial, int splits, int64_t MN, int N,
-                                      const float* __restrict__ bias, float* __restrict__ C) {
+                                      const float* __restrict__ bias, float* __restrict__ C, int accumulate) {
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= MN) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // accumulate: C already holds the sum over the earlier K chunks (launch order = summation order: deterministic)
+  float4 acc = accumulate ? *reinterpret_cast<const float4*>(C + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int sp = 0; sp < splits; ++sp) {
     const float4 v = *reinterpret_cast<const float4*>(partial + (size_t)sp * MN + i);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -56,15 +57,16 @@ __global__ void film_transpose_feat_kernel(const float* __restrict__ a, const fl
     vt[idx] = b < B ? v[(int64_t)b * D + i] : 0.f;
   }
 }
+// Rows [f0, f0 + nf) of the feature-major matrix are written to Zt[0 .. nf) (a K chunk: see gdl_film_outer_chunk).
 __global__ void __launch_bounds__(256) film_outer_kernel(const float* __restrict__ at, const float* __restrict__ vt,
                                                          bf16* __restrict__ Zt, int B, int D, int ZB, int Bp,
-                                                         int variants) {
+                                                         int variants, int64_t f0, int64_t nf) {
   const int groups = ZB / 8;
-  const int64_t total = (int64_t)D * D * groups;
+  const int64_t total = nf * groups;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int g = int(idx % groups);
-    const int64_t f = idx / groups;
+    const int64_t fl = idx / groups, f = f0 + fl;
     const int i = int(f / D), j = int(f - (int64_t)i * D);
     const float* ai = at + (int64_t)i * Bp;
     const float* aj = at + (int64_t)j * Bp;
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(256) film_outer_kernel(const float* __restrict
       if (var < variants) val = var == 0 ? ai[b] * vj[b] : (var == 1 ? ai[b] * aj[b] : vi[b] * vj[b]);
       o[c] = val;
     }
-    *reinterpret_cast<uint4*>(Zt + f * ZB + g * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(Zt + fl * ZB + g * 8) = pack8(o);
   }
 }
 
@@ -108,33 +110,41 @@ __global__ void cast_pad_kernel(const float* __restrict__ src0, int r0, const fl
 // batch columns (one 16-byte load per G row) and one of KS interleaved k slices; slices are combined in a
 // fixed order through shared memory.  xt / yt are the features transposed to [D][Bp].
 constexpr int kContractThreads = 256;
+// G holds the rows of i in [i0, i0 + ni) only (row (i - i0)*D + j): block t adds its part of both contractions to the
+// outputs — dx[b][t] (+)= sum_j G[(t - i0)*D + j] y[b][j] when t lies in the chunk (complete: all j are in the chunk),
+// dy[b][t] (+)= sum_{i in chunk} G[(i - i0)*D + t] x[b][i] — the first chunk writes (acc = 0), the later ones add
+// (launch order = summation order: deterministic).  Whole matrix: i0 = 0, ni = D, acc = 0.
 __global__ void __launch_bounds__(kContractThreads) film_contract_kernel(
     const bf16* __restrict__ G, int ldg, int c0, const float* __restrict__ xt, const float* __restrict__ yt,
-    float* __restrict__ dx, float* __restrict__ dy, int B, int D, int Bp, int sum_mode) {
+    float* __restrict__ dx, float* __restrict__ dy, int B, int D, int Bp, int sum_mode, int i0, int ni, int acc) {
   __shared__ float red[2][kContractThreads][8];
   const int t = blockIdx.x;
   const int bgroups = B / 8;                       // vector path only
   const int KS = kContractThreads / bgroups;       // k slices
   const int bq = threadIdx.x % bgroups, ks = threadIdx.x / bgroups;
+  const bool own = t >= i0 && t < i0 + ni;
   float sx[8], sy[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) sx[c] = sy[c] = 0.f;
   if (ks < KS) {
-    for (int k = ks; k < D; k += KS) {
-      float g1[8], g2[8];
-      unpack8(ld_stream16(G + ((int64_t)t * D + k) * ldg + c0 + bq * 8), g1);
+    if (own)
+      for (int k = ks; k < D; k += KS) {
+        float g1[8];
+        unpack8(ld_stream16(G + ((int64_t)(t - i0) * D + k) * ldg + c0 + bq * 8), g1);
+        const float4 y0 = *reinterpret_cast<const float4*>(yt + (int64_t)k * Bp + bq * 8);
+        const float4 y1 = *reinterpret_cast<const float4*>(yt + (int64_t)k * Bp + bq * 8 + 4);
+        const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sx[c] = fmaf(g1[c], yv[c], sx[c]);
+      }
+    for (int k = ks; k < ni; k += KS) {
+      float g2[8];
       unpack8(ld_stream16(G + ((int64_t)k * D + t) * ldg + c0 + bq * 8), g2);
-      const float4 y0 = *reinterpret_cast<const float4*>(yt + (int64_t)k * Bp + bq * 8);
-      const float4 y1 = *reinterpret_cast<const float4*>(yt + (int64_t)k * Bp + bq * 8 + 4);
-      const float4 x0 = *reinterpret_cast<const float4*>(xt + (int64_t)k * Bp + bq * 8);
-      const float4 x1 = *reinterpret_cast<const float4*>(xt + (int64_t)k * Bp + bq * 8 + 4);
-      const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      const float4 x0 = *reinterpret_cast<const float4*>(xt + (int64_t)(i0 + k) * Bp + bq * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(xt + (int64_t)(i0 + k) * Bp + bq * 8 + 4);
       const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        sx[c] = fmaf(g1[c], yv[c], sx[c]);
-        sy[c] = fmaf(g2[c], xv[c], sy[c]);
-      }
+      for (int c = 0; c < 8; ++c) sy[c] = fmaf(g2[c], xv[c], sy[c]);
     }
   }
 #pragma unroll
@@ -152,57 +162,66 @@ __global__ void __launch_bounds__(kContractThreads) film_contract_kernel(
         ay += red[1][s2 * bgroups + bq][c];
       }
       const int b = bq * 8 + c;
+      float* px = dx + (int64_t)b * D + t;
       if (sum_mode) {
-        dx[(int64_t)b * D + t] = ax + ay;
+        *px = acc ? *px + (ax + ay) : ax + ay;
       } else {
-        dx[(int64_t)b * D + t] = ax;
-        dy[(int64_t)b * D + t] = ay;
+        float* py = dy + (int64_t)b * D + t;
+        if (!acc || own) *px = acc ? *px + ax : ax;  // ax == 0 outside the chunk
+        *py = acc ? *py + ay : ay;
       }
     }
   }
 }
-// scalar path for batches that are not a multiple of 8
+// scalar path for batches that are not a multiple of 8 (same chunk semantics)
 __global__ void __launch_bounds__(256) film_contract_scalar_kernel(const bf16* __restrict__ G, int ldg, int c0,
                                                                    const float* __restrict__ xt,
                                                                    const float* __restrict__ yt, float* __restrict__ dx,
                                                                    float* __restrict__ dy, int B, int D, int Bp,
-                                                                   int sum_mode) {
+                                                                   int sum_mode, int i0, int ni, int acc) {
   const int t = blockIdx.x;
+  const bool own = t >= i0 && t < i0 + ni;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     float sx = 0.f, sy = 0.f;
     const bf16* gcol = G + c0 + b;
-    for (int k = 0; k < D; ++k) {
-      sx = fmaf(__bfloat162float(gcol[((int64_t)t * D + k) * ldg]), yt[(int64_t)k * Bp + b], sx);
-      sy = fmaf(__bfloat162float(gcol[((int64_t)k * D + t) * ldg]), xt[(int64_t)k * Bp + b], sy);
-    }
+    if (own)
+      for (int k = 0; k < D; ++k)
+        sx = fmaf(__bfloat162float(gcol[((int64_t)(t - i0) * D + k) * ldg]), yt[(int64_t)k * Bp + b], sx);
+    for (int k = 0; k < ni; ++k)
+      sy = fmaf(__bfloat162float(gcol[((int64_t)k * D + t) * ldg]), xt[(int64_t)(i0 + k) * Bp + b], sy);
+    float* px = dx + (int64_t)b * D + t;
     if (sum_mode) {
-      dx[(int64_t)b * D + t] = sx + sy;
+      *px = acc ? *px + (sx + sy) : sx + sy;
     } else {
-      dx[(int64_t)b * D + t] = sx;
-      dy[(int64_t)b * D + t] = sy;
+      float* py = dy + (int64_t)b * D + t;
+      if (!acc || own) *px = acc ? *px + sx : sx;
+      *py = acc ? *py + sy : sy;
     }
   }
 }
 
 // 32x32 tiled transposes between the fp32 parameter layout [R][Cn] and the bf16 feature-major shadow [Cn][R]
-__global__ void transpose_f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int64_t Cn) {
+// src is a column window of a row-major fp32 matrix with row stride lds: src[r][c] = src[r * lds + c], c in [0, Cn)
+__global__ void transpose_f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int64_t Cn,
+                                             int64_t lds) {
   __shared__ float tile[32][33];
   const int64_t c0 = (int64_t)blockIdx.x * 32;
   const int r0 = blockIdx.y * 32;
-  for (int k = threadIdx.y; k < 32; k += 8) tile[k][threadIdx.x] = src[(int64_t)(r0 + k) * Cn + c0 + threadIdx.x];
+  for (int k = threadIdx.y; k < 32; k += 8) tile[k][threadIdx.x] = src[(int64_t)(r0 + k) * lds + c0 + threadIdx.x];
   __syncthreads();
   for (int k = threadIdx.y; k < 32; k += 8)
     dst[(c0 + k) * R + r0 + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x][k]);
 }
-__global__ void transpose_bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int R, int64_t Cn) {
-  // src [Cn][R] -> dst [R][Cn]
+__global__ void transpose_bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int R, int64_t Cn,
+                                             int64_t ldd) {
+  // src [Cn][R] -> dst [R][Cn] inside a row-major matrix with row stride ldd
   __shared__ float tile[32][33];
   const int64_t c0 = (int64_t)blockIdx.x * 32;
   const int r0 = blockIdx.y * 32;
   for (int k = threadIdx.y; k < 32; k += 8)
     tile[k][threadIdx.x] = __bfloat162float(src[(c0 + k) * R + r0 + threadIdx.x]);
   __syncthreads();
-  for (int k = threadIdx.y; k < 32; k += 8) dst[(int64_t)(r0 + k) * Cn + c0 + threadIdx.x] = tile[threadIdx.x][k];
+  for (int k = threadIdx.y; k < 32; k += 8) dst[(int64_t)(r0 + k) * ldd + c0 + threadIdx.x] = tile[threadIdx.x][k];
 }
 
 }  // namespace gdl
@@ -231,8 +250,8 @@ extern "C" int64_t gdl_gemm_tn_workspace_bytes(int M, int N, int64_t K) {
   return b > 0 ? b : GDL_EINVAL;
 }
 
-extern "C" int gdl_gemm_tn_f32(const void* At, const void* Bt, const float* bias, float* C, int M, int N, int64_t K,
-                               void* workspace, int64_t workspace_bytes, gdl_stream_t s) {
+static int gemm_tn_impl(const void* At, const void* Bt, const float* bias, float* C, int M, int N, int64_t K,
+                        void* workspace, int64_t workspace_bytes, int accumulate, gdl_stream_t s) {
   GDL_REQUIRE(At && Bt && C && workspace, "gdl_gemm_tn_f32: null pointer");
   GDL_REQUIRE(K > 0 && K % kGemmW == 0 && N % 4 == 0, "gdl_gemm_tn_f32: need K % 128 == 0");
   const int H = int(K / kGemmW);
@@ -245,9 +264,19 @@ extern "C" int gdl_gemm_tn_f32(const void* At, const void* Bt, const float* bias
   }
   const int64_t MN = (int64_t)M * N;
   gemm_tn_reduce_kernel<<<(unsigned)ceil_div64(MN / 4, 256), 256, 0, (cudaStream_t)s>>>((const float*)workspace, ns, MN,
-                                                                                      N, bias, C);
+                                                                                      N, bias, C, accumulate);
   GDL_CHECK_LAUNCH("gemm_tn_reduce_kernel");
   return GDL_OK;
+}
+
+extern "C" int gdl_gemm_tn_f32(const void* At, const void* Bt, const float* bias, float* C, int M, int N, int64_t K,
+                               void* workspace, int64_t workspace_bytes, gdl_stream_t s) {
+  return gemm_tn_impl(At, Bt, bias, C, M, N, K, workspace, workspace_bytes, 0, s);
+}
+
+extern "C" int gdl_gemm_tn_f32_acc(const void* At, const void* Bt, float* C, int M, int N, int64_t K, void* workspace,
+                                   int64_t workspace_bytes, gdl_stream_t s) {
+  return gemm_tn_impl(At, Bt, nullptr, C, M, N, K, workspace, workspace_bytes, 1, s);
 }
 
 static int film_bp(int B) { return (B + 7) / 8 * 8; }
@@ -262,21 +291,34 @@ static int film_transpose(const float* a, const float* v, float* scratch, int B,
   return GDL_OK;
 }
 
-extern "C" int gdl_film_outer(const float* a, const float* v, void* Zt, int B, int D, int ZB, int variants,
-                              float* scratch, gdl_stream_t s) {
+static int film_outer_impl(const float* a, const float* v, void* Zt, int B, int D, int ZB, int variants, float* scratch,
+                           int64_t f0, int64_t nf, bool transpose, gdl_stream_t s) {
   GDL_REQUIRE(a && v && Zt && scratch && B > 0 && D > 0 && ZB % 8 == 0 && variants >= 1 && variants <= 3 &&
-                  variants * B <= ZB,
+                  variants * B <= ZB && f0 >= 0 && nf > 0 && f0 + nf <= (int64_t)D * D,
               "gdl_film_outer: bad arguments");
-  int rc = film_transpose(a, v, scratch, B, D, (cudaStream_t)s);
-  if (rc != GDL_OK) return rc;
+  if (transpose) {
+    int rc = film_transpose(a, v, scratch, B, D, (cudaStream_t)s);
+    if (rc != GDL_OK) return rc;
+  }
   const int Bp = film_bp(B);
-  const int64_t total = (int64_t)D * D * (ZB / 8);
+  const int64_t total = nf * (ZB / 8);
   int64_t blocks = ceil_div64(total, 256);
   if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
   film_outer_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(scratch, scratch + (int64_t)D * Bp, (bf16*)Zt, B, D, ZB,
-                                                                  Bp, variants);
+                                                                  Bp, variants, f0, nf);
   GDL_CHECK_LAUNCH("film_outer_kernel");
   return GDL_OK;
+}
+
+extern "C" int gdl_film_outer(const float* a, const float* v, void* Zt, int B, int D, int ZB, int variants,
+                              float* scratch, gdl_stream_t s) {
+  return film_outer_impl(a, v, Zt, B, D, ZB, variants, scratch, 0, (int64_t)D * D, true, s);
+}
+
+extern "C" int gdl_film_outer_chunk(const float* a, const float* v, void* Zt_chunk, int B, int D, int ZB, int variants,
+                                    float* scratch, int64_t f0, int64_t nf, gdl_stream_t s) {
+  // the transposed features in scratch are (re)built by the chunk that starts at feature 0
+  return film_outer_impl(a, v, Zt_chunk, B, D, ZB, variants, scratch, f0, nf, f0 == 0, s);
 }
 
 extern "C" int gdl_cast_pad_bf16(const float* src0, int r0, const float* src1, int r1, int cols, int ld, int transpose,
@@ -292,28 +334,44 @@ extern "C" int gdl_cast_pad_bf16(const float* src0, int r0, const float* src1, i
   return GDL_OK;
 }
 
-extern "C" int gdl_film_contract(const void* G, int ldg, int c0, const float* x, const float* y, float* dx, float* dy,
-                                 int B, int D, int sum_mode, float* scratch, gdl_stream_t s) {
-  GDL_REQUIRE(G && x && y && dx && scratch && (sum_mode || dy) && B > 0 && D > 0, "gdl_film_contract: bad arguments");
-  int rc = film_transpose(x, y, scratch, B, D, (cudaStream_t)s);
-  if (rc != GDL_OK) return rc;
+static int film_contract_impl(const void* G, int ldg, int c0, const float* x, const float* y, float* dx, float* dy, int B,
+                              int D, int sum_mode, float* scratch, int i0, int ni, int acc, bool transpose,
+                              gdl_stream_t s) {
+  GDL_REQUIRE(G && x && y && dx && scratch && (sum_mode || dy) && B > 0 && D > 0 && i0 >= 0 && ni > 0 && i0 + ni <= D,
+              "gdl_film_contract: bad arguments");
+  if (transpose) {
+    int rc = film_transpose(x, y, scratch, B, D, (cudaStream_t)s);
+    if (rc != GDL_OK) return rc;
+  }
   const int Bp = film_bp(B);
   const float* xt = scratch;
   const float* yt = scratch + (int64_t)D * Bp;
   if (B % 8 == 0 && c0 % 8 == 0 && ldg % 8 == 0 && B / 8 <= kContractThreads)
     film_contract_kernel<<<D, kContractThreads, 0, (cudaStream_t)s>>>((const bf16*)G, ldg, c0, xt, yt, dx, dy, B, D, Bp,
-                                                                     sum_mode);
+                                                                     sum_mode, i0, ni, acc);
   else
     film_contract_scalar_kernel<<<D, 256, 0, (cudaStream_t)s>>>((const bf16*)G, ldg, c0, xt, yt, dx, dy, B, D, Bp,
-                                                                sum_mode);
+                                                                sum_mode, i0, ni, acc);
   GDL_CHECK_LAUNCH("film_contract_kernel");
   return GDL_OK;
+}
+
+extern "C" int gdl_film_contract(const void* G, int ldg, int c0, const float* x, const float* y, float* dx, float* dy,
+                                 int B, int D, int sum_mode, float* scratch, gdl_stream_t s) {
+  return film_contract_impl(G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch, 0, D, 0, true, s);
+}
+
+extern "C" int gdl_film_contract_chunk(const void* G_chunk, int ldg, int c0, const float* x, const float* y, float* dx,
+                                       float* dy, int B, int D, int sum_mode, float* scratch, int i0, int ni,
+                                       int accumulate, int rebuild_scratch, gdl_stream_t s) {
+  return film_contract_impl(G_chunk, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch, i0, ni, accumulate != 0,
+                            rebuild_scratch != 0, s);
 }
 
 extern "C" int gdl_transpose_f32_to_bf16(const float* src, void* dst, int R, int64_t Cn, gdl_stream_t s) {
   GDL_REQUIRE(src && dst && R % 32 == 0 && Cn % 32 == 0, "gdl_transpose_f32_to_bf16: dims must be multiples of 32");
   dim3 grid((unsigned)(Cn / 32), R / 32), block(32, 8);
-  transpose_f32_to_bf16_kernel<<<grid, block, 0, (cudaStream_t)s>>>(src, (bf16*)dst, R, Cn);
+  transpose_f32_to_bf16_kernel<<<grid, block, 0, (cudaStream_t)s>>>(src, (bf16*)dst, R, Cn, Cn);
   GDL_CHECK_LAUNCH("transpose_f32_to_bf16_kernel");
   return GDL_OK;
 }
@@ -321,7 +379,18 @@ extern "C" int gdl_transpose_f32_to_bf16(const float* src, void* dst, int R, int
 extern "C" int gdl_transpose_bf16_to_f32(const void* src, float* dst, int R, int64_t Cn, gdl_stream_t s) {
   GDL_REQUIRE(src && dst && R % 32 == 0 && Cn % 32 == 0, "gdl_transpose_bf16_to_f32: dims must be multiples of 32");
   dim3 grid((unsigned)(Cn / 32), R / 32), block(32, 8);
-  transpose_bf16_to_f32_kernel<<<grid, block, 0, (cudaStream_t)s>>>((const bf16*)src, dst, R, Cn);
+  transpose_bf16_to_f32_kernel<<<grid, block, 0, (cudaStream_t)s>>>((const bf16*)src, dst, R, Cn, Cn);
   GDL_CHECK_LAUNCH("transpose_bf16_to_f32_kernel");
+  return GDL_OK;
+}
+
+// Column window [c0, c0 + Cn) of the fp32 matrix dst [R][ldd] from the bf16 chunk src [Cn][R] (K-chunked FiLM weight gradient)
+extern "C" int gdl_transpose_bf16_to_f32_window(const void* src, float* dst, int R, int64_t Cn, int64_t ldd, int64_t c0,
+                                                gdl_stream_t s) {
+  GDL_REQUIRE(src && dst && R % 32 == 0 && Cn % 32 == 0 && c0 >= 0 && c0 + Cn <= ldd,
+              "gdl_transpose_bf16_to_f32_window: bad arguments");
+  dim3 grid((unsigned)(Cn / 32), R / 32), block(32, 8);
+  transpose_bf16_to_f32_kernel<<<grid, block, 0, (cudaStream_t)s>>>((const bf16*)src, dst + c0, R, Cn, ldd);
+  GDL_CHECK_LAUNCH("transpose_bf16_to_f32_kernel(window)");
   return GDL_OK;
 }

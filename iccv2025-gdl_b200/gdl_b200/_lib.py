@@ -72,12 +72,16 @@ SIGNATURES = {
     "gdl_gemm_nt_bf16": (_i, [_p, _l, _p, _p, _l, _i, _i, _p]),
     "gdl_gemm_tn_workspace_bytes": (_l, [_i, _i, _l]),
     "gdl_gemm_tn_f32": (_i, [_p, _p, _p, _p, _i, _i, _l, _p, _l, _p]),
+    "gdl_gemm_tn_f32_acc": (_i, [_p, _p, _p, _i, _i, _l, _p, _l, _p]),
     "gdl_film_scratch_floats": (_l, [_i, _i]),
     "gdl_film_outer": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "gdl_film_outer_chunk": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _l, _l, _p]),
     "gdl_cast_pad_bf16": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p]),
     "gdl_film_contract": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "gdl_film_contract_chunk": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
     "gdl_transpose_f32_to_bf16": (_i, [_p, _p, _i, _l, _p]),
     "gdl_transpose_bf16_to_f32": (_i, [_p, _p, _i, _l, _p]),
+    "gdl_transpose_bf16_to_f32_window": (_i, [_p, _p, _i, _l, _l, _l, _p]),
     "gdl_maxpool_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "gdl_maxpool_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "gdl_gap_fwd": (_i, [_p, _p, _i, _i, _i, _p]),

@@ -405,6 +405,13 @@ def gemm_tn_f32(At, Bt, bias, Cm, M, N, K, ws):
                                       ws.numel() * ws.element_size(), _stream()), "gdl_gemm_tn_f32")
 
 
+@_op("gemm_tn", 2, lambda At, Bt, Cm, M, N, K, ws: ("flops", 2.0 * M * N * K))
+def gemm_tn_f32_acc(At, Bt, Cm, M, N, K, ws):
+    """C += At^T * Bt: a later K chunk of a reduction started by gemm_tn_f32."""
+    check(_lib.load().gdl_gemm_tn_f32_acc(_ptr(At), _ptr(Bt), _ptr(Cm), M, N, K, _ptr(ws),
+                                          ws.numel() * ws.element_size(), _stream()), "gdl_gemm_tn_f32_acc")
+
+
 def film_scratch_floats(B, D):
     return int(_lib.load().gdl_film_scratch_floats(B, D))
 
@@ -413,6 +420,12 @@ def film_scratch_floats(B, D):
 def film_outer(a, v, Zt, B, D, ZB, variants, scratch):
     check(_lib.load().gdl_film_outer(_ptr(a), _ptr(v), _ptr(Zt), B, D, ZB, variants, _ptr(scratch), _stream()),
           "gdl_film_outer")
+
+
+@_op("film_outer", 1, lambda a, v, Zt, B, D, ZB, variants, scratch, f0, nf: ("bytes", 2.0 * nf * ZB))
+def film_outer_chunk(a, v, Zt, B, D, ZB, variants, scratch, f0, nf):
+    check(_lib.load().gdl_film_outer_chunk(_ptr(a), _ptr(v), _ptr(Zt), B, D, ZB, variants, _ptr(scratch), f0, nf,
+                                           _stream()), "gdl_film_outer_chunk")
 
 
 @_op("cast_pad", 1)
@@ -425,6 +438,19 @@ def cast_pad_bf16(src0, r0, src1, r1, cols, ld, transpose, dst, drows, dcols):
 def film_contract(G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch):
     check(_lib.load().gdl_film_contract(_ptr(G), ldg, c0, _ptr(x), _ptr(y), _ptr(dx), _ptr(dy), B, D,
                                         int(sum_mode), _ptr(scratch), _stream()), "gdl_film_contract")
+
+
+@_op("film_contract", 1, lambda G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch, i0, ni, acc, rebuild: ("bytes", 4.0 * ni * D * B))
+def film_contract_chunk(G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch, i0, ni, acc, rebuild):
+    check(_lib.load().gdl_film_contract_chunk(_ptr(G), ldg, c0, _ptr(x), _ptr(y), _ptr(dx), _ptr(dy), B, D,
+                                              int(sum_mode), _ptr(scratch), i0, ni, int(acc), int(rebuild), _stream()),
+          "gdl_film_contract_chunk")
+
+
+@_op("transpose", 1, lambda src, dst, R, Cn, ldd, c0: ("bytes", 6.0 * R * Cn))
+def transpose_bf16_to_f32_window(src, dst, R, Cn, ldd, c0):
+    check(_lib.load().gdl_transpose_bf16_to_f32_window(_ptr(src), _ptr(dst), R, Cn, ldd, c0, _stream()),
+          "gdl_transpose_bf16_to_f32_window")
 
 
 @_op("transpose", 1, lambda src, dst, R, Cn: ("bytes", 6.0 * R * Cn))

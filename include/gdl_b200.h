@@ -271,11 +271,18 @@ int gdl_gemm_nt_bf16(const void* A, int64_t lda, const void* B, void* C, int64_t
 int64_t gdl_gemm_tn_workspace_bytes(int M, int N, int64_t K);
 int gdl_gemm_tn_f32(const void* At, const void* Bt, const float* bias, float* C, int M, int N, int64_t K,
                     void* workspace, int64_t workspace_bytes, gdl_stream_t s);
+/* Same, C += (a later K chunk of a reduction started by gdl_gemm_tn_f32; chunk order = summation order). */
+int gdl_gemm_tn_f32_acc(const void* At, const void* Bt, float* C, int M, int N, int64_t K, void* workspace,
+                        int64_t workspace_bytes, gdl_stream_t s);
 /* Zt bf16 [D*D][ZB]: column b of variant 0 = a_b (x) v_b, variant 1 = a_b (x) a_b, variant 2 = v_b (x) v_b
  * (columns var*B + b; the rest zero).  a, v f32 [B][D]. */
 int64_t gdl_film_scratch_floats(int B, int D); /* scratch of gdl_film_outer / gdl_film_contract */
 int gdl_film_outer(const float* a, const float* v, void* Zt, int B, int D, int ZB, int variants, float* scratch,
                    gdl_stream_t s);
+/* K-chunked form (the fused step never holds the whole 262144-row Zt): rows [f0, f0 + nf) of Zt into Zt_chunk[0 .. nf).
+ * The chunk with f0 == 0 (re)builds the transposed features in scratch; run it first. */
+int gdl_film_outer_chunk(const float* a, const float* v, void* Zt_chunk, int B, int D, int ZB, int variants,
+                         float* scratch, int64_t f0, int64_t nf, gdl_stream_t s);
 /* dst bf16 [drows][dcols], zero padded, from f32 rows [src0 (r0 rows); src1 (r1 rows)] of `cols` columns
  * (row stride ld); transpose != 0 writes dst[c][r]. */
 int gdl_cast_pad_bf16(const float* src0, int r0, const float* src1, int r1, int cols, int ld, int transpose,
@@ -284,9 +291,17 @@ int gdl_cast_pad_bf16(const float* src0, int r0, const float* src1, int r1, int 
  * sum_mode != 0: dx <- dx + dy (x == y), dy untouched. */
 int gdl_film_contract(const void* G, int ldg, int c0, const float* x, const float* y, float* dx, float* dy,
                       int B, int D, int sum_mode, float* scratch, gdl_stream_t s);
+/* K-chunked form: G_chunk holds the rows of i in [i0, i0 + ni) only (row (i - i0)*D + j).  accumulate == 0 (first
+ * chunk) writes dx / dy, accumulate != 0 adds to them; rebuild_scratch != 0 re-transposes x, y into scratch. */
+int gdl_film_contract_chunk(const void* G_chunk, int ldg, int c0, const float* x, const float* y, float* dx, float* dy,
+                            int B, int D, int sum_mode, float* scratch, int i0, int ni, int accumulate,
+                            int rebuild_scratch, gdl_stream_t s);
 /* fp32 [R][Cn] <-> bf16 [Cn][R] (the feature-major shadow of fc.weight and its gradient). */
 int gdl_transpose_f32_to_bf16(const float* src, void* dst, int R, int64_t Cn, gdl_stream_t s);
 int gdl_transpose_bf16_to_f32(const void* src, float* dst, int R, int64_t Cn, gdl_stream_t s);
+/* bf16 chunk [Cn][R] -> columns [c0, c0 + Cn) of the fp32 matrix dst [R][ldd]. */
+int gdl_transpose_bf16_to_f32_window(const void* src, float* dst, int R, int64_t Cn, int64_t ldd, int64_t c0,
+                                     gdl_stream_t s);
 
 /* ---- FP32 check mode (north_star: "1e-4 with an FP32-accumulate check mode") -------------------------------
  * The encoder ops once more with fp32-STORED activations in the reference's own layout (NCHW activations, OIHW
