@@ -127,24 +127,38 @@ __global__ void __launch_bounds__(kContractThreads) film_contract_kernel(
 #pragma unroll
   for (int c = 0; c < 8; ++c) sx[c] = sy[c] = 0.f;
   if (ks < KS) {
-    if (own)
-      for (int k = ks; k < D; k += KS) {
-        float g1[8];
-        unpack8(ld_stream16(G + ((int64_t)(t - i0) * D + k) * ldg + c0 + bq * 8), g1);
-        const float4 y0 = *reinterpret_cast<const float4*>(yt + (int64_t)k * Bp + bq * 8);
-        const float4 y1 = *reinterpret_cast<const float4*>(yt + (int64_t)k * Bp + bq * 8 + 4);
-        const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    // four G rows in flight per thread (the loop is a chain of L2 / DRAM latencies otherwise)
+    auto fma8 = [&](const uint4& gu, const float* f, float (&acc)[8]) {
+      float g[8];
+      unpack8(gu, g);
+      const float4 f0 = *reinterpret_cast<const float4*>(f), f1 = *reinterpret_cast<const float4*>(f + 4);
+      const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sx[c] = fmaf(g1[c], yv[c], sx[c]);
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(g[c], fv[c], acc[c]);
+    };
+    if (own) {
+      const bf16* g0 = G + (int64_t)(t - i0) * D * ldg + c0 + bq * 8;
+      int k = ks;
+      for (; k + 3 * KS < D; k += 4 * KS) {
+        uint4 u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[q] = ld_stream16(g0 + (int64_t)(k + q * KS) * ldg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) fma8(u[q], yt + (int64_t)(k + q * KS) * Bp + bq * 8, sx);
       }
-    for (int k = ks; k < ni; k += KS) {
-      float g2[8];
-      unpack8(ld_stream16(G + ((int64_t)k * D + t) * ldg + c0 + bq * 8), g2);
-      const float4 x0 = *reinterpret_cast<const float4*>(xt + (int64_t)(i0 + k) * Bp + bq * 8);
-      const float4 x1 = *reinterpret_cast<const float4*>(xt + (int64_t)(i0 + k) * Bp + bq * 8 + 4);
-      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      for (; k < D; k += KS) fma8(ld_stream16(g0 + (int64_t)k * ldg), yt + (int64_t)k * Bp + bq * 8, sx);
+    }
+    {
+      const bf16* g0 = G + (int64_t)t * ldg + c0 + bq * 8;
+      int k = ks;
+      for (; k + 3 * KS < ni; k += 4 * KS) {
+        uint4 u[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) sy[c] = fmaf(g2[c], xv[c], sy[c]);
+        for (int q = 0; q < 4; ++q) u[q] = ld_stream16(g0 + (int64_t)(k + q * KS) * D * ldg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) fma8(u[q], xt + (int64_t)(i0 + k + q * KS) * Bp + bq * 8, sy);
+      }
+      for (; k < ni; k += KS) fma8(ld_stream16(g0 + (int64_t)k * D * ldg), xt + (int64_t)(i0 + k) * Bp + bq * 8, sy);
     }
   }
 #pragma unroll

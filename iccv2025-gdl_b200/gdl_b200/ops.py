@@ -422,7 +422,8 @@ def film_outer(a, v, Zt, B, D, ZB, variants, scratch):
           "gdl_film_outer")
 
 
-@_op("film_outer", 1, lambda a, v, Zt, B, D, ZB, variants, scratch, f0, nf: ("bytes", 2.0 * nf * ZB))
+@_op("film_outer", lambda a, v, Zt, B, D, ZB, variants, scratch, f0, nf: 2 if f0 == 0 else 1,
+     lambda a, v, Zt, B, D, ZB, variants, scratch, f0, nf: ("bytes", 2.0 * nf * ZB))
 def film_outer_chunk(a, v, Zt, B, D, ZB, variants, scratch, f0, nf):
     check(_lib.load().gdl_film_outer_chunk(_ptr(a), _ptr(v), _ptr(Zt), B, D, ZB, variants, _ptr(scratch), f0, nf,
                                            _stream()), "gdl_film_outer_chunk")
@@ -440,7 +441,8 @@ def film_contract(G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch):
                                         int(sum_mode), _ptr(scratch), _stream()), "gdl_film_contract")
 
 
-@_op("film_contract", 1, lambda G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch, i0, ni, acc, rebuild: ("bytes", 4.0 * ni * D * B))
+@_op("film_contract", lambda G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch, i0, ni, acc, rebuild: 2 if rebuild else 1,
+     lambda G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch, i0, ni, acc, rebuild: ("bytes", 4.0 * ni * D * B))
 def film_contract_chunk(G, ldg, c0, x, y, dx, dy, B, D, sum_mode, scratch, i0, ni, acc, rebuild):
     check(_lib.load().gdl_film_contract_chunk(_ptr(G), ldg, c0, _ptr(x), _ptr(y), _ptr(dx), _ptr(dy), B, D,
                                               int(sum_mode), _ptr(scratch), i0, ni, int(acc), int(rebuild), _stream()),
