@@ -445,6 +445,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
 // Multi-tensor variant: one launch refreshes the bf16 shadows of a whole encoder (reference
 // main_dgl.py:154 optimizer.step() is followed by nothing — the shadows are this library's own state).
 __global__ void pack_weights_multi_kernel(const gdl_pack_entry* __restrict__ tab, int n, int64_t total) {
+  pdl_enter();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int lo = 0, hi = n - 1;  // last entry with start <= idx
@@ -476,6 +477,7 @@ __global__ void pack_weights_multi_kernel(const gdl_pack_entry* __restrict__ tab
 // coalesced fp32 reads (64*R*S contiguous floats per co), 128-byte runs into wp[co][tap][ci], 64-byte runs into
 // wT[ci][tap][co].  blockIdx.y = table entry, blockIdx.x = tile (CTAs beyond the entry's tile count exit).
 __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const gdl_pack_entry* __restrict__ tab) {
+  pdl_enter();
   extern __shared__ bf16 s_tile[];  // [32 co][RS][64 ci + 2 pad] (row stride 33 words: the transposed read is conflict-free)
   constexpr int LD = 66;
   const gdl_pack_entry e = tab[blockIdx.y];
@@ -530,6 +532,7 @@ struct TapSplits {
 template <int G>
 __global__ void __launch_bounds__(256) wgrad_reduce_t_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                              const TapSplits ts, int Kp, int Co, int Ci, int taps) {
+  pdl_enter();
   constexpr int OB = 256 / G;  // outputs per block
   __shared__ float red[G > 1 ? 256 : 1];
   const int o = threadIdx.x % OB, g = threadIdx.x / OB;
@@ -570,6 +573,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_t_kernel(const float* __rest
 constexpr int kRedCB = 128;
 __global__ void __launch_bounds__(256) wgrad_reduce_tile_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                                 const TapSplits ts, int Kp, int Co, int Ci, int taps) {
+  pdl_enter();
   __shared__ float tile[9][kRedCB + 1];
   const int co = blockIdx.y, ci0 = blockIdx.x * kRedCB;
   const size_t total = (size_t)Co * Kp;
@@ -603,16 +607,16 @@ static int launch_wgrad_reduce_t(const float* partial, float* dw, int splits, co
   const int64_t total = (int64_t)Co * Kp;
   const bool many_splits = (total < 400000 && splits >= 16) || (total < 800000 && splits >= 8);
   if (!many_splits && Ci % kRedCB == 0 && taps <= 9 && Kp == taps * Ci && Co <= 65535) {
-    wgrad_reduce_tile_kernel<<<dim3(Ci / kRedCB, Co), 256, 0, s>>>(partial, dw, ts, Kp, Co, Ci, taps);
+    launch_pdl(wgrad_reduce_tile_kernel, dim3(Ci / kRedCB, Co), 256, 0, s, partial, dw, ts, Kp, Co, Ci, taps);
     GDL_CHECK_LAUNCH("wgrad_reduce_tile_kernel");
     return GDL_OK;
   }
   if (total < 400000 && splits >= 16) {
-    wgrad_reduce_t_kernel<8><<<(unsigned)ceil_div64(total, 32), 256, 0, s>>>(partial, dw, ts, Kp, Co, Ci, taps);
+    launch_pdl(wgrad_reduce_t_kernel<8>, (unsigned)ceil_div64(total, 32), 256, 0, s, partial, dw, ts, Kp, Co, Ci, taps);
   } else if (total < 800000 && splits >= 8) {
-    wgrad_reduce_t_kernel<4><<<(unsigned)ceil_div64(total, 64), 256, 0, s>>>(partial, dw, ts, Kp, Co, Ci, taps);
+    launch_pdl(wgrad_reduce_t_kernel<4>, (unsigned)ceil_div64(total, 64), 256, 0, s, partial, dw, ts, Kp, Co, Ci, taps);
   } else {
-    wgrad_reduce_t_kernel<1><<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(partial, dw, ts, Kp, Co, Ci, taps);
+    launch_pdl(wgrad_reduce_t_kernel<1>, (unsigned)ceil_div64(total, 256), 256, 0, s, partial, dw, ts, Kp, Co, Ci, taps);
   }
   GDL_CHECK_LAUNCH("wgrad_reduce_t_kernel");
   return GDL_OK;
@@ -844,7 +848,7 @@ extern "C" int gdl_conv_pack_weights_tiled(const gdl_pack_entry* table_dev, int 
                                            gdl_stream_t s) {
   GDL_REQUIRE(table_dev && n > 0 && max_tiles > 0 && max_rs > 0 && max_rs <= 9, "gdl_conv_pack_weights_tiled: bad arguments");
   const size_t smem = (size_t)32 * max_rs * 66 * sizeof(bf16);
-  pack_weights_tiled_kernel<<<dim3(max_tiles, n), 256, smem, (cudaStream_t)s>>>(table_dev);
+  launch_pdl(pack_weights_tiled_kernel, dim3(max_tiles, n), 256, smem, (cudaStream_t)s, table_dev);
   GDL_CHECK_LAUNCH("pack_weights_tiled_kernel");
   return GDL_OK;
 }
@@ -853,7 +857,7 @@ extern "C" int gdl_conv_pack_weights_multi(const gdl_pack_entry* table_dev, int 
   GDL_REQUIRE(table_dev && n > 0 && total > 0, "gdl_conv_pack_weights_multi: bad arguments");
   int64_t blocks = ceil_div64(total, 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  pack_weights_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(table_dev, n, total);
+  launch_pdl(pack_weights_multi_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)s, table_dev, n, total);
   GDL_CHECK_LAUNCH("pack_weights_multi_kernel");
   return GDL_OK;
 }

@@ -277,6 +277,7 @@ __device__ __forceinline__ void flat_load_rows(const FlatParams& p, int plane, u
 // receives and reads the whole tile — and was removed; the CTA-pair kernel below splits the tile instead.)
 template <int BN, int MT, int WST, bool STATS, bool RES = false>
 __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid_constant__ FlatParams p) {
+  pdl_launch_dependents();  // the next kernel may start its prologue now (common.cuh: PDL)
   constexpr int W_BYTES = BN * 128;
   constexpr int TM = MT * 128;
   constexpr int kMaxWin = 4;
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
     tma_prefetch_desc(&p.tm_x[0]);
     tma_prefetch_desc(&p.tm_w);
   }
+  pdl_wait();  // everything above touched only shared memory / TMEM / kernel parameters
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -494,6 +496,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat_kernel(const __grid
 //   for their shared-memory-bandwidth bound: no weight ring traffic and 5 KB instead of 6 KB of operands per MMA.
 template <int BN, int MT, int WST, bool STATS, bool RES = false>
 __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __grid_constant__ FlatParams p) {
+  pdl_launch_dependents();  // the next kernel may start its prologue now (common.cuh: PDL)
   constexpr int HB = BN / 2;
   constexpr int W_BYTES = HB * 128;
   constexpr int TM = MT * 128;
@@ -544,6 +547,7 @@ __global__ void __launch_bounds__(kFlatThreads, 1) conv_flat2_kernel(const __gri
     tma_prefetch_desc(&p.tm_x[0]);
     tma_prefetch_desc(&p.tm_w_half);
   }
+  pdl_wait();  // everything above touched only shared memory / TMEM / kernel parameters
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit / remote complete_tx
@@ -734,9 +738,9 @@ static int launch_flat(FlatParams& p, int64_t Q, cudaStream_t s) {
   int grid = p.items_total < kNumSMs ? p.items_total : kNumSMs;
   g_flat_last_grid = grid;
   if (st)
-    conv_flat_kernel<BN, MT, WST, true, RES><<<grid, kFlatThreads, total, s>>>(p);
+    launch_pdl(conv_flat_kernel<BN, MT, WST, true, RES>, grid, kFlatThreads, total, s, p);
   else
-    conv_flat_kernel<BN, MT, WST, false, RES><<<grid, kFlatThreads, total, s>>>(p);
+    launch_pdl(conv_flat_kernel<BN, MT, WST, false, RES>, grid, kFlatThreads, total, s, p);
   GDL_CHECK_LAUNCH("conv_flat_kernel");
   return 1;
 }
@@ -781,13 +785,15 @@ static int launch_flat2(FlatParams& p, int64_t Q, cudaStream_t s) {
   cfg.blockDim = dim3(kFlatThreads);
   cfg.dynamicSmemBytes = total;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   g_flat_last_grid = grid2;
   cudaError_t e = st ? cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST, true, RES>, p)
                      : cudaLaunchKernelEx(&cfg, conv_flat2_kernel<BN, MT, WST, false, RES>, p);

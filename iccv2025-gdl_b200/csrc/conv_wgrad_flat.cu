@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
   const int type = y % p.ntypes;
   const int t0 = min(blockIdx.x * p.tps[type], p.tiles_total);
   const int t1 = min(t0 + p.tps[type], p.tiles_total);
+  pdl_launch_dependents();  // the next kernel may start its prologue now (common.cuh: PDL)
   if (t0 >= t1) return;  // this type has fewer splits than the grid is wide (whole CTA, before any setup)
   y /= p.ntypes;
   const int co0 = (y % p.co_tiles) * BN;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
     tma_prefetch_desc(&p.tm_dy);
   }
   fence_proxy_async();
+  pdl_wait();  // everything above touched only shared memory / TMEM / kernel parameters
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -422,7 +424,7 @@ static int launch_wf(const WfParams& p, const WfPlan& w, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(w.splits, w.gy);
-  conv_wgrad_flat_kernel<BN, MODE><<<grid, kWfThreads, w.stages * w.stage_bytes + 512 + 1024, s>>>(p);
+  launch_pdl(conv_wgrad_flat_kernel<BN, MODE>, grid, kWfThreads, w.stages * w.stage_bytes + 512 + 1024, s, p);
   GDL_CHECK_LAUNCH("conv_wgrad_flat_kernel");
   return GDL_OK;
 }

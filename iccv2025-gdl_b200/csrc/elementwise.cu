@@ -148,6 +148,7 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int 
                                          const float* __restrict__ beta, float eps, float momentum,
                                          float* running_mean, float* running_var, float* mean_out,
                                          float* invstd_out, float* scale, float* shift) {
+  pdl_enter();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
                                                        bf16* __restrict__ y, int64_t nvec, int C,
                                                        const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int relu, int rev) {
+  pdl_enter();
   const int groups = C / 8;
   const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = fixed_channel_group(first, nvec, groups, rev);
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     const bf16* dy, const bf16* __restrict__ y, const bf16* __restrict__ x, bf16* dz, int64_t P, int C,
     float* __restrict__ partial, int relu, int rev) {
+  pdl_enter();
   const int groups = C / 8;
   const int lanes = kBnThreads / groups;
   const int cg = threadIdx.x % groups;
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     int C, float invP, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ dgamma,
     const float* __restrict__ dbeta, int rev) {
+  pdl_enter();
   // dx = a*dz + b*x + c  with  a = gamma*invstd,  b = -a*invstd*dgamma/P,
   //                            c = -a*dbeta/P - b*mean          (per channel, in registers: see fixed_channel_group)
   const int groups = C / 8;
@@ -456,6 +460,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict
 __global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_nores_reduce_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, int64_t P, int C, const float* __restrict__ scale,
     const float* __restrict__ shift, float* __restrict__ partial, int rev) {
+  pdl_enter();
   const int groups = C / 8;
   const int lanes = kBnThreads / groups;
   const int cg = threadIdx.x % groups;
@@ -504,6 +509,7 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_bwd_nores_reduce_kernel(
 __global__ void bn_bwd_finalize_raw_kernel(const float* __restrict__ partial, int nblk, int C,
                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_enter();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -525,6 +531,7 @@ __global__ void __launch_bounds__(256) bn_bwd_nores_apply_kernel(
     float invP, const float* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int rev) {
+  pdl_enter();
   const int groups = C / 8;
   const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = fixed_channel_group(first, nvec, groups, rev);
@@ -778,6 +785,7 @@ __global__ void __launch_bounds__(256, 3) bn_relu_maxpool_fwd3_kernel(
     const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
     bf16* __restrict__ y, uint8_t* __restrict__ amax, bf16* __restrict__ xmax, int N, int H, int W, int C, int Ho,
     int Wo, int nseg, int rev) {
+  pdl_enter();
   __shared__ int s_tapoff[16];  // element offset of tap (r,s) from the window's top-left pixel
   if (threadIdx.x < 9) s_tapoff[threadIdx.x] = ((threadIdx.x / 3) * W + threadIdx.x % 3) * C;
   __syncthreads();
@@ -988,6 +996,7 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_apply_kernel(
     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ dgamma,
     const float* __restrict__ dbeta) {
+  pdl_enter();
   // per-channel coefficients in registers: the grid stride is a multiple of C/8, so a thread keeps its channel group
   // (the shared-memory tables cost 40 LDS.128 per block); block indices are 32-bit (the launcher checks the range)
   const int groups = C / 8;
@@ -1052,6 +1061,7 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_apply_kernel(
 // ------------------------------------------------------------------------------------------
 __global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ out, int B, int G,
                                int C) {
+  pdl_enter();
   const int groups = C / 8;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * groups) return;
@@ -1074,6 +1084,7 @@ __global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ o
 
 __global__ void gap_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ dx, int B, int G,
                                int C) {
+  pdl_enter();
   const int groups = C / 8;
   const int64_t total = (int64_t)B * G * groups;
   const float inv = 1.f / (float)G;
@@ -1125,8 +1136,7 @@ extern "C" int gdl_bn_stats(const void* x, int64_t P, int C, float* partial, con
   int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_stats_kernel, kBnThreads));
   bn_stats_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)x, P, C, partial, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_stats_kernel");
-  bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(
-      partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
+  launch_pdl(bn_stats_finalize_kernel, (C * 32 + 255) / 256, 256, 0, (cudaStream_t)s, partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
   GDL_CHECK_LAUNCH("bn_stats_finalize_kernel");
   return GDL_OK;
 }
@@ -1137,8 +1147,7 @@ extern "C" int gdl_bn_stats_finalize(const float* partial, int rows, int64_t P, 
                                      gdl_stream_t s) {
   GDL_REQUIRE(chan_ok(C) && P > 0 && rows > 0, "gdl_bn_stats_finalize: bad shape");
   GDL_REQUIRE(partial && gamma && beta && mean && invstd && scale && shift, "gdl_bn_stats_finalize: null pointer");
-  bn_stats_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(
-      partial, rows, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
+  launch_pdl(bn_stats_finalize_kernel, (C * 32 + 255) / 256, 256, 0, (cudaStream_t)s, partial, rows, P, C, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
   GDL_CHECK_LAUNCH("bn_stats_finalize_kernel");
   return GDL_OK;
 }
@@ -1158,7 +1167,7 @@ extern "C" int gdl_bn_apply(const void* x, const void* res, void* y, int64_t P, 
   GDL_REQUIRE(chan_ok(C) && P > 0, "gdl_bn_apply: bad shape");
   GDL_REQUIRE(x && y && scale && shift, "gdl_bn_apply: null pointer");
   int64_t nvec = P * C / 8;
-  bn_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>((const bf16*)x, (const bf16*)res,
+  launch_pdl(bn_apply_kernel, ew_grid(nvec, 256, GDL_RESIDENT(bn_apply_kernel, 256)), 256, 0, (cudaStream_t)s, (const bf16*)x, (const bf16*)res,
                                                                   (bf16*)y, nvec, C, scale, shift, relu, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_apply_kernel");
   return GDL_OK;
@@ -1172,16 +1181,14 @@ extern "C" int gdl_bn_bwd(const void* dy, const void* y, const void* x, void* dz
   GDL_REQUIRE(dy && x && dx && gamma && mean && invstd && partial && dgamma && dbeta, "gdl_bn_bwd: null pointer");
   GDL_REQUIRE(!relu || (y && dz), "gdl_bn_bwd: relu needs y and dz");
   int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_bwd_reduce_kernel, kBnThreads));
-  bn_bwd_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>(
-      (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, partial, relu, g_sweep_rev);
+  launch_pdl(bn_bwd_reduce_kernel, nblk, kBnThreads, 0, (cudaStream_t)s, (const bf16*)dy, (const bf16*)y, (const bf16*)x, (bf16*)dz, P, C, partial, relu, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_reduce_kernel");
-  bn_bwd_finalize_raw_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, mean, invstd, dgamma,
+  launch_pdl(bn_bwd_finalize_raw_kernel, (C * 32 + 255) / 256, 256, 0, (cudaStream_t)s, partial, nblk, C, mean, invstd, dgamma,
                                                                                dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_raw_kernel");
   int64_t nvec = P * C / 8;
   const bf16* dzp = relu ? (const bf16*)dz : (const bf16*)dy;
-  bn_bwd_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
-      dzp, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, dgamma, dbeta, !g_sweep_rev);
+  launch_pdl(bn_bwd_apply_kernel, ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_apply_kernel, 256)), 256, 0, (cudaStream_t)s, dzp, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, dgamma, dbeta, !g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return GDL_OK;
 }
@@ -1193,15 +1200,14 @@ extern "C" int gdl_bn_bwd_nores(const void* dy, const void* x, void* dx, int64_t
   GDL_REQUIRE(dy && x && dx && gamma && mean && invstd && scale && shift && partial && dgamma && dbeta,
               "gdl_bn_bwd_nores: null pointer");
   int nblk = bn_blocks_cap(P, C, GDL_RESIDENT(bn_bwd_nores_reduce_kernel, kBnThreads));
-  bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)dy, (const bf16*)x, P, C, scale,
+  launch_pdl(bn_bwd_nores_reduce_kernel, nblk, kBnThreads, 0, (cudaStream_t)s, (const bf16*)dy, (const bf16*)x, P, C, scale,
                                                                       shift, partial, g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_nores_reduce_kernel");
-  bn_bwd_finalize_raw_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, mean, invstd, dgamma,
+  launch_pdl(bn_bwd_finalize_raw_kernel, (C * 32 + 255) / 256, 256, 0, (cudaStream_t)s, partial, nblk, C, mean, invstd, dgamma,
                                                                                dbeta);
   GDL_CHECK_LAUNCH("bn_bwd_finalize_raw_kernel");
   int64_t nvec = P * C / 8;
-  bn_bwd_nores_apply_kernel<<<ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_nores_apply_kernel, 256)), 256, 0, (cudaStream_t)s>>>(
-      (const bf16*)dy, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, scale, shift, dgamma,
+  launch_pdl(bn_bwd_nores_apply_kernel, ew_grid(nvec, 256, GDL_RESIDENT(bn_bwd_nores_apply_kernel, 256)), 256, 0, (cudaStream_t)s, (const bf16*)dy, (const bf16*)x, (bf16*)dx, nvec, C, 1.f / (float)P, gamma, mean, invstd, scale, shift, dgamma,
       dbeta, !g_sweep_rev);
   GDL_CHECK_LAUNCH("bn_bwd_nores_apply_kernel");
   return GDL_OK;
@@ -1221,8 +1227,7 @@ extern "C" int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const 
   if (variant >= 3 && (int64_t)N * H * W * C < ((int64_t)1 << 31)) {  // 32-bit indexing inside the kernel
     const int nseg = (Ho + kTailSeg - 1) / kTailSeg;
     int64_t total3 = (int64_t)N * nseg * Wo * (C / 8);
-    bn_relu_maxpool_fwd3_kernel<<<ew_grid(total3, 256, GDL_RESIDENT(bn_relu_maxpool_fwd3_kernel, 256)), 256, 0,
-                                  (cudaStream_t)s>>>((const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H,
+    launch_pdl(bn_relu_maxpool_fwd3_kernel, ew_grid(total3, 256, GDL_RESIDENT(bn_relu_maxpool_fwd3_kernel, 256)), 256, 0, (cudaStream_t)s, (const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H,
                                                      W, C, Ho, Wo, nseg, g_sweep_rev);
     GDL_CHECK_LAUNCH("bn_relu_maxpool_fwd3_kernel");
     return GDL_OK;
@@ -1257,10 +1262,10 @@ extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax,
     // whose conv output the forward saved — the no-residual BN reduce kernel on (gpool, xmax)
     const int64_t Pp = (int64_t)N * Ho * Wo;
     nblk = bn_blocks_cap(Pp, C, GDL_RESIDENT(bn_bwd_nores_reduce_kernel, kBnThreads));
-    bn_bwd_nores_reduce_kernel<<<nblk, kBnThreads, 0, (cudaStream_t)s>>>((const bf16*)gpool, (const bf16*)xmax, Pp, C,
+    launch_pdl(bn_bwd_nores_reduce_kernel, nblk, kBnThreads, 0, (cudaStream_t)s, (const bf16*)gpool, (const bf16*)xmax, Pp, C,
                                                                         scale, shift, partial, g_sweep_rev);
     GDL_CHECK_LAUNCH("bn_bwd_nores_reduce_kernel(stem tail)");
-    bn_bwd_finalize_raw_kernel<<<(C * 32 + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, nblk, C, mean, invstd, dgamma,
+    launch_pdl(bn_bwd_finalize_raw_kernel, (C * 32 + 255) / 256, 256, 0, (cudaStream_t)s, partial, nblk, C, mean, invstd, dgamma,
                                                                                  dbeta);
   } else {
     nblk = bn_blocks_cap((int64_t)N * Ho * Wo * 4, C, GDL_RESIDENT(bn_relu_maxpool_bwd_reduce_kernel, kBnThreads));
@@ -1272,9 +1277,7 @@ extern "C" int gdl_bn_relu_maxpool_bwd(const void* gpool, const uint8_t* argmax,
   GDL_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
   GDL_REQUIRE(total < ((int64_t)1 << 30), "gdl_bn_relu_maxpool_bwd: too many pooled pixels for 32-bit block indices");
-  bn_relu_maxpool_bwd_apply_kernel<<<ew_grid(total, 256, GDL_RESIDENT(bn_relu_maxpool_bwd_apply_kernel, 256)), 256, 0,
-                                     (cudaStream_t)s>>>(
-      (const bf16*)gpool, argmax, (const bf16*)x, (bf16*)dx, N, H, W, C, Ho, Wo, 1.f / (float)P, gamma, mean, invstd,
+  launch_pdl(bn_relu_maxpool_bwd_apply_kernel, ew_grid(total, 256, GDL_RESIDENT(bn_relu_maxpool_bwd_apply_kernel, 256)), 256, 0, (cudaStream_t)s, (const bf16*)gpool, argmax, (const bf16*)x, (bf16*)dx, N, H, W, C, Ho, Wo, 1.f / (float)P, gamma, mean, invstd,
       scale, shift, dgamma, dbeta);
   GDL_CHECK_LAUNCH("bn_relu_maxpool_bwd_apply_kernel");
   return GDL_OK;
@@ -1305,7 +1308,7 @@ extern "C" int gdl_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, 
 extern "C" int gdl_gap_fwd(const void* x, float* out, int B, int G, int C, gdl_stream_t s) {
   GDL_REQUIRE(x && out && B > 0 && G > 0 && C % 8 == 0, "gdl_gap_fwd: bad arguments");
   int64_t total = (int64_t)B * (C / 8);
-  gap_fwd_kernel<<<(unsigned)ceil_div64(total, 128), 128, 0, (cudaStream_t)s>>>((const bf16*)x, out, B, G, C);
+  launch_pdl(gap_fwd_kernel, (unsigned)ceil_div64(total, 128), 128, 0, (cudaStream_t)s, (const bf16*)x, out, B, G, C);
   GDL_CHECK_LAUNCH("gap_fwd_kernel");
   return GDL_OK;
 }
@@ -1313,7 +1316,7 @@ extern "C" int gdl_gap_fwd(const void* x, float* out, int B, int G, int C, gdl_s
 extern "C" int gdl_gap_bwd(const float* dout, void* dx, int B, int G, int C, gdl_stream_t s) {
   GDL_REQUIRE(dout && dx && B > 0 && G > 0 && C % 8 == 0, "gdl_gap_bwd: bad arguments");
   int64_t total = (int64_t)B * G * (C / 8);
-  gap_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)s>>>(dout, (bf16*)dx, B, G, C);
+  launch_pdl(gap_bwd_kernel, ew_grid(total, 256), 256, 0, (cudaStream_t)s, dout, (bf16*)dx, B, G, C);
   GDL_CHECK_LAUNCH("gap_bwd_kernel");
   return GDL_OK;
 }

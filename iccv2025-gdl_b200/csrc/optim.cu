@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kOptThreads) grad_stats_kernel(
     const float* __restrict__ grad, int64_t numel, const int64_t* __restrict__ seg_end,
     const int32_t* __restrict__ seg_group, const float* __restrict__ seg_inv_numel, int nseg,
     float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float red[32];
   __shared__ int s_lo, s_hi;
   const int64_t start = (int64_t)blockIdx.x * kChunk;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(kOptThreads) grad_stats_kernel(
 
 __global__ void grad_stats_finalize_kernel(const float* __restrict__ partial, int nblk, float max_norm,
                                            float* __restrict__ stats) {
+  pdl_enter();
   // single block; fixed-order strided accumulation in double, then a fixed tree
   __shared__ double red[3][256];
   double a0 = 0, a1 = 0, a2 = 0;
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(256) sgd_momentum_kernel(float* __restrict__ p
                                                            int64_t numel, float lr, float mu,
                                                            float wd, int first,
                                                            const float* __restrict__ stats) {
+  pdl_enter();
   const float coef = stats ? stats[1] : 1.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -179,10 +182,10 @@ extern "C" int gdl_grad_stats(const float* grad, int64_t numel, const int64_t* s
   GDL_REQUIRE(grad && seg_end && seg_group && seg_inv_numel && scratch && stats_out, "gdl_grad_stats: null pointer");
   GDL_REQUIRE(numel > 0 && nseg > 0, "gdl_grad_stats: bad shape");
   int nblk = (int)ceil_div64(numel, kChunk);
-  grad_stats_kernel<<<nblk, kOptThreads, 0, (cudaStream_t)s>>>(grad, numel, seg_end, seg_group,
+  launch_pdl(grad_stats_kernel, nblk, kOptThreads, 0, (cudaStream_t)s, grad, numel, seg_end, seg_group,
                                                               seg_inv_numel, nseg, scratch);
   GDL_CHECK_LAUNCH("grad_stats_kernel");
-  grad_stats_finalize_kernel<<<1, 256, 0, (cudaStream_t)s>>>(scratch, nblk, max_norm, stats_out);
+  launch_pdl(grad_stats_finalize_kernel, 1, 256, 0, (cudaStream_t)s, scratch, nblk, max_norm, stats_out);
   GDL_CHECK_LAUNCH("grad_stats_finalize_kernel");
   return GDL_OK;
 }
@@ -196,7 +199,7 @@ extern "C" int gdl_sgd_momentum(float* param, float* grad, float* momentum_buf, 
   int64_t n4 = numel / 4;
   int64_t blocks = ceil_div64(n4 > 0 ? n4 : 1, 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  sgd_momentum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(param, grad, momentum_buf, n4, numel,
+  launch_pdl(sgd_momentum_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)s, param, grad, momentum_buf, n4, numel,
                                                                     lr, mu, wd, first_step, stats);
   GDL_CHECK_LAUNCH("sgd_momentum_kernel");
   return GDL_OK;

@@ -3,12 +3,21 @@
 // (pointer, geometry, box) so that a CUDA-graph-captured step never re-encodes a descriptor.
 #include <mutex>
 #include <unordered_map>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "tma.cuh"
 
 namespace gdl {
 using namespace tc05;
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("GDL_PDL");
+    return e ? atoi(e) != 0 : false;
+  }();
+  return on;
+}
 
 // ------------------------------------------------------------------------------------------
 // tensor-map cache
