@@ -93,7 +93,12 @@ class ResNet(nn.Module):
                 raise RuntimeError("gdl_b200.ResNet runs on a B200 only (no CPU fallback); "
                                    "move the model to cuda first")
             eng = EncoderEngine(self, N, H, W, dev)
-            self._engines = {key: eng}  # one live geometry: activation arenas are large
+            # two live geometries (the full batch and an epoch's short tail batch): activation arenas are large
+            if len(self._engines) >= 2:
+                self._engines.pop(next(iter(self._engines)))
+        else:
+            self._engines.pop(key)
+        self._engines[key] = eng  # most recently used last
         return eng
 
     def forward(self, x):

@@ -94,6 +94,16 @@ class ParamArena:
         self.seg_inv = torch.tensor(seg_inv, device=device, dtype=torch.float32)
         self.scratch = torch.empty(ops.optim_scratch_floats(off, self.nseg), device=device)
 
+    def owns(self, model, device):
+        """True while every parameter of `model` still is the view into this arena that __init__ made (a
+        `model.to(...)`, `load_state_dict(assign=True)` or a changed trainable set breaks that)."""
+        groups = head_trainable(model.fusion_module) + list(model.audio_net.parameters()) + \
+            list(model.visual_net.parameters())
+        if self.param.device != device or len(groups) != len(self.params):
+            return False
+        base = self.param.data_ptr()
+        return all(p is q and p.data.data_ptr() == base + 4 * o for p, q, o in zip(groups, self.params, self.offsets))
+
     def late_split(self, gid, late_params):
         """Offset where the `late_params` of group gid start, checked to be exactly the tail of the group
         (module registration order: conv1, bn1, layer1 .. layer4)."""
@@ -133,7 +143,13 @@ class DGLStep:
         self.use_graph = use_graph
         B, T = self.B, self.T
 
-        self.arena = ParamArena(model, dev)
+        # ONE arena per model: a second DGLStep of another batch geometry (an epoch's short tail batch) shares the
+        # parameters, gradients and momentum of the first instead of re-allocating and copying them
+        arena = getattr(model, "_gdl_arena", None)
+        if arena is None or not arena.owns(model, dev):
+            arena = ParamArena(model, dev)
+            model._gdl_arena = arena
+        self.arena = arena
         if check_fp32 is None:
             check_fp32 = os.environ.get("GDL_CHECK_FP32", "0") != "0"
         self.check_fp32 = bool(check_fp32)
@@ -340,6 +356,14 @@ class DGLStep:
             self.film.refresh()
         self.stats[0:3].copy_(self.losses)
         torch._foreach_add_(self._bn_counters, 1)
+
+    def refresh_shadows(self):
+        """Re-derive the bf16 weight shadows of this step's engines from the fp32 parameters (after ANOTHER step of
+        the same model — a different batch geometry — or a load_state_dict changed them)."""
+        self.enc_a.repack()
+        self.enc_v.repack()
+        if self.film is not None:
+            self.film.refresh()
 
     def load_inputs(self, spec, image, label):
         """Copy a batch (host or device tensors of the reference contract) into the current staging set,

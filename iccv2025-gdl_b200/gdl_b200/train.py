@@ -36,16 +36,33 @@ def _get_step(args, model, optimizer, spec, image, pipeline=None, audio_pipeline
     thw = (pipeline.T, pipeline.S, pipeline.S) if pipeline is not None else tuple(image.shape[2:])
     spec_hw = (audio_pipeline.F, audio_pipeline.frames) if audio_pipeline is not None else tuple(spec.shape[1:])
     key = (B, spec_hw, thw)
-    st = getattr(inner, "_gdl_step", None)
-    if st is not None and getattr(inner, "_gdl_step_key", None) == key:
+    # per-geometry cache (two entries: the full batch and an epoch's short tail batch when the loader does not drop it).
+    # The steps share ONE parameter / gradient / momentum arena (DGLStep), so switching costs a weight-shadow refresh,
+    # not a re-allocation, a momentum copy and a graph re-capture.
+    steps = getattr(inner, "_gdl_steps", None)
+    if steps is None:
+        steps = inner._gdl_steps = {}
+    last = getattr(inner, "_gdl_step_key", None)
+    st = steps.get(key)
+    if st is not None:
+        if last != key:
+            st.refresh_shadows()
+            st.momentum_loaded = True  # the momentum arena is live: never torch's first-step `buf = g` again
+        inner._gdl_step, inner._gdl_step_key = st, key
         return st
     g = optimizer.param_groups[0]
     world = torch.distributed.get_world_size() if torch.distributed.is_available() and \
         torch.distributed.is_initialized() else 1
+    trained = any(s.steps_done > 0 for s in steps.values())
     st = DGLStep(inner, B, spec_hw, thw, alpha=args.alpha, lr=g['lr'],
                  momentum=g.get('momentum', 0.9), weight_decay=g.get('weight_decay', 1e-4), max_norm=40.0,
                  world_size=world, process_group=torch.distributed.group.WORLD if world > 1 else None)
     adopt_momentum(st.arena, optimizer, st)
+    if trained:
+        st.momentum_loaded = True
+    if len(steps) >= 2:
+        steps.pop(next(k for k in steps if k != last))
+    steps[key] = st
     inner._gdl_step, inner._gdl_step_key = st, key
     return st
 

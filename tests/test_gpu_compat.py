@@ -173,6 +173,63 @@ def test_train_epoch_over_a_pinning_dataloader_with_graph_capture(tmp_path):
     assert model._gdl_step._graph is not None           # the captured path really ran
 
 
+def test_train_epoch_with_a_short_tail_batch_shares_one_arena(tmp_path):
+    """A loader WITHOUT drop_last (the train_epoch drop-in contract allows it): every epoch ends with a short batch.
+    The two batch geometries get one cached DGLStep each (graphs, engines), both on ONE parameter / gradient /
+    momentum arena — switching refreshes the weight shadows, nothing is re-allocated — and the run tracks the fp32
+    oracle stepping through the same 4, 4, 2 | 4, 4, 2 sequence with one momentum state."""
+    from torch.utils.data import DataLoader, Dataset
+    from gdl_b200.train import train_epoch
+    from oracle import dgl_oracle as O
+    from oracle.synth import make_batch
+
+    items = [make_batch(1, 6, "tiny", seed=300 + i) for i in range(10)]
+
+    class DS(Dataset):
+        def __len__(self):
+            return len(items)
+
+        def __getitem__(self, i):
+            spec, image, label = items[i]
+            return spec[0], image[0], label[0]
+
+    args, model = make_model("concat")
+    dp = _Wrap(model)
+    opt = torch.optim.SGD(dp.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    loader = DataLoader(DS(), batch_size=4, shuffle=False, num_workers=0, pin_memory=True, drop_last=False)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for epoch in range(2):
+            res = train_epoch(args, epoch, dp, torch.device("cuda"), loader, opt, None)
+    finally:
+        os.chdir(cwd)
+    torch.cuda.synchronize()
+    steps = model._gdl_steps
+    assert sorted(k[0] for k in steps) == [2, 4]
+    a, b = steps.values()
+    assert a.arena is b.arena and model._gdl_arena is a.arena
+    assert a.steps_done + b.steps_done == 6
+    for p in dp.parameters():  # the optimizer's momentum buffers alias the shared arena
+        if p in opt.state:
+            o = a.arena.offset_of[id(p)]
+            assert opt.state[p]["momentum_buffer"].data_ptr() == a.arena.momentum.data_ptr() + 4 * o
+    # oracle: same sequence, one state dict, one momentum dict
+    sd, mom, last = O.init_state("concat", "CREMAD", 0), {}, None
+    for epoch in range(2):
+        tot, n = [0.0, 0.0, 0.0], 0
+        for lo in (0, 4, 8):
+            chunk = items[lo:lo + 4]
+            batch = [torch.cat([c[j] for c in chunk]) for j in range(3)]
+            r = O.dgl_step(sd, mom, *batch, fusion="concat", alpha=args.alpha, lr=0.01)
+            tot = [t + float(x) for t, x in zip(tot, r["losses"])]
+            n += 1
+        last = [t / n for t in tot]
+    print("tail-batch run: epoch-2 mean losses %s vs oracle %s" % (list(res[:3]), last))
+    for g, r in zip(res[:3], last):
+        assert abs(g - r) <= 5e-2 * abs(r), (res[:3], last)
+
+
 def test_valid_with_folded_batchnorm_on_a_64_sample_test_set(tmp_path):
     """SURVEY.md §8f rank 1 (reference valid(), main_dgl.py:168-222): eval-mode forward with BatchNorm folded into
     the packed conv weights (one fused conv kernel per unit, no BN pass) on a 64-sample synthetic test set after a
