@@ -12,7 +12,9 @@ weights, bf16 activations, fp32 accumulation.  Per-GPU batch is fixed (weak scal
 Prints ONE JSON line (rank 0).  `value`: inputs already resident in HBM; `e2e`: the same step
 through the public DGLStep.prefetch()/step()/read_stats() API with every step's pinned-host inputs
 copied H2D (on a copy stream, overlapping the previous step) and the 7-float result read D2H inside
-the timed region.  `roofline`: the dominant kernel class (implicit-GEMM convolutions),
+the timed region (at N > 1 the leg whose frames come from a uint8 store resident in HBM and are cropped / resized on
+the device — N host copies of 512 MB per step share one host — with the host-frames leg next to it as
+`e2e_host_frames`; at N = 1 the other way round, `e2e_device_pipeline`).  `roofline`: the dominant kernel class (implicit-GEMM convolutions),
 algorithmic FLOPs / CUDA-event time measured in an instrumented pass after the timed region.
 `cpu_baseline`: the CPU oracle port timed on this box's host cores on a bounded sample.
 """
@@ -341,8 +343,16 @@ def run_gpu(a):
             "clocks": clocks,
             "final_losses": {"Lf": stats[0], "La": stats[1], "Lv": stats[2]},
             "wall_ms_per_step": wall_ms / a.steps}
+    line["e2e"]["path"] = "fp32 frames + spectrograms from pinned host memory (DGLStep.prefetch / step / read_stats)"
     if dp is not None:
-        line["e2e_device_pipeline"] = dp
+        dp["path"] = "uint8 frame store in HBM, crop boxes + spectrograms from pinned host memory (prefetch(pipeline=))"
+        if world > 1:
+            # N > 1: N copies of 512 MB per step share one host; the data-parallel entry point (main_dgl.py
+            # --audio_path synthetic_device) keeps the decoded frames on the GPUs, so that is the
+            # end-to-end path reported as `e2e`; the host-frames leg stays next to it
+            line["e2e_host_frames"], line["e2e"] = line["e2e"], dp
+        else:
+            line["e2e_device_pipeline"] = dp
 
     if not a.no_roofline:
         # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports it
