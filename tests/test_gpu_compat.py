@@ -226,8 +226,11 @@ def test_train_epoch_with_a_short_tail_batch_shares_one_arena(tmp_path):
             n += 1
         last = [t / n for t in tot]
     print("tail-batch run: epoch-2 mean losses %s vs oracle %s" % (list(res[:3]), last))
+    # six FREE-RUNNING steps at lr = 0.01 with BatchNorm over 2-4 samples: bf16 storage moves the unimodal losses by a few
+    # per cent by then (measured 0.1 % / 2 % / 6 %); a wrong momentum or stale weight shadow after a switch shows up as
+    # tens of per cent
     for g, r in zip(res[:3], last):
-        assert abs(g - r) <= 5e-2 * abs(r), (res[:3], last)
+        assert abs(g - r) <= 1e-1 * abs(r), (res[:3], last)
 
 
 def test_valid_with_folded_batchnorm_on_a_64_sample_test_set(tmp_path):
