@@ -26,4 +26,27 @@ for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_kernels.py -q -m gpu --no-header -p no:cacheprovider -x -k "$SAN_K" > gpurun_out/sanitizer_${tool}_r2.log 2>&1
   echo "== compute-sanitizer $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/sanitizer_${tool}_r2.log | tail -3
 done
+# BASELINE config 2: the other three heads at batch 256, and the stock-PyTorch (cuDNN / cuBLAS) side bar
+for f in concat sum gated film; do
+  timeout 300 python bench.py --fusion $f --steps 10 --warmup 3 --no-cpu --no-device-pipeline --no-roofline > gpurun_out/r2_variant_$f.log 2>&1
+  echo "== bench $f exit $?"
+done
+timeout 600 python bench.py --impl cudnn_sidebar --steps 5 --warmup 3 > gpurun_out/r2_variant_sidebar.log 2>&1
+echo "== cudnn sidebar exit $?"
+python - <<'PY'
+import json
+out = {"what": "bench.py --fusion F --steps 10 --warmup 3 (batch 256, CREMA-D shape, one B200, same box) and --impl cudnn_sidebar"}
+for f in ("concat", "sum", "gated", "film", "sidebar"):
+    try:
+        line = [l for l in open("gpurun_out/r2_variant_%s.log" % f) if l.startswith("{")][-1]
+        d = json.loads(line)
+        out[f] = {k: d[k] for k in ("value", "ms_per_step", "unit") if k in d}
+        if "e2e" in d: out[f]["e2e"] = d["e2e"]["value"]
+        if "launches_per_step" in d: out[f]["launches_per_step"] = d["launches_per_step"]
+        if "modes" in d: out[f]["modes"] = d["modes"]
+    except Exception as e:
+        out[f] = {"error": str(e)}
+json.dump(out, open("gpurun_out/r2_variants.json", "w"), indent=1)
+print(json.dumps(out)[:900])
+PY
 ls -la gpurun_out/*r2* | head -30

@@ -7,6 +7,7 @@ mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 nvidia-smi --query-gpu=index,name --format=csv,noheader > $OUT/gpus.txt; nproc >> $OUT/gpus.txt; free -g | head -2 >> $OUT/gpus.txt
 
+if [ -z "$R2_DIST_ONLY_SCALING" ]; then
 # 1. N-rank DGLStep == the oracle's N-shard simulation of nn.DataParallel (bf16 product path, then FP32 check mode)
 timeout 400 $TR --nproc-per-node $N --master-port 29541 tests/dist_step_check.py > $OUT/dist_step_check.log 2>&1
 echo "== dist_step_check N=$N exit $?"; grep -E "vs the|dist step|DIST_STEP|Error|assert" $OUT/dist_step_check.log | cut -c1-300 | tail -12
@@ -26,10 +27,11 @@ if [ -n "$BEST" ]; then
   ls -la $CK | tail -5 > $OUT/ckpt_listing.txt; rm -f $CK/*.pth
 fi
 
+fi
 # 3. fixed global batch (BASELINE configs 3-4): N ranks, then the smaller rank counts side by side on disjoint GPUs
 bench() {  # dataset G ranks gpus port
   CUDA_VISIBLE_DEVICES=$4 timeout 400 $TR --nproc-per-node $3 --master-port $5 bench.py --gpus $3 --dataset $1 --global-batch $2 \
-      --steps 10 --warmup 3 --no-cpu --no-device-pipeline --no-roofline > $OUT/strong_$1_G$2_n$3.log 2>&1
+      --steps 10 --warmup 3 --no-cpu --no-roofline > $OUT/strong_$1_G$2_n$3.log 2>&1
 }
 ALL=$(seq -s, 0 $((N-1)))
 for cfg in "VGGSound 1024" "KineticSound 512"; do
@@ -47,7 +49,7 @@ for cfg in "VGGSound 1024" "KineticSound 512"; do
     grep '^{"metric"' $f | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
-print('   %s G=%d N=%d: %.0f samples/s, %.3f ms/step, e2e %.0f (%s)' % ('$1', $2, d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['scaling']))
+print('   %s G=%d N=%d: %.0f samples/s, %.3f ms/step, e2e %.0f%s (%s)' % ('$1', $2, d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], (' [host frames %.0f]' % d['e2e_host_frames']['value']) if 'e2e_host_frames' in d else '', d['scaling']))
 " || echo "   $f: no result"
   done
 done

@@ -16,6 +16,9 @@ for f in sorted(glob.glob(os.path.join(sys.argv[1], "strong_*_n*.log"))):
     out.setdefault(key, {})[int(m.group(3))] = {"samples_per_s": round(d["value"], 1), "ms_per_step": round(d["ms_per_step"], 3),
                                                "e2e_samples_per_s": round(d["e2e"]["value"], 1),
                                                "per_gpu_batch": d["config"]["global_batch"] // d["n_gpus"],
+                                               "e2e_path": d["e2e"].get("path"),
+                                               "e2e_host_frames_samples_per_s": round(d["e2e_host_frames"]["value"], 1)
+                                               if "e2e_host_frames" in d else None,
                                                "clocks": d.get("clocks")}
 for key, rows in out.items():
     if 1 in rows:
