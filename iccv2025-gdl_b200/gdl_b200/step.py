@@ -187,7 +187,11 @@ class DGLStep:
         self._bn_counters = [m.num_batches_tracked for m in model.modules()
                              if isinstance(m, torch.nn.BatchNorm2d)]
         self._init_head()
-        self.stream_a, self.stream_v = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        # GDL_STREAM_PRIO: 0 = equal priorities, 1 = the visual encoder's stream (the long chain: 3x the audio work) is
+        # high priority so its kernels' CTAs are placed first and the audio kernels fill the gaps, 2 = the reverse
+        prio = int(os.environ.get("GDL_STREAM_PRIO", "1"))  # measured: 20.40 / 20.09 ms vs 20.48 / 20.40 ms per step, e2e +1.7 %
+        self.stream_a = torch.cuda.Stream(dev, priority=-1 if prio == 2 else 0)
+        self.stream_v = torch.cuda.Stream(dev, priority=-1 if prio == 1 else 0)
         self.steps_done = 0
         self.momentum_loaded = False  # set by train.adopt_momentum when a checkpoint's buffers were copied in
         self._graph = None
