@@ -784,7 +784,7 @@ __device__ __forceinline__ void tail_row_keys(const uint4& u, const float (&sc)[
 __global__ void __launch_bounds__(256, 3) bn_relu_maxpool_fwd3_kernel(
     const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
     bf16* __restrict__ y, uint8_t* __restrict__ amax, bf16* __restrict__ xmax, int N, int H, int W, int C, int Ho,
-    int Wo, int nseg, int rev) {
+    int Wo, int nseg, int seglen, int rev) {
   pdl_enter();
   __shared__ int s_tapoff[16];  // element offset of tap (r,s) from the window's top-left pixel
   if (threadIdx.x < 9) s_tapoff[threadIdx.x] = ((threadIdx.x / 3) * W + threadIdx.x % 3) * C;
@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(256, 3) bn_relu_maxpool_fwd3_kernel(
         for (int c = 0; c < 8; ++c) hm[c] = max(hm[c], k[c]);
       }
     };
-    const int ho0 = seg * kTailSeg, ho1 = min(ho0 + kTailSeg, Ho);
+    const int ho0 = seg * seglen, ho1 = min(ho0 + seglen, Ho);
     uint32_t carry[8];
     uint32_t carry_tag = 0u;  // 6 once the carried row exists (it is row r = 0 of the next window)
     if (ho0 > 0) {
@@ -1225,10 +1225,14 @@ extern "C" int gdl_bn_relu_maxpool_fwd(const void* x, const float* scale, const 
     return e ? atoi(e) : 3;
   }();
   if (variant >= 3 && (int64_t)N * H * W * C < ((int64_t)1 << 31)) {  // 32-bit indexing inside the kernel
-    const int nseg = (Ho + kTailSeg - 1) / kTailSeg;
+    static const int seglen = []() {
+      const char* e = getenv("GDL_STEM_TAIL_SEG");
+      return e && atoi(e) > 0 ? atoi(e) : kTailSeg;
+    }();
+    const int nseg = (Ho + seglen - 1) / seglen;
     int64_t total3 = (int64_t)N * nseg * Wo * (C / 8);
     launch_pdl(bn_relu_maxpool_fwd3_kernel, ew_grid(total3, 256, GDL_RESIDENT(bn_relu_maxpool_fwd3_kernel, 256)), 256, 0, (cudaStream_t)s, (const bf16*)x, scale, shift, (bf16*)y, argmax, (bf16*)xmax, N, H,
-                                                     W, C, Ho, Wo, nseg, g_sweep_rev);
+                                                     W, C, Ho, Wo, nseg, seglen, g_sweep_rev);
     GDL_CHECK_LAUNCH("bn_relu_maxpool_fwd3_kernel");
     return GDL_OK;
   }
