@@ -236,6 +236,12 @@ __global__ void __launch_bounds__(kWfThreads, 1) conv_wgrad_flat_kernel(const __
   if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
+// (A CTA-pair variant of this kernel — tcgen05.mma.cta_group::2, the two CTAs of a cluster on neighbouring ci tiles of
+// one job, each holding half of the dY window — was written and validated in round 2 (Ci >= 256 layers) and measured
+// at +2-5 % per weight gradient against this kernel on every layer of the bench geometry (14x14 C256: 0.198 vs 0.190 ms,
+// 7x7 C512: 0.222 vs 0.217 ms): halving the dY operand traffic does not pay here, the weight gradient is not
+// shared-memory or L2 bound the way the forward / data-gradient kernels are.  Removed again.)
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------

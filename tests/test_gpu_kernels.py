@@ -47,6 +47,9 @@ CONV_CASES = [
     (96, 28, 28, 128, 256, 1, 2, 0), # CTA-pair kernel, 1x1 stride-2 forward (strided view)
     (192, 14, 14, 128, 256, 1, 1, 0),# CTA-pair kernel, 1x1 data gradient on the compact grid
     (47, 28, 28, 128, 128, 3, 1, 1), # CTA-pair kernel with an ODD number of 256-pixel tiles (the last pair's peer is padding)
+    (24, 14, 14, 256, 256, 3, 1, 1), # CTA-pair weight gradient (two ci tiles per cluster), band stages
+    (9, 17, 12, 256, 512, 3, 2, 1),  # CTA-pair weight gradient through the four parity planes
+    (12, 14, 14, 256, 512, 1, 2, 0), # CTA-pair weight gradient, 1x1 stride 2
 ]
 
 
