@@ -32,6 +32,7 @@ USE_WGRAD_STREAM = os.environ.get("GDL_WGRAD_STREAM", "0") != "0"
 #      reduce descending after the (ascending) dgrad, apply ascending
 #   2  the convolutions alternate as well (conv1 of a block descending, conv2 ascending, BN passes in between)
 SWEEP = int(os.environ.get("GDL_SWEEP", "1"))
+APPLY_SWEEP = int(os.environ.get("GDL_APPLY_SWEEP", "1"))
 STEM_STATS = int(os.environ.get("GDL_STEM_STATS", "1"))  # BatchNorm statistics of the stem from its epilogue
 
 
@@ -100,7 +101,10 @@ class _ConvBN:
             ops.bn_stats(self.x, self.P, self.C, eng.bn_partial, bn.weight.data, bn.bias.data, bn.eps,
                          bn.momentum, bn.running_mean, bn.running_var, self.mean, self.invstd,
                          self.scale, self.shift)
-        ops.sweep(c)
+        # with the statistics out of the conv epilogue the apply pass is the FIRST pass over x after the convolution: it
+        # walks against the convolution's direction (starts on the tail that is still in L2) and leaves the head of y,
+        # where the next convolution starts, in L2.  GDL_APPLY_SWEEP=0: the round-1 order (same direction).
+        ops.sweep(((not c) if (rows and APPLY_SWEEP and SWEEP) else c))
         ops.bn_apply(self.x, res, self.y, self.P, self.C, self.scale, self.shift, self.relu)
         return self.y
 
