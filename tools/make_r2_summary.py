@@ -31,7 +31,14 @@ for name, (n, t, b, ls) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     big = sorted(ls, key=lambda x: -x[1])[:3]
     hbm.append("| `%s` | %d | %.3f | %.2f | %.0f | %s |" % (name[:60], n, t / 1e6, b / 1e9, b / t if t else 0,
                                                      ", ".join("%.0f" % (bb / tt) for tt, bb in big)))
-full = run("tools/ncu_table.py", "gpurun_out/prof_final_r2.ncu-rep") if os.path.exists(os.path.join(G, "prof_final_r2.ncu-rep")) else "(capture not present)"
+fullp = os.path.join(P, "r2_full_audio_bwd.md")
+if os.path.exists(os.path.join(G, "prof_final_r2.ncu-rep")):
+    open(fullp, "w").write(run("tools/ncu_table.py", "gpurun_out/prof_final_r2.ncu-rep"))
+full = open(fullp).read() if os.path.exists(fullp) else "(capture not present)"
+visp = os.path.join(P, "r2_full_visual_bwd.md")
+if os.path.exists(os.path.join(G, "prof_flat2_visual_r2.ncu-rep")):
+    open(visp, "w").write(run("tools/ncu_table.py", "gpurun_out/prof_flat2_visual_r2.ncu-rep"))
+vis = open(visp).read() if os.path.exists(visp) else "(capture not present)"
 
 open(os.path.join(P, "r2_ncu_summary.md"), "w").write("""# Round 2 — ncu evidence (B200, batch 256 CREMA-D shape, eager step; `tools/profile_r2_final.sh` under gpurun)
 
@@ -65,5 +72,11 @@ average down; the three largest launches of each kernel show what the kernel rea
 ## 4. `--set full` captures (24 launches of the audio encoder's backward; `gpurun_out/prof_final_r2.ncu-rep`, scratch)
 
 %s
-""" % (launch, traffic, "\n".join(hbm), full))
+## 5. `--set full` capture of 20 CTA-pair convolution launches at the end of the audio and the start of the VISUAL backward
+(`-k regex:conv_flat2_kernel -s 196 -c 20`).  The 137-158 us launches are the data gradients of the visual layer4 / layer3
+(7x7 C512, 14x14 C256): **tensor pipe 86-92 %% active**; `<64, 2, 8, 0, 1>` are the 64-channel layers with resident weights
+(audio 65x47 maps here: 39-51 %%, shared-memory-bandwidth bound).
+
+%s
+""" % (launch, traffic, "\n".join(hbm), full, vis))
 print("wrote profiles/r2_ncu_summary.md")
